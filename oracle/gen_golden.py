@@ -1,0 +1,162 @@
+"""Mint the golden fixtures under tests/golden/ by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (needs /root/reference):   python -m oracle.gen_golden
+Inputs are regenerated from seeds by havatar_b200/synth.py, so each fixture stores reference
+OUTPUTS only (+ the case parameters).  tests/test_oracle_golden.py checks oracle/ against them;
+the gpu tests check the CUDA path against them too.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+from havatar_b200 import synth  # noqa: E402
+
+# case name -> parameters.  `crop` = (y0, x0, h, w) window of a 512x512 frame.
+RENDER_CASES = {
+    # BASELINE.json configs[0] scaled to fixture size: 32x32 crop, 32 samples, coarse only
+    "render_c32_s32": dict(batch=1, crop=(240, 240, 32, 32), num_coarse=32, num_fine=0, rand=False, seed=0),
+    # hierarchical 64 + 16 (-> 48 fine samples), deterministic (perturb off), B=2
+    "render_hier_det": dict(batch=2, crop=(200, 260, 16, 16), num_coarse=64, num_fine=16, rand=False, seed=10),
+    # train-mode randoms supplied explicitly: perturb + sigma noise 0.1 + stratified sample_pdf
+    "render_hier_rand": dict(batch=1, crop=(300, 180, 16, 16), num_coarse=64, num_fine=16, rand=True, seed=20),
+    # non-square planes / non-cubic volume pin the axis conventions; window at the frame corner leaves the box
+    "render_oddshape": dict(batch=1, crop=(0, 0, 8, 16), num_coarse=16, num_fine=0, rand=False, seed=30,
+                            plane_hw=(24, 40), vol_dhw=(6, 10, 14)),
+}
+
+
+def _reference_render(trainer, torch, case):
+    sc = synth.scene(batch=case["batch"], crop=case["crop"], seed=case["seed"],
+                     plane_hw=case.get("plane_hw", (128, 128)), vol_dhw=case.get("vol_dhw", (64, 64, 64)))
+    B, R = sc["ray_batch"].shape[:2]
+    mc = trainer.model_coarse
+    sd = {k: torch.from_numpy(v) for k, v in sc["weights"].items()}
+    mc.load_state_dict(sd, strict=False)
+    mc.triPlane_embeddings = torch.from_numpy(sc["planes"])
+    hs = trainer.headpose_skin_net
+    hs.fix_canoW = True
+    hs.canonical_W = torch.from_numpy(sc["wvol"])
+    opt = trainer.cfg.nerf.train
+    opt.num_coarse, opt.num_fine = case["num_coarse"], case["num_fine"]
+    opt.perturb = bool(case["rand"])
+    opt.radiance_field_noise_std = 0.1 if case["rand"] else 0.0
+
+    rays = torch.from_numpy(sc["ray_batch"])
+    viewdirs = rays[..., 3:6] / rays[..., 3:6].norm(p=2, dim=-1).unsqueeze(-1)   # nerf_trainer.py:52
+    rays11 = torch.cat((rays, viewdirs), dim=-1)                                  # nerf_trainer.py:63
+
+    orig_rand, orig_randn = torch.rand, torch.randn
+    if case["rand"]:
+        rnd = synth.randoms(B, R, case["num_coarse"], case["num_fine"], seed=case["seed"] + 7)
+        q_rand = [rnd["t_rand"], rnd["u_rand"].reshape(B * R, -1)]
+        q_randn = [rnd["unit_coarse"].reshape(B * R, -1), rnd["unit_fine"].reshape(B * R, -1)]
+
+        def fake_rand(shape, *a, **k):
+            v = q_rand.pop(0)
+            assert tuple(shape) == v.shape, (tuple(shape), v.shape)
+            return torch.from_numpy(v.copy())
+
+        def fake_randn(shape, *a, **k):
+            v = q_randn.pop(0)
+            assert tuple(shape) == v.shape, (tuple(shape), v.shape)
+            return torch.from_numpy(v.copy())
+
+        torch.rand, torch.randn = fake_rand, fake_randn
+    try:
+        with torch.no_grad():
+            out = trainer.predict_and_render_radiance("train", rays11, torch.from_numpy(sc["background_prior"]),
+                                                      inv_head_T=torch.from_numpy(sc["inv_head_T"]))
+    finally:
+        torch.rand, torch.randn = orig_rand, orig_randn
+    names = ["rgb_coarse", "depth_coarse", "acc_coarse", "weights_max", "rgb_fine", "depth_fine", "acc_fine"]
+    return {n: o.numpy() for n, o in zip(names, out) if o is not None}
+
+
+def gen_render(trainer, torch):
+    for name, case in RENDER_CASES.items():
+        out = _reference_render(trainer, torch, case)
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), case=json.dumps(case), **out)
+        print(name, {k: v.shape for k, v in out.items()}, "acc mean %.4f" % out["acc_coarse"].mean())
+
+
+def gen_stages(torch):
+    """Stage-level goldens straight from the reference functions (no Trainer needed)."""
+    from model.network.embedder import get_embedder
+    from utils import nerf_util
+    from utils.util import sample_from_triplane_new, voxel_feature
+    from dataloader import data_util
+
+    rs = np.random.RandomState(100)
+    out = {}
+    # positional encoding (embedder.py:32-61) on canonical-space magnitudes
+    x = rs.uniform(-1.7, 1.7, size=(257, 3)).astype(np.float32)
+    emb, dim = get_embedder(multires=8, input_dims=3, include_input=False)
+    out["pe_x"], out["pe_y"] = x, emb(torch.from_numpy(x)).numpy()
+    # bi-plane fetch incl. out-of-range coordinates (zeros padding)
+    pl = rs.standard_normal((2, 1, 5, 7, 9)).astype(np.float32)
+    q = rs.uniform(-1.3, 1.3, size=(1, 300, 3)).astype(np.float32)
+    out["tp_planes"], out["tp_q"] = pl, q
+    out["tp_y"] = sample_from_triplane_new(torch.from_numpy(q), torch.from_numpy(pl)).numpy()
+    # trilinear border fetch
+    vol = rs.uniform(0, 1, size=(1, 1, 4, 5, 6)).astype(np.float32)
+    out["vx_vol"], out["vx_q"] = vol, q
+    out["vx_y"] = voxel_feature(torch.from_numpy(q), torch.from_numpy(vol)).numpy()
+    # sample_pdf, both modes
+    bins = np.sort(rs.uniform(2.4, 5.0, size=(64, 63)).astype(np.float32), axis=-1)
+    wts = rs.uniform(0, 1, size=(64, 62)).astype(np.float32) ** 4
+    wts[:4] = 0.0                                      # all-zero weights: uniform pdf from the 1e-5 floor
+    out["pdf_bins"], out["pdf_w"] = bins, wts
+    out["pdf_det"] = nerf_util.sample_pdf(torch.from_numpy(bins), torch.from_numpy(wts), 16, det=True).numpy()
+    u = rs.uniform(0, 1, size=(64, 16)).astype(np.float32)
+    orig = torch.rand
+    torch.rand = lambda shape, *a, **k: torch.from_numpy(u.copy())
+    try:
+        out["pdf_rand"] = nerf_util.sample_pdf(torch.from_numpy(bins), torch.from_numpy(wts), 16, det=False).numpy()
+    finally:
+        torch.rand = orig
+    out["pdf_u"] = u
+    # composite
+    rf = rs.standard_normal((33, 17, 68)).astype(np.float32)
+    z = np.sort(rs.uniform(2.4, 5.0, size=(33, 17)).astype(np.float32), axis=-1)
+    rd = rs.standard_normal((33, 3)).astype(np.float32)
+    bg = rs.uniform(0, 1, size=(33, 3)).astype(np.float32)
+    res = nerf_util.volume_render_radiance_field(torch.from_numpy(rf.copy()), torch.from_numpy(z), torch.from_numpy(rd),
+                                                 background_prior=torch.from_numpy(bg), act_feat=False)
+    out["cmp_rf"], out["cmp_z"], out["cmp_rd"], out["cmp_bg"] = rf, z, rd, bg
+    for n, r in zip(("rgb", "disp", "acc", "w", "depth"), res):
+        out["cmp_" + n] = r.numpy()
+    # ray generation (data_util.py:28-56)
+    intr = np.array([700.0, 690.0, 0.49, 0.52], dtype=np.float32)
+    c2w = np.array([[0.96, 0.05, -0.27, 0.3], [0.0, -0.98, -0.19, 0.1], [-0.28, 0.18, -0.94, 3.9]], dtype=np.float32)
+    o, d = data_util.get_rays(6, 8, intr, torch.from_numpy(c2w))
+    out["ray_intr"], out["ray_c2w"] = intr, c2w
+    out["ray_o"], out["ray_d"] = o.reshape(-1, 3).numpy().copy(), d.reshape(-1, 3).numpy()
+    np.savez_compressed(os.path.join(GOLD, "stages.npz"), **out)
+    print("stages", sorted(out))
+
+
+def main():
+    from oracle import ref_shim
+
+    cfg = ref_shim.load_cfg()
+    import torch
+
+    torch.manual_seed(0)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    os.makedirs(GOLD, exist_ok=True)
+    gen_stages(torch)
+    from model.nerf_trainer import Trainer
+
+    trainer = Trainer(cfg, 4)
+    gen_render(trainer, torch)
+
+
+if __name__ == "__main__":
+    main()
