@@ -1,0 +1,85 @@
+"""ctypes binding of libhavatar_b200.so (C ABI: include/havatar_b200.h).
+
+There is no CPU fallback: lib() raises if the library is missing or stale symbols are found, and
+every op in this package goes through it.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhavatar_b200.so")
+
+HAV_ABI_VERSION = 1
+PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16}
+
+_fp = C.c_void_p  # device pointers travel as integers
+
+
+class RenderArgs(C.Structure):
+    """hav_render_args (include/havatar_b200.h) -- field order and types must match the header."""
+    _fields_ = [
+        ("struct_bytes", C.c_uint32), ("precision", C.c_int32), ("batch", C.c_int32), ("rays", C.c_int32),
+        ("num_coarse", C.c_int32), ("num_fine", C.c_int32), ("plane_c", C.c_int32),
+        ("plane_h", C.c_int32), ("plane_w", C.c_int32),
+        ("vol_d", C.c_int32), ("vol_h", C.c_int32), ("vol_w", C.c_int32), ("flags", C.c_int32),
+        ("plane_scale", C.c_float * 3), ("plane_trans", C.c_float * 3),
+        ("skin_scale", C.c_float * 3), ("skin_trans", C.c_float * 3),
+        ("ray_batch", _fp), ("background", _fp), ("inv_head_T", _fp), ("planes", _fp), ("wvol", _fp),
+        ("w0", _fp), ("b0", _fp), ("w1", _fp), ("b1", _fp), ("w_alpha", _fp), ("b_alpha", _fp),
+        ("w_feat", _fp), ("b_feat", _fp), ("w_rgb", _fp), ("b_rgb", _fp),
+        ("t_rand", _fp), ("noise_coarse", _fp), ("u_rand", _fp), ("noise_fine", _fp),
+        ("rgb_coarse", _fp), ("depth_coarse", _fp), ("acc_coarse", _fp), ("weights_max", _fp),
+        ("rgb_fine", _fp), ("depth_fine", _fp), ("acc_fine", _fp), ("z_fine", _fp),
+        ("workspace", _fp), ("workspace_bytes", C.c_uint64),
+    ]
+
+
+# symbol -> (restype, argtypes); tests check that every one of these is exported
+SIGNATURES = {
+    "hav_abi_version": (C.c_int, []),
+    "hav_error_string": (C.c_char_p, [C.c_int]),
+    "hav_fused_bias_act": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                     C.c_float, C.c_float, _fp]),
+    "hav_upfirdn2d": (C.c_int, [_fp, _fp, _fp] + [C.c_int] * 14 + [_fp]),
+    "hav_render_workspace_bytes": (C.c_uint64, [C.POINTER(RenderArgs)]),
+    "hav_render_forward": (C.c_int, [C.POINTER(RenderArgs), _fp]),
+    "hav_get_rays": (C.c_int, [_fp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
+                               C.c_float, _fp]),
+}
+
+_lib = None
+
+
+class HavError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises HavError when the CUDA library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HavError(
+            "libhavatar_b200.so is not built (%s). Run `python -m havatar_b200.build` (needs nvcc); "
+            "havatar_b200 has no CPU fallback." % LIB_PATH)
+    h = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(h, name)
+        except AttributeError as e:
+            raise HavError("libhavatar_b200.so does not export %s -- rebuild it" % name) from e
+        fn.restype, fn.argtypes = res, args
+    if h.hav_abi_version() != HAV_ABI_VERSION:
+        raise HavError("libhavatar_b200.so ABI %d != binding ABI %d -- rebuild it" % (h.hav_abi_version(), HAV_ABI_VERSION))
+    _lib = h
+    return h
+
+
+def check(rc, what):
+    """Turn a C-ABI return code into a RuntimeError (the reference raises RuntimeError via TORCH_CHECK,
+    model/op/fused_bias_act.cpp:10-16)."""
+    if rc != 0:
+        msg = lib().hav_error_string(int(rc)).decode()
+        raise HavError("%s failed: %s (code %d)" % (what, msg, rc))

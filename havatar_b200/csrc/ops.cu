@@ -1,0 +1,237 @@
+// HBM-bound element-wise / FIR operators behind the reference's `model/op` extension boundary,
+// plus ray generation.  See include/havatar_b200.h for the contracts and reference citations.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/havatar_b200.h"
+
+namespace hav {
+
+constexpr int kSMs = 148;  // B200: grids are sized in multiples of the SM count
+
+// ------------------------------------------------------------------------------------------------
+// fused bias + activation  (model/op/fused_bias_act_kernel.cu:18-65)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bias_act_one(float x, float ref, int mode, float alpha, float scale) {
+  float y;
+  switch (mode) {
+    case 30: y = (x > 0.0f) ? x : x * alpha; break;
+    case 31: y = (ref > 0.0f) ? x : x * alpha; break;
+    case 12:
+    case 32: y = 0.0f; break;
+    default: y = x; break;  // 10, 11 and anything else: linear (kernel.cu:41-49)
+  }
+  return y * scale;
+}
+
+// Vector path: 4 consecutive elements share one bias channel when step_b % 4 == 0.
+__global__ void __launch_bounds__(256) bias_act_vec4_kernel(float4 *__restrict__ out, const float4 *__restrict__ x,
+                                                            const float *__restrict__ bias,
+                                                            const float4 *__restrict__ ref, int64_t n4, int64_t step_b4,
+                                                            int64_t size_b, int mode, float alpha, float scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = __ldcs(x + i);
+    if (bias != nullptr) {
+      float b = __ldg(bias + (i / step_b4) % size_b);
+      v.x += b, v.y += b, v.z += b, v.w += b;
+    }
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ref != nullptr) r = __ldcs(ref + i);
+    float4 y;
+    y.x = bias_act_one(v.x, r.x, mode, alpha, scale);
+    y.y = bias_act_one(v.y, r.y, mode, alpha, scale);
+    y.z = bias_act_one(v.z, r.z, mode, alpha, scale);
+    y.w = bias_act_one(v.w, r.w, mode, alpha, scale);
+    out[i] = y;
+  }
+}
+
+__global__ void __launch_bounds__(256) bias_act_scalar_kernel(float *__restrict__ out, const float *__restrict__ x,
+                                                              const float *__restrict__ bias,
+                                                              const float *__restrict__ ref, int64_t n, int64_t step_b,
+                                                              int64_t size_b, int mode, float alpha, float scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (bias != nullptr) v += __ldg(bias + (i / step_b) % size_b);
+    float r = ref != nullptr ? ref[i] : 0.0f;
+    out[i] = bias_act_one(v, r, mode, alpha, scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// upfirdn2d  (model/op/upfirdn2d_kernel.cu:49-207; executable spec model/op/upfirdn2d.py:172-213)
+//   out[oy,ox] = sum_{ky,kx} U[oy*dy + ky - py0, ox*dx + kx - px0] * K[kh-1-ky, kw-1-kx]
+//   U[Y,X] = x[Y/uy, X/ux] when Y%uy == 0 && X%ux == 0 and inside the input, else 0.
+// One CTA computes a 32x64 output tile of one (major, minor) image from an input window staged in
+// shared memory, so every input element is read from HBM/L2 once per tile.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileH = 32, kTileW = 64;
+constexpr int kMaxTaps = 24;  // per dimension
+
+struct UfdParams {
+  int in_h, in_w, minor, out_h, out_w, kh, kw;
+  int up_x, up_y, down_x, down_y, pad_x0, pad_y0;
+  int win_h, win_w;  // smem window size (input coords)
+};
+
+__device__ __forceinline__ int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+__device__ __forceinline__ int ceil_div(int a, int b) { return -floor_div(-a, b); }
+
+__global__ void __launch_bounds__(256) upfirdn2d_kernel(float *__restrict__ out, const float *__restrict__ x,
+                                                        const float *__restrict__ kernel, UfdParams p, int tiles_x) {
+  extern __shared__ float sm[];
+  float *sk = sm;                          // flipped kernel [kh][kw]
+  float *sw = sm + kMaxTaps * kMaxTaps;    // input window [win_h][win_w]
+  const int img = blockIdx.y;              // major * minor + m
+  const int major_i = img / p.minor, m = img % p.minor;
+  const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x % tiles_x;
+  const int oy0 = tile_y * kTileH, ox0 = tile_x * kTileW;
+  for (int i = threadIdx.x; i < p.kh * p.kw; i += blockDim.x) {
+    int ky = i / p.kw, kx = i % p.kw;
+    sk[i] = __ldg(kernel + (p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx));
+  }
+  // first input row/col any output of this tile can touch: ceil((o0*d - pad) / up)
+  const int iy0 = ceil_div(oy0 * p.down_y - p.pad_y0, p.up_y);
+  const int ix0 = ceil_div(ox0 * p.down_x - p.pad_x0, p.up_x);
+  const float *xin = x + (size_t)major_i * p.in_h * p.in_w * p.minor + m;
+  for (int i = threadIdx.x; i < p.win_h * p.win_w; i += blockDim.x) {
+    int wy = i / p.win_w, wx = i % p.win_w;
+    int iy = iy0 + wy, ix = ix0 + wx;
+    float v = 0.0f;
+    if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) v = __ldg(xin + ((size_t)iy * p.in_w + ix) * p.minor);
+    sw[i] = v;
+  }
+  __syncthreads();
+  float *oimg = out + (size_t)major_i * p.out_h * p.out_w * p.minor + m;
+  for (int i = threadIdx.x; i < kTileH * kTileW; i += blockDim.x) {
+    int oy = oy0 + i / kTileW, ox = ox0 + i % kTileW;
+    if (oy >= p.out_h || ox >= p.out_w) continue;
+    const int Y0 = oy * p.down_y - p.pad_y0, X0 = ox * p.down_x - p.pad_x0;
+    // first tap with (Y0 + ky) % up == 0
+    int ky_first = ((-Y0) % p.up_y + p.up_y) % p.up_y;
+    int kx_first = ((-X0) % p.up_x + p.up_x) % p.up_x;
+    float acc = 0.0f;
+    for (int ky = ky_first; ky < p.kh; ky += p.up_y) {
+      const int wy = (Y0 + ky) / p.up_y - iy0;  // exact: Y0 + ky is a multiple of up_y
+      if (wy < 0 || wy >= p.win_h) continue;
+      for (int kx = kx_first; kx < p.kw; kx += p.up_x) {
+        const int wx = (X0 + kx) / p.up_x - ix0;
+        if (wx < 0 || wx >= p.win_w) continue;
+        acc = fmaf(sw[wy * p.win_w + wx], sk[ky * p.kw + kx], acc);
+      }
+    }
+    oimg[((size_t)oy * p.out_w + ox) * p.minor] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ray generation (dataloader/data_util.py:28-56)
+// ------------------------------------------------------------------------------------------------
+struct RayGen {
+  float kinv[9], rot[9], org[3], near, far;
+  int H, W;
+};
+__global__ void __launch_bounds__(256) get_rays_kernel(float *__restrict__ rays, RayGen g) {
+  const int n = g.H * g.W;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const float i = (float)(r % g.W), j = (float)(r / g.W);  // pixel (x=i, y=j): dataloader/dataloader.py:72
+    float c[3], d[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) c[a] = g.kinv[a * 3] * i + g.kinv[a * 3 + 1] * j + g.kinv[a * 3 + 2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) d[a] = g.rot[a * 3] * c[0] + g.rot[a * 3 + 1] * c[1] + g.rot[a * 3 + 2] * c[2];
+    float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    float4 *o = reinterpret_cast<float4 *>(rays + (size_t)r * 8);
+    o[0] = make_float4(g.org[0], g.org[1], g.org[2], d[0] / nrm);
+    o[1] = make_float4(d[1] / nrm, d[2] / nrm, g.near, g.far);
+  }
+}
+
+}  // namespace hav
+
+using namespace hav;
+
+extern "C" int hav_fused_bias_act(float *out, const float *x, const float *bias, const float *ref, int64_t numel,
+                                  int64_t step_b, int64_t size_b, int act, int grad, float alpha, float scale,
+                                  void *stream) {
+  if (numel < 0) return HAV_E_SHAPE;
+  if (numel == 0) return HAV_OK;
+  if (out == nullptr || x == nullptr) return HAV_E_NULL;
+  if (bias != nullptr && (step_b < 1 || size_b < 1)) return HAV_E_SHAPE;
+  const int mode = act * 10 + grad;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (numel % 4 == 0) && (bias == nullptr || step_b % 4 == 0) &&
+                   (((uintptr_t)out | (uintptr_t)x | (uintptr_t)ref) & 15) == 0;
+  if (vec) {
+    int64_t n4 = numel / 4;
+    int64_t want = (n4 + 255) / 256;
+    int grid = (int)(want < (int64_t)kSMs * 16 ? want : (int64_t)kSMs * 16);
+    bias_act_vec4_kernel<<<grid, 256, 0, st>>>((float4 *)out, (const float4 *)x, bias, (const float4 *)ref, n4,
+                                               bias != nullptr ? step_b / 4 : 1, bias != nullptr ? size_b : 1, mode,
+                                               alpha, scale);
+  } else {
+    int64_t want = (numel + 255) / 256;
+    int grid = (int)(want < (int64_t)kSMs * 16 ? want : (int64_t)kSMs * 16);
+    bias_act_scalar_kernel<<<grid, 256, 0, st>>>(out, x, bias, ref, numel, bias != nullptr ? step_b : 1,
+                                                 bias != nullptr ? size_b : 1, mode, alpha, scale);
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? HAV_OK : (int)e;
+}
+
+extern "C" int hav_upfirdn2d(float *out, const float *x, const float *kernel, int major, int in_h, int in_w,
+                             int minor, int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0,
+                             int pad_x1, int pad_y0, int pad_y1, void *stream) {
+  if (major < 0 || in_h < 1 || in_w < 1 || minor < 1 || kh < 1 || kw < 1) return HAV_E_SHAPE;
+  if (up_x < 1 || up_y < 1 || down_x < 1 || down_y < 1) return HAV_E_SHAPE;
+  if (kh > kMaxTaps || kw > kMaxTaps) return HAV_E_SHAPE;
+  const int out_h = (in_h * up_y + pad_y0 + pad_y1 - kh + down_y) / down_y;  // upfirdn2d_kernel.cu:236-241
+  const int out_w = (in_w * up_x + pad_x0 + pad_x1 - kw + down_x) / down_x;
+  if (out_h < 1 || out_w < 1) return HAV_E_SHAPE;
+  if (major == 0) return HAV_OK;
+  if (out == nullptr || x == nullptr || kernel == nullptr) return HAV_E_NULL;
+  if ((int64_t)major * minor > 65535 && minor != 1) return HAV_E_SHAPE;  // gridDim.y chunking needs minor == 1
+  UfdParams p;
+  p.in_h = in_h, p.in_w = in_w, p.minor = minor, p.out_h = out_h, p.out_w = out_w, p.kh = kh, p.kw = kw;
+  p.up_x = up_x, p.up_y = up_y, p.down_x = down_x, p.down_y = down_y, p.pad_x0 = pad_x0, p.pad_y0 = pad_y0;
+  p.win_h = ((kTileH - 1) * down_y + kh - 1) / up_y + 2;
+  p.win_w = ((kTileW - 1) * down_x + kw - 1) / up_x + 2;
+  const size_t smem = (size_t)(kMaxTaps * kMaxTaps + p.win_h * p.win_w) * sizeof(float);
+  if (smem > 200 * 1024) return HAV_E_SHAPE;
+  cudaError_t e = cudaFuncSetAttribute(upfirdn2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int tiles_x = (out_w + kTileW - 1) / kTileW, tiles_y = (out_h + kTileH - 1) / kTileH;
+  const int64_t imgs = (int64_t)major * minor;
+  // gridDim.y is limited to 65535: loop over image chunks
+  for (int64_t i0 = 0; i0 < imgs; i0 += 65535) {
+    int ny = (int)((imgs - i0) < 65535 ? (imgs - i0) : 65535);
+    dim3 grid(tiles_x * tiles_y, ny);
+    upfirdn2d_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(out + (size_t)i0 * out_h * out_w,
+                                                                 x + (size_t)i0 * in_h * in_w, kernel, p, tiles_x);
+  }
+  e = cudaGetLastError();
+  return e == cudaSuccess ? HAV_OK : (int)e;
+}
+
+extern "C" int hav_get_rays(float *ray_batch, int height, int width, const float intr[4], const float c2w[12],
+                            float near, float far, void *stream) {
+  if (height < 1 || width < 1 || (int64_t)height * width > (int64_t)1 << 30) return HAV_E_SHAPE;
+  if (ray_batch == nullptr || intr == nullptr || c2w == nullptr) return HAV_E_NULL;
+  if (intr[0] == 0.0f || intr[1] == 0.0f) return HAV_E_VALUE;
+  RayGen g;
+  // K = [[fx,0,cx*W],[0,fy,cy*H],[0,0,1]] (data_util.py:38-39); closed-form inverse
+  const float fx = intr[0], fy = intr[1], cx = intr[2] * (float)width, cy = intr[3] * (float)height;
+  const float kinv[9] = {1.0f / fx, 0.0f, -cx / fx, 0.0f, 1.0f / fy, -cy / fy, 0.0f, 0.0f, 1.0f};
+  for (int i = 0; i < 9; ++i) g.kinv[i] = kinv[i];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) g.rot[r * 3 + c] = c2w[r * 4 + c];
+    g.org[r] = c2w[r * 4 + 3];
+  }
+  g.near = near, g.far = far, g.H = height, g.W = width;
+  const int n = height * width;
+  int grid = (n + 255) / 256;
+  if (grid > kSMs * 8) grid = kSMs * 8;
+  get_rays_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ray_batch, g);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? HAV_OK : (int)e;
+}

@@ -1,0 +1,33 @@
+// Internal (non-ABI) declarations shared by the render translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/havatar_b200.h"
+
+namespace hav {
+
+struct RenderDev;
+
+// ---- fp32 packed-weight blob (float offsets), built by pack_mlp_fp32_kernel ----
+constexpr int kOffW0t = 0;                       // [176][128]
+constexpr int kOffW1t = kOffW0t + 176 * 128;     // [128][128]
+constexpr int kOffWht = kOffW1t + 128 * 128;     // [128][68]
+constexpr int kOffB0 = kOffWht + 128 * 68;       // [128]
+constexpr int kOffB1 = kOffB0 + 128;             // [128]
+constexpr int kOffBh = kOffB1 + 128;             // [68]
+constexpr int kOffWr = kOffBh + 68;              // [3][64]
+constexpr int kOffBr = kOffWr + 192;             // [3] (+1 pad)
+constexpr int kPackF32Floats = kOffBr + 4;
+
+void launch_pack_mlp_fp32(const hav_render_args *a, float *out, cudaStream_t st);
+cudaError_t launch_render_fp32(const RenderDev &P, int num_blocks, cudaStream_t st);
+
+// ---- bf16 tcgen05 path (render_tc.cu) ----
+uint64_t tc_weight_image_bytes();
+void launch_pack_mlp_bf16(const hav_render_args *a, uint8_t *wimg, cudaStream_t st);
+void launch_pack_planes_bf16(const float *planes, uint16_t *out, int nplanes_b, int C, int H, int W, cudaStream_t st);
+cudaError_t launch_render_bf16(const RenderDev &P, int num_ray_blocks, cudaStream_t st);
+int tc_num_ctas(int num_ray_blocks);
+
+}  // namespace hav

@@ -1,0 +1,156 @@
+"""Host side of the fused volumetric render: torch tensors in, one C-ABI call, torch tensors out.
+
+`render_rays` is Trainer.predict_and_render_radiance (reference model/nerf_trainer.py:120-201) over the
+whole ray batch in ONE kernel launch -- the reference's 4096-ray chunk loop (nerf_trainer.py:65-71)
+only exists to bound the per-sample tensors it materialises in HBM; the fused kernel has none.
+PyTorch is used for device memory and streams only.  No CPU fallback: CPU tensors raise.
+"""
+import ctypes as C
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+RenderOut = namedtuple("RenderOut", "rgb_coarse depth_coarse acc_coarse weights_max rgb_fine depth_fine acc_fine z_fine")
+
+MLP_KEYS = ("layers_xyz.0.weight", "layers_xyz.0.bias", "layers_xyz.1.weight", "layers_xyz.1.bias",
+            "fc_alpha.weight", "fc_alpha.bias", "fc_rgbFeat.weight", "fc_rgbFeat.bias", "fc_rgb.weight", "fc_rgb.bias")
+_MLP_FIELDS = ("w0", "b0", "w1", "b1", "w_alpha", "b_alpha", "w_feat", "b_feat", "w_rgb", "b_rgb")
+_MLP_SHAPES = ((128, 176), (128,), (128, 128), (128,), (1, 128), (1,), (64, 128), (64,), (3, 64), (3,))
+
+_workspaces = {}  # (device index, stream) -> uint8 tensor, grown on demand
+
+
+def box_warp_param(xb, yb, zb):
+    """reference utils/util.py:179-186 get_box_warp_param -> (scales, trans)."""
+    out_s, out_t = [], []
+    for lo, hi in (xb, yb, zb):
+        f = 2.0 / (hi - lo)
+        out_s.append(f)
+        out_t.append(-(f * (lo + hi) * 0.5))
+    return tuple(out_s), tuple(out_t)
+
+
+def default_boxes(xyz_bounding=((-1.5, 1.5), (-1.6, 1.4), (-1.6, 1.2))):
+    """(plane_scale, plane_trans, skin_scale, skin_trans): plane box = models.coarse.XYZ_bounding
+    (reference config/singleview_512_base.yml:51), skin box = same with Y[0] = 0.3*Y[1] (nerf_trainer.py:29-34)."""
+    xb, yb, zb = [tuple(float(v) for v in b) for b in xyz_bounding]
+    ps, pt = box_warp_param(xb, yb, zb)
+    ss, st = box_warp_param(xb, (0.3 * yb[1], yb[1]), zb)
+    return ps, pt, ss, st
+
+
+def _f32c(t, name, shape=None):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.HavError("%s must be a CUDA tensor (havatar_b200 has no CPU path)" % name)
+    if t.dtype != torch.float32:
+        raise _lib.HavError("%s must be float32, got %s" % (name, t.dtype))
+    t = t.detach()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise _lib.HavError("%s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
+    return t
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _workspace(device, nbytes):
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, num_coarse, num_fine=0,
+                boxes=None, t_rand=None, noise_coarse=None, u_rand=None, noise_fine=None, precision="fp16",
+                want_z_fine=False):
+    """ray_batch [B,R,8] (o3 d3 near far; extra trailing columns such as the reference's viewdirs are
+    ignored), background_prior [B,R,3] or None, inv_head_T [B,4,3], planes [2,B,64,H,W], wvol [1,2,D,H,W],
+    weights: mapping with the reference's model_coarse keys (MLP_KEYS).  Random draws are explicit inputs
+    (SURVEY.md section 8a quirk v): t_rand [B,R,Sc], noise_* [B,R,S] already scaled by the noise std,
+    u_rand [B,R,num_fine]; None switches that randomness off (u_rand None == sample_pdf det=True).
+    Returns RenderOut of [B,R,*] tensors (fine slots None when num_fine == 0)."""
+    L = _lib.lib()
+    if ray_batch.dim() != 3 or ray_batch.shape[-1] < 8:
+        raise _lib.HavError("ray_batch must be [B,R,>=8]")
+    if ray_batch.shape[-1] > 8:
+        ray_batch = ray_batch[..., :8]
+    ray_batch = _f32c(ray_batch, "ray_batch")
+    dev = ray_batch.device
+    B, R = int(ray_batch.shape[0]), int(ray_batch.shape[1])
+    planes = _f32c(planes, "planes")
+    if planes.dim() != 5 or planes.shape[0] != 2 or planes.shape[1] != B:
+        raise _lib.HavError("planes must be [2,B,C,H,W] with B == ray_batch.shape[0]")
+    wvol = _f32c(wvol, "wvol")
+    if wvol.dim() != 5 or wvol.shape[0] != 1 or wvol.shape[1] != 2:
+        raise _lib.HavError("wvol must be [1,2,D,H,W]")
+    Sf = (num_coarse + 1) // 2 + num_fine if num_fine > 0 else 0
+    a = _lib.RenderArgs()
+    a.struct_bytes = C.sizeof(_lib.RenderArgs)
+    a.precision = _lib.PRECISIONS[precision]
+    a.batch, a.rays, a.num_coarse, a.num_fine = B, R, int(num_coarse), int(num_fine)
+    a.plane_c, a.plane_h, a.plane_w = int(planes.shape[2]), int(planes.shape[3]), int(planes.shape[4])
+    a.vol_d, a.vol_h, a.vol_w = int(wvol.shape[2]), int(wvol.shape[3]), int(wvol.shape[4])
+    ps, pt, ss, st = boxes if boxes is not None else default_boxes()
+    for i in range(3):
+        a.plane_scale[i], a.plane_trans[i] = float(ps[i]), float(pt[i])
+        a.skin_scale[i], a.skin_trans[i] = float(ss[i]), float(st[i])
+    keep = [ray_batch, planes, wvol]
+    a.ray_batch, a.planes, a.wvol = _ptr(ray_batch), _ptr(planes), _ptr(wvol)
+    bg = _f32c(background_prior, "background_prior", (B, R, 3))
+    ihT = _f32c(inv_head_T, "inv_head_T", (B, 4, 3))
+    a.background, a.inv_head_T = _ptr(bg), _ptr(ihT)
+    keep += [bg, ihT]
+    for key, field, shape in zip(MLP_KEYS, _MLP_FIELDS, _MLP_SHAPES):
+        w = _f32c(weights[key], key, shape)
+        keep.append(w)
+        setattr(a, field, _ptr(w))
+    for name, t, shape in (("t_rand", t_rand, (B, R, num_coarse)), ("noise_coarse", noise_coarse, (B, R, num_coarse)),
+                           ("u_rand", u_rand, (B, R, num_fine)), ("noise_fine", noise_fine, (B, R, Sf))):
+        t = _f32c(t, name, shape)
+        keep.append(t)
+        setattr(a, name, _ptr(t))
+    new = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    out = dict(rgb_coarse=new(B, R, 67), depth_coarse=new(B, R, 1), acc_coarse=new(B, R, 1), weights_max=new(B, R, 1),
+               rgb_fine=None, depth_fine=None, acc_fine=None, z_fine=None)
+    if num_fine > 0:
+        out.update(rgb_fine=new(B, R, 67), depth_fine=new(B, R, 1), acc_fine=new(B, R, 1))
+        if want_z_fine:
+            out["z_fine"] = new(B, R, Sf)
+    for k, v in out.items():
+        setattr(a, k, _ptr(v))
+    with torch.cuda.device(dev):
+        need = int(L.hav_render_workspace_bytes(C.byref(a)))
+        if need == 0 and B * R > 0:
+            # re-run the checks through the real entry point to get the specific error code
+            _lib.check(L.hav_render_forward(C.byref(a), None) or -2, "hav_render_forward")
+        ws = _workspace(dev, need)
+        a.workspace, a.workspace_bytes = C.c_void_p(ws.data_ptr()), ws.numel()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(L.hav_render_forward(C.byref(a), C.c_void_p(stream)), "hav_render_forward")
+    del keep
+    return RenderOut(**out)
+
+
+def get_rays(height, width, intr, c2w, near, far, device="cuda"):
+    """Ray generation on the device (reference dataloader/data_util.py:28-56 + dataloader.py:174-180):
+    intr = (fx, fy, cx, cy), c2w [3,4] (or [4,4]) array-like on the host.  -> ray_batch [H*W, 8]."""
+    L = _lib.lib()
+    dev = torch.device(device)
+    out = torch.empty((height * width, 8), dtype=torch.float32, device=dev)
+    intr_c = (C.c_float * 4)(*[float(v) for v in np.asarray(intr, dtype=np.float32).reshape(-1)[:4]])
+    c2w_c = (C.c_float * 12)(*[float(v) for v in np.asarray(c2w, dtype=np.float32)[:3, :4].reshape(-1)])
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(L.hav_get_rays(_ptr(out), int(height), int(width), intr_c, c2w_c, float(near), float(far),
+                                  C.c_void_p(stream)), "hav_get_rays")
+    return out

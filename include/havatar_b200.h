@@ -1,0 +1,138 @@
+/*
+ * havatar_b200 -- C ABI of the B200-native (sm_100a) HAvatar render hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry point
+ *   - takes DEVICE pointers to contiguous float32 tensors in the reference's own layouts,
+ *   - never allocates (the caller passes outputs and, where needed, a workspace),
+ *   - launches asynchronously on the CUDA stream passed as `stream` (a cudaStream_t cast to void*;
+ *     NULL = legacy default stream) on the current device, and is re-entrant,
+ *   - returns 0 on success, a negative HAV_E_* code for an argument error, or a positive
+ *     cudaError_t when the launch failed.  No exception crosses the boundary.
+ *
+ * Reference interfaces replaced (paths relative to the XChenZ/havatar tree):
+ *   hav_fused_bias_act   <- model/op/fused_bias_act.cpp:18-32   (pybind module `fused`)
+ *   hav_upfirdn2d        <- model/op/upfirdn2d.cpp:17-31        (pybind module `upfirdn2d`)
+ *   hav_render_forward   <- model/nerf_trainer.py:120-201       (Trainer.predict_and_render_radiance; the
+ *                            reference has no native boundary here -- it is ~140 ATen launches per chunk)
+ *   hav_get_rays         <- dataloader/data_util.py:28-56 + dataloader/dataloader.py:174-180
+ *   hav_pack_planes      <- model/nerf_model.py:85 (plane stacking; layout change for the bf16 path)
+ * INTEGRATION.md shows the reference-side binding for each.
+ */
+#ifndef HAVATAR_B200_H_
+#define HAVATAR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HAV_ABI_VERSION 1
+
+/* argument errors (negative); positive return values are cudaError_t */
+#define HAV_OK 0
+#define HAV_E_NULL (-1)       /* a required pointer is NULL */
+#define HAV_E_SHAPE (-2)      /* unsupported or inconsistent sizes */
+#define HAV_E_WORKSPACE (-3)  /* workspace too small (see hav_render_workspace_bytes) */
+#define HAV_E_ARCH (-4)       /* device is not sm_100 */
+#define HAV_E_VALUE (-5)      /* bad enum / flag value */
+
+/* arithmetic of the MLP inside hav_render_forward */
+#define HAV_PREC_FP32 0 /* CUDA-core fp32 everywhere: reference-exact mode (1e-5 class parity) */
+#define HAV_PREC_BF16 1 /* tcgen05 bf16 operands, fp32 accumulate in TMEM (fast path, fp32 exponent range) */
+#define HAV_PREC_FP16 2 /* tcgen05 fp16 operands (saturating converts), fp32 accumulate: fast path, 8x finer rounding */
+
+int hav_abi_version(void);
+const char *hav_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------------
+ * fused bias + activation.  Replaces fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)
+ * (model/op/fused_bias_act.cpp:18-32, kernel model/op/fused_bias_act_kernel.cu:18-65).
+ *   y[i] = f(x[i] + bias[(i / step_b) % size_b]) * scale,   selected by act*10+grad:
+ *     30: leaky-relu(alpha) fwd   31: its gradient gated by sign(ref[i])   32: 0
+ *     10/11: linear               12: 0
+ *   bias == NULL <=> "empty bias tensor"; ref == NULL <=> "empty refer tensor" (kernel.cu:79-80).
+ *   step_b = product of dims after the channel dim (kernel.cu:86-88), size_b = channels.
+ */
+int hav_fused_bias_act(float *out, const float *x, const float *bias, const float *ref, int64_t numel,
+                       int64_t step_b, int64_t size_b, int act, int grad, float alpha, float scale,
+                       void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * upfirdn2d.  Replaces upfirdn2d.upfirdn2d(input[major,in_h,in_w,minor], kernel[kh,kw], up_x, up_y,
+ * down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1) (model/op/upfirdn2d.cpp:17-31, kernels
+ * model/op/upfirdn2d_kernel.cu:49-207): zero-insert upsample, pad (negative = crop), correlate with
+ * the FLIPPED kernel, decimate.  out is [major, out_h, out_w, minor] with
+ *   out_h = (in_h*up_y + pad_y0 + pad_y1 - kh + down_y) / down_y   (kernel.cu:236-241), same for w.
+ */
+int hav_upfirdn2d(float *out, const float *x, const float *kernel, int major, int in_h, int in_w,
+                  int minor, int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0,
+                  int pad_x1, int pad_y0, int pad_y1, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused volumetric render: per-ray depth sampling -> 2-bone skinning warp -> bi-plane bilinear fetch
+ * -> positional encoding -> 5-linear MLP -> alpha composite (-> sample_pdf -> second pass).
+ * One call == Trainer.predict_and_render_radiance over ALL B*R rays (model/nerf_trainer.py:120-201);
+ * the reference's 4096-ray python chunk loop (nerf_trainer.py:65-71) is not needed because no
+ * per-sample tensor ever reaches HBM.
+ */
+typedef struct hav_render_args {
+  uint32_t struct_bytes; /* = sizeof(hav_render_args): ABI guard */
+  int32_t precision;     /* HAV_PREC_* */
+  int32_t batch;         /* B */
+  int32_t rays;          /* R rays per batch element */
+  int32_t num_coarse;    /* S_c: nerf.<mode>.num_coarse (2..256) */
+  int32_t num_fine;      /* nerf.<mode>.num_fine; 0 = coarse only; fine pass has (S_c+1)/2 + num_fine samples */
+  int32_t plane_c;       /* feature channels per plane (64) */
+  int32_t plane_h, plane_w;
+  int32_t vol_d, vol_h, vol_w;
+  int32_t flags;         /* reserved, 0 */
+  float plane_scale[3], plane_trans[3]; /* model_coarse.gridwarper (utils/util.py:214-236) */
+  float skin_scale[3], skin_trans[3];   /* headpose_skin_net.gridwarper (model/nerf_trainer.py:29-34) */
+
+  /* inputs, float32, reference layouts */
+  const float *ray_batch;   /* [B,R,8]  o3 d3 near far   (dataloader/dataloader.py:179-180) */
+  const float *background;  /* [B,R,3]  or NULL          (utils/nerf_util.py:70-71) */
+  const float *inv_head_T;  /* [B,4,3]  rows 0-2 R^-1, row 3 -t (dataloader/dataloader.py:215-216) */
+  const float *planes;      /* [2,B,C,H,W] NCHW          (model/nerf_model.py:85) */
+  const float *wvol;        /* [1,2,D,H,W] skinning weights (model/Skinning_Field.py:79) */
+  const float *w0, *b0;     /* layers_xyz.0  [128,176],[128]  (model/nerf_model.py:46) */
+  const float *w1, *b1;     /* layers_xyz.1  [128,128],[128] */
+  const float *w_alpha, *b_alpha; /* fc_alpha   [1,128],[1] */
+  const float *w_feat, *b_feat;   /* fc_rgbFeat [64,128],[64] */
+  const float *w_rgb, *b_rgb;     /* fc_rgb     [3,64],[3] */
+
+  /* the reference's random draws as explicit inputs (all optional; NULL = that randomness is off) */
+  const float *t_rand;       /* [B,R,S_c] U[0,1): stratified jitter (model/nerf_trainer.py:132-139) */
+  const float *noise_coarse; /* [B,R,S_c] N(0,1)*std: sigma noise (utils/nerf_util.py:47-57) */
+  const float *u_rand;       /* [B,R,num_fine] U[0,1): sample_pdf jitter (utils/nerf_util.py:93-96); NULL = det */
+  const float *noise_fine;   /* [B,R,S_f] */
+
+  /* outputs, float32 (fine outputs may be NULL when num_fine == 0) */
+  float *rgb_coarse;   /* [B,R,67]  rgb3 | feature64 */
+  float *depth_coarse; /* [B,R] */
+  float *acc_coarse;   /* [B,R] */
+  float *weights_max;  /* [B,R]  max_s w of the LAST pass (model/nerf_trainer.py:195,200) */
+  float *rgb_fine, *depth_fine, *acc_fine;
+  float *z_fine;       /* optional [B,R,S_f]: merged+sorted fine depths (debug / tests), or NULL */
+
+  void *workspace;          /* >= hav_render_workspace_bytes(args) bytes, 256-byte aligned */
+  uint64_t workspace_bytes;
+} hav_render_args;
+
+uint64_t hav_render_workspace_bytes(const hav_render_args *args);
+int hav_render_forward(const hav_render_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ray generation (dataloader/data_util.py:28-56 get_rays + near/far of dataloader/dataloader.py:174-180).
+ * intr = {fx, fy, cx, cy} (focal in pixels, principal point as a fraction of the image size);
+ * c2w = row-major [3,4].  Writes ray_batch [H*W, 8] = o3 d3 near far, ray r <-> pixel (r / W, r % W).
+ */
+int hav_get_rays(float *ray_batch, int height, int width, const float intr[4], const float c2w[12],
+                 float near, float far, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAVATAR_B200_H_ */

@@ -182,7 +182,7 @@ def sample_pdf(bins, weights, num_samples, u_rand=None):
         u = np.broadcast_to(np.linspace(0.0, 1.0, num_samples).astype(F32), (R, num_samples))  # :87-91
     else:
         s = 1 / num_samples
-        u = (np.arange(num_samples) * s).astype(F32)[None, :]                      # :93-94
+        u = (np.arange(num_samples).astype(F32) * F32(s))[None, :]                      # :93-94
         u = (u + u_rand.astype(F32) * F32(s - 1e-6)).astype(F32)                   # :95
     inds = np.empty((R, num_samples), dtype=np.int64)
     for r in range(R):
