@@ -34,7 +34,7 @@ struct RenderDev {
   // bf16 path: pre-swizzled UMMA smem image of the weights + channels-last bf16 planes
   const uint8_t *wimg;
   const uint16_t *planes_cl;  // [2,B,H,W,64] bf16
-  // per-block scratch in the workspace: [num_blocks][kMaxSamples][128] each
+  // per-block scratch in the workspace: zbuf [num_blocks][Sf][128], wbuf [num_blocks][Sc][128]
   float *zbuf, *wbuf;
 };
 
@@ -69,7 +69,8 @@ __device__ __forceinline__ float linspace01(int s, int S) {
 // model/nerf_trainer.py:129-139: coarse depth of sample s (stratified jitter when t_rand != NULL).
 __device__ __forceinline__ float coarse_z_plain(const Ray &r, int s, int S) {
   float t = linspace01(s, S);
-  return r.near * (1.0f - t) + r.far * t;
+  // separately rounded products, then one add -- what the ATen elementwise kernels produce (no FMA contraction)
+  return __fadd_rn(__fmul_rn(r.near, 1.0f - t), __fmul_rn(r.far, t));
 }
 __device__ __forceinline__ float coarse_z(const RenderDev &P, const Ray &r, int g, int s) {
   float z = coarse_z_plain(r, s, P.Sc);
@@ -79,7 +80,7 @@ __device__ __forceinline__ float coarse_z(const RenderDev &P, const Ray &r, int 
   float lower = (s > 0) ? 0.5f * (z + zl) : z;
   float upper = (s < P.Sc - 1) ? 0.5f * (zu + z) : z;
   float tr = __ldg(P.t_rand + (size_t)g * P.Sc + s);
-  return lower + (upper - lower) * tr;
+  return __fadd_rn(lower, __fmul_rn(upper - lower, tr));
 }
 
 // align_corners=True un-normalisation of ATen grid_sampler: ((x + 1) / 2) * (size - 1)
@@ -206,7 +207,7 @@ __device__ __forceinline__ void sample_pdf_merge(ZFn zc, int Sc, int nfine, floa
       u = (nfine == 1) ? 0.0f : linspace01(k, nfine);
     } else {
       // (arange(n) * s) + rand * (s - 1e-6) (:93-95); s is a python double there
-      u = (float)k * (float)(1.0 / (double)nfine) + u_rand[k] * (float)(1.0 / (double)nfine - 1e-6);
+      u = __fadd_rn(__fmul_rn((float)k, (float)(1.0 / (double)nfine)), __fmul_rn(u_rand[k], (float)(1.0 / (double)nfine - 1e-6)));
     }
     // inds = searchsorted(cdf, u, right=True): first index with cdf[i] > u, M if none (:102)
     int lo = 0, hi = M;
@@ -220,7 +221,7 @@ __device__ __forceinline__ void sample_pdf_merge(ZFn zc, int Sc, int nfine, floa
     float denom = c1 - c0;
     denom = (denom < 1e-5f) ? 1.0f : denom;                                          // :112-113
     float t = (u - c0) / denom;
-    zs[k] = b0 + t * (b1 - b0);                                                      // :114-115
+    zs[k] = __fadd_rn(b0, __fmul_rn(t, b1 - b0));                                                      // :114-115
   }
   // torch.sort semantics even if rounding ever produced an inversion: insertion sort (normally a no-op)
   for (int k = 1; k < nfine; ++k) {

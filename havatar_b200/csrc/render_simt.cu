@@ -78,8 +78,8 @@ __global__ void __launch_bounds__(kRaysPerBlock, 1) render_fp32_kernel(const Ren
   const size_t plane_sz = (size_t)P.PH * P.PW;
   const float *pl0 = P.planes + ((size_t)0 * P.B + ray.b) * kPlaneC * plane_sz;  // XY plane of this frame
   const float *pl1 = P.planes + ((size_t)1 * P.B + ray.b) * kPlaneC * plane_sz;  // ZY plane
-  float *zcol = P.zbuf + (size_t)blockIdx.x * kMaxSamples * kRaysPerBlock + tid;
-  float *wcol = P.wbuf + (size_t)blockIdx.x * kMaxSamples * kRaysPerBlock + tid;
+  float *zcol = P.zbuf + (size_t)blockIdx.x * P.Sf * kRaysPerBlock + tid;
+  float *wcol = P.wbuf + (size_t)blockIdx.x * P.Sc * kRaysPerBlock + tid;
   float bgc[3] = {0.f, 0.f, 0.f};
   if (P.bg != nullptr) {
 #pragma unroll
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kRaysPerBlock, 1) render_fp32_kernel(const Ren
       z_cur = z_next;
       float p[3], pc[3];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) p[j] = ray.o[j] + ray.d[j] * z;
+      for (int j = 0; j < 3; ++j) p[j] = __fadd_rn(ray.o[j], __fmul_rn(ray.d[j], z));  // separate mul/add like ATen (:141)
       // ---- skinning warp (model/Skinning_Field.py:70-98)
       skin_warp(P, Tm, p, pc);
       // ---- bi-plane features, feature index = 2*c + plane (utils/util.py:359-392, model/nerf_model.py:88-99)

@@ -142,6 +142,59 @@ def gen_stages(torch):
     print("stages", sorted(out))
 
 
+# upfirdn2d call shapes of the reference (model/styleUnet.py): Blur after convT-up, Blur before stride-2 conv,
+# Upsample, Downsample, Haar analysis / synthesis, plus asymmetric / cropping / non-square cases.
+UFD_CASES = [
+    # name, shape NCHW, taps (1-D list or "haar_xx"), gain, up, down, pad(x0,x1,y0,y1)
+    ("blur_up", (2, 5, 17, 17), [1, 3, 3, 1], 4.0, (1, 1), (1, 1), (1, 1, 1, 1)),
+    ("blur_down", (2, 3, 16, 16), [1, 3, 3, 1], 1.0, (1, 1), (1, 1), (2, 2, 2, 2)),
+    ("upsample", (1, 4, 9, 12), [1, 3, 3, 1], 4.0, (2, 2), (1, 1), (2, 1, 2, 1)),
+    ("downsample", (1, 4, 14, 10), [1, 3, 3, 1], 1.0, (1, 1), (2, 2), (1, 1, 1, 1)),
+    ("haar_ll_down", (1, 3, 8, 12), "ll", 1.0, (1, 1), (2, 2), (0, 0, 0, 0)),
+    ("haar_lh_down", (1, 3, 8, 12), "lh", 1.0, (1, 1), (2, 2), (0, 0, 0, 0)),
+    ("haar_hl_up", (1, 3, 6, 5), "hl", 1.0, (2, 2), (1, 1), (1, 0, 1, 0)),
+    ("haar_hh_up", (1, 3, 6, 5), "hh", 1.0, (2, 2), (1, 1), (1, 0, 1, 0)),
+    ("asym_crop", (1, 2, 11, 13), [1, 2, 4, 2, 1], 1.0, (3, 2), (2, 3), (-1, 2, 3, -2)),
+    ("wide_tile", (1, 1, 40, 150), [1, 3, 3, 1], 1.0, (1, 1), (1, 1), (2, 1, 2, 1)),
+]
+
+
+def ufd_kernel(np_mod, taps, gain):
+    if isinstance(taps, str):
+        s = 1 / (2 ** 0.5)
+        lo, hi = np_mod.array([[s, s]], dtype=np_mod.float32), np_mod.array([[-s, s]], dtype=np_mod.float32)
+        a, b = {"ll": (lo, lo), "lh": (hi, lo), "hl": (lo, hi), "hh": (hi, hi)}[taps]
+        return (a.T * b).astype(np_mod.float32)            # model/styleUnet.py:371-381
+    k = np_mod.asarray(taps, dtype=np_mod.float32)
+    k = k[None, :] * k[:, None]
+    return (k / k.sum() * np_mod.float32(gain)).astype(np_mod.float32)
+
+
+def gen_ops(torch):
+    """model/op goldens from the reference's own CPU fallbacks (upfirdn2d.py:172-213, fused_act.py:107-119)."""
+    from model.op.fused_act import fused_leaky_relu
+    from model.op.upfirdn2d import upfirdn2d_native
+
+    rs = np.random.RandomState(200)
+    out = {}
+    for name, shape, taps, gain, up, down, pad in UFD_CASES:
+        x = rs.standard_normal(shape).astype(np.float32)
+        k = ufd_kernel(np, taps, gain)
+        y = upfirdn2d_native(torch.from_numpy(x), torch.from_numpy(k), up[0], up[1], down[0], down[1], *pad)
+        out["ufd_%s_x" % name], out["ufd_%s_y" % name] = x, y.numpy()
+    x = rs.standard_normal((3, 6, 5, 7)).astype(np.float32)
+    b = rs.standard_normal(6).astype(np.float32)
+    out["act_x"], out["act_b"] = x, b
+    out["act_y"] = fused_leaky_relu(torch.from_numpy(x), torch.from_numpy(b)).numpy()
+    out["act_y_nobias"] = fused_leaky_relu(torch.from_numpy(x)).numpy()
+    x2 = rs.standard_normal((4, 10)).astype(np.float32)
+    b2 = rs.standard_normal(10).astype(np.float32)
+    out["act2_x"], out["act2_b"] = x2, b2
+    out["act2_y"] = fused_leaky_relu(torch.from_numpy(x2), torch.from_numpy(b2)).numpy()
+    np.savez_compressed(os.path.join(GOLD, "ops.npz"), **out)
+    print("ops", len(out))
+
+
 def main():
     from oracle import ref_shim
 
@@ -152,6 +205,7 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(GOLD, exist_ok=True)
     gen_stages(torch)
+    gen_ops(torch)
     from model.nerf_trainer import Trainer
 
     trainer = Trainer(cfg, 4)
