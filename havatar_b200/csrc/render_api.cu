@@ -27,6 +27,7 @@ static int check_args(const hav_render_args *a) {
   if (a->plane_c != kPlaneC) return HAV_E_SHAPE;
   if (a->plane_h < 1 || a->plane_w < 1 || a->plane_h > 4096 || a->plane_w > 4096) return HAV_E_SHAPE;
   if (a->vol_d < 1 || a->vol_h < 1 || a->vol_w < 1) return HAV_E_SHAPE;
+  if ((int64_t)2 * a->batch * (a->plane_h + 3) * (a->plane_w + 3) >= ((int64_t)1 << 31) / 64) return HAV_E_SHAPE;
   if ((int64_t)a->batch * a->rays == 0) return HAV_OK;
   const void *req[] = {a->ray_batch, a->inv_head_T, a->planes, a->wvol, a->w0, a->b0, a->w1, a->b1, a->w_alpha,
                        a->b_alpha, a->w_feat, a->b_feat, a->w_rgb, a->b_rgb, a->rgb_coarse, a->depth_coarse,
@@ -47,8 +48,8 @@ static WsLayout layout(const hav_render_args *a) {
   L.pack_f32 = off, off = align_up(off + (uint64_t)kPackF32Floats * 4, 256);
   if (a->precision != HAV_PREC_FP32) {
     L.wimg = off, off = align_up(off + tc_weight_image_bytes(), 256);
-    L.planes_cl = off, off = align_up(off + (uint64_t)2 * a->batch * a->plane_h * a->plane_w * kPlaneC * 2, 256);
-    L.scratch_blocks = tc_num_ctas(L.num_blocks);
+    L.planes_cl = off, off = align_up(off + tc_planes_bytes(2 * a->batch, a->plane_h, a->plane_w), 256);
+    L.scratch_blocks = tc_scratch_slots(L.num_blocks);
   } else {
     L.scratch_blocks = L.num_blocks;
   }
@@ -110,9 +111,11 @@ extern "C" int hav_render_forward(const hav_render_args *a, void *stream) {
     if (major != 10) return HAV_E_ARCH;
     P.wimg = ws + L.wimg;
     P.planes_cl = (const uint16_t *)(ws + L.planes_cl);
-    launch_pack_mlp_bf16(a, ws + L.wimg, st);
-    launch_pack_planes_bf16(a->planes, (uint16_t *)(ws + L.planes_cl), 2 * a->batch, kPlaneC, a->plane_h, a->plane_w, st);
-    e = launch_render_bf16(P, L.num_blocks, st);
+    const bool bf16 = a->precision == HAV_PREC_BF16;
+    launch_pack_mlp_16(a, ws + L.wimg, st);
+    e = launch_pack_planes_16(a->planes, (uint16_t *)(ws + L.planes_cl), 2 * a->batch, a->plane_h, a->plane_w, bf16, st);
+    if (e != cudaSuccess) return (int)e;
+    e = launch_render_16(P, L.num_blocks, bf16, st);
   }
   return e == cudaSuccess ? HAV_OK : (int)e;
 }

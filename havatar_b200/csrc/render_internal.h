@@ -23,11 +23,13 @@ constexpr int kPackF32Floats = kOffBr + 4;
 void launch_pack_mlp_fp32(const hav_render_args *a, float *out, cudaStream_t st);
 cudaError_t launch_render_fp32(const RenderDev &P, int num_blocks, cudaStream_t st);
 
-// ---- bf16 tcgen05 path (render_tc.cu) ----
+// ---- 16-bit tcgen05 path (render_tc.cu) ----
 uint64_t tc_weight_image_bytes();
-void launch_pack_mlp_bf16(const hav_render_args *a, uint8_t *wimg, cudaStream_t st);
-void launch_pack_planes_bf16(const float *planes, uint16_t *out, int nplanes_b, int C, int H, int W, cudaStream_t st);
-cudaError_t launch_render_bf16(const RenderDev &P, int num_ray_blocks, cudaStream_t st);
+uint64_t tc_planes_bytes(int nimg, int H, int W);
 int tc_num_ctas(int num_ray_blocks);
+int tc_scratch_slots(int num_ray_blocks);
+void launch_pack_mlp_16(const hav_render_args *a, uint8_t *wimg, cudaStream_t st);
+cudaError_t launch_pack_planes_16(const float *planes, uint16_t *out, int nimg, int H, int W, bool bf16, cudaStream_t st);
+cudaError_t launch_render_16(const RenderDev &P, int num_ray_blocks, bool bf16, cudaStream_t st);
 
 }  // namespace hav
