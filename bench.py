@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s of the fused volumetric render on B200 (BASELINE.json metric, configs[1]:
+full 512x512 frame, 64 samples/ray, stage-one NeRF render, synthetic 3DMM inputs).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one render of one 512x512 frame (262144 rays x 64 samples) per GPU.  N > 1 is launched by torchrun,
+one rank per GPU, every rank renders its own frame (weak scaling, no data-path collective: rays are
+independent -- DESIGN.md "multi-GPU").  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 512
+S = 64
+FLOP_PER_SAMPLE = 94848          # 2 * (176*128 + 128*128 + 128*1 + 128*64 + 64*3): model/nerf_model.py:46-51
+BYTES_PER_RAY = 365              # algorithmic HBM bytes per ray at S = 64
+METRIC = "rays_per_sec_512x512x64"
+CPU_CHUNK_RAYS = 4096            # one reference chunk (nerf.validation.chunksize)
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"bf16_burst": d.get("bf16_tflops", 1590.0), "bf16_sustained": d.get("bf16_tflops_sustained", 1400.0),
+                "hbm": d.get("hbm_gbs", 6650.0), "source": "measured"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows),
+                "power_w_max": max(float(r[2]) for r in rows)}
+
+
+def cpu_reference_rate(chunks, threads):
+    """rays/s of the CPU port of the reference path (oracle/render_oracle_torch.py) on `chunks` 4096-ray chunks
+    of the benchmark frame.  Returns (rays_per_s, seconds, sample description)."""
+    import numpy as np
+    import torch
+
+    from havatar_b200 import synth
+    from oracle import render_oracle as ro
+    from oracle import render_oracle_torch as rt
+
+    torch.set_num_threads(threads)
+    rows = CPU_CHUNK_RAYS // W
+    sc = synth.scene(batch=1, height=H, width=W, crop=(H // 2 - rows * chunks // 2, 0, rows * chunks, W), seed=0)
+    args = (sc["ray_batch"], sc["background_prior"], sc["inv_head_T"], sc["planes"], sc["wvol"], sc["weights"],
+            ro.default_boxes(), S, 0)
+    warm = dict(sc, ray_batch=sc["ray_batch"][:, :CPU_CHUNK_RAYS], background_prior=sc["background_prior"][:, :CPU_CHUNK_RAYS])
+    rt.render_rays(warm["ray_batch"], warm["background_prior"], *args[2:], chunk=CPU_CHUNK_RAYS)
+    t0 = time.perf_counter()
+    out = rt.render_rays(*args, chunk=CPU_CHUNK_RAYS)
+    dt = time.perf_counter() - t0
+    assert np.isfinite(out["rgb_coarse"]).all()
+    n = rows * chunks * W
+    return n / dt, dt, "%d x %d-ray chunks (rows %d..%d of the 512x512 frame), 64 samples, torch-CPU port, %d threads" % (
+        chunks, CPU_CHUNK_RAYS, H // 2 - rows * chunks // 2, H // 2 + rows * chunks // 2 - 1, threads)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (torch-CPU port; the reference tree
+    itself is PyTorch and does not exist on the GPU box), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    chunks = 2 if args.warmup + args.steps <= 30 else 1
+    rates, secs, sample = [], [], ""
+    for i in range(args.warmup + args.steps):
+        r, dt, sample = cpu_reference_rate(chunks, threads)
+        if i >= args.warmup:
+            rates.append(r), secs.append(dt)
+    value = sum(rates) / len(rates)
+    line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "stage-one NeRF render, 512x512 frame x 64 samples/ray, coarse only (BASELINE.json configs[1])",
+                       "step": "bounded sample: " + sample},
+            "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    from havatar_b200 import _lib, render, synth
+
+    _lib.lib()  # fail loudly if the CUDA library is missing
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (havatar_b200 has no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic frame of this rank (weak scaling: one frame per GPU per step, different head pose per rank)
+    sc = synth.scene(batch=1, height=H, width=W, seed=rank)
+    sc["weights"] = synth.mlp_weights(0)      # same model on every rank
+    sc["wvol"] = synth.skin_volume(2)
+    R = H * W
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    host = {k: pin(sc[k]) for k in ("ray_batch", "background_prior", "inv_head_T", "planes")}
+    d = {k: v.to(dev) for k, v in host.items()}
+    wts = {k: torch.from_numpy(v).to(dev) for k, v in sc["weights"].items()}
+    wvol = torch.from_numpy(sc["wvol"]).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def step(out=None, reuse=False):
+        return render.render_rays(d["ray_batch"], d["background_prior"], d["inv_head_T"], d["planes"], wvol, wts, S, 0,
+                                  precision=args.precision, out=out, reuse_packed=reuse)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = None
+    for _ in range(max(args.warmup, 3)):
+        out = step(out)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs, K steps, per-step CUDA events, L2 flushed between steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    t0 = time.time()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        out = step(out)
+        b.record()
+    barrier()
+    t1 = time.time()
+    step_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    launches = args.steps * 4     # pack_mlp_fp32 + pack_mlp_16 + pack_planes + render_tc per hav_render_forward
+
+    # ---- the dominant kernel alone (weights/planes already packed): roofline numerator
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in kev:
+        flush.zero_()
+        a.record()
+        out = step(out, reuse=True)
+        b.record()
+    barrier()
+    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    clocks = sampler.stop(t0, time.time()) if sampler is not None else None
+    acc_mean = float(out.acc_coarse.mean())
+
+    # ---- timed region 2: end to end through the host-buffer API (pinned host in, pinned host out)
+    hr = render.HostRenderer(sc["weights"], sc["wvol"], S, 0, precision=args.precision, device=dev)
+    for _ in range(2):
+        res = hr(**host)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = hr(**host)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - e0) * 1e3 / args.steps
+    h2d, d2h = hr.h2d_bytes, hr.d2h_bytes
+    assert abs(float(res["acc_coarse"].mean()) - acc_mean) < 1e-6
+
+    t = torch.tensor([step_ms, kern_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms, kern_ms, e2e_ms = [float(v) for v in t.tolist()]
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = _peaks()
+    achieved = R * S * FLOP_PER_SAMPLE / (kern_ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "render_tc_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    threads = os.cpu_count() or 1
+    cpu_rate, cpu_s, cpu_sample = cpu_reference_rate(4, threads)
+    line = {
+        "metric": METRIC, "value": world * R / (step_ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": "stage-one NeRF render, 512x512 frame x 64 samples/ray, coarse only (BASELINE.json configs[1])",
+                   "frames_per_gpu_per_step": 1, "rays_per_step": world * R, "samples_per_ray": S,
+                   "mlp_arithmetic": "%s operands, fp32 accumulate (tcgen05/TMEM)" % args.precision if args.precision != "fp32" else "fp32 CUDA cores",
+                   "l2": "256 MiB buffer written between timed steps (L2 flush); per-step CUDA events on the launch stream",
+                   "acc_mean": acc_mean},
+        "e2e": {"value": world * R / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "havatar_b200.render.HostRenderer (pinned host in/out, hav_render_forward in between)"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_burst"], "traffic": traffic,
+                     "kernel": "render_tc_kernel", "kernel_ms": kern_ms, "flop_per_launch": R * S * FLOP_PER_SAMPLE,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone between L2 flushes), of %s" % peaks["source"],
+                     "frac_of_sustained": achieved / peaks["bf16_sustained"],
+                     "hbm_gbs_algorithmic": R * BYTES_PER_RAY / (kern_ms * 1e-3) / 1e9},
+        "cpu_baseline": {"value": cpu_rate, "unit": "rays/s", "cores": threads, "kind": "port", "sample": cpu_sample,
+                         "seconds": cpu_s},
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

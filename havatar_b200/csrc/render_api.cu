@@ -18,6 +18,7 @@ static int check_args(const hav_render_args *a) {
   if (a == nullptr) return HAV_E_NULL;
   if (a->struct_bytes != sizeof(hav_render_args)) return HAV_E_VALUE;
   if (a->precision != HAV_PREC_FP32 && a->precision != HAV_PREC_BF16 && a->precision != HAV_PREC_FP16) return HAV_E_VALUE;
+  if ((a->flags & ~HAV_RENDER_REUSE_PACKED) != 0) return HAV_E_VALUE;
   if (a->batch < 0 || a->rays < 0) return HAV_E_SHAPE;
   if ((int64_t)a->batch * a->rays > (int64_t)1 << 30) return HAV_E_SHAPE;
   if (a->num_coarse < 2 || a->num_coarse > kMaxSamples) return HAV_E_SHAPE;
@@ -100,8 +101,9 @@ extern "C" int hav_render_forward(const hav_render_args *a, void *stream) {
   P.b0 = pk + kOffB0, P.b1 = pk + kOffB1, P.bh = pk + kOffBh, P.Wr = pk + kOffWr, P.br = pk + kOffBr;
   if (a->num_fine > 0) P.zbuf = (float *)(ws + L.zbuf), P.wbuf = (float *)(ws + L.wbuf);
 
-  launch_pack_mlp_fp32(a, pk, st);
-  cudaError_t e;
+  const bool reuse = (a->flags & HAV_RENDER_REUSE_PACKED) != 0;
+  if (!reuse) launch_pack_mlp_fp32(a, pk, st);
+  cudaError_t e = cudaSuccess;
   if (a->precision == HAV_PREC_FP32) {
     e = launch_render_fp32(P, L.num_blocks, st);
   } else {
@@ -112,9 +114,11 @@ extern "C" int hav_render_forward(const hav_render_args *a, void *stream) {
     P.wimg = ws + L.wimg;
     P.planes_cl = (const uint16_t *)(ws + L.planes_cl);
     const bool bf16 = a->precision == HAV_PREC_BF16;
-    launch_pack_mlp_16(a, ws + L.wimg, st);
-    e = launch_pack_planes_16(a->planes, (uint16_t *)(ws + L.planes_cl), 2 * a->batch, a->plane_h, a->plane_w, bf16, st);
-    if (e != cudaSuccess) return (int)e;
+    if (!reuse) {
+      launch_pack_mlp_16(a, ws + L.wimg, st);
+      e = launch_pack_planes_16(a->planes, (uint16_t *)(ws + L.planes_cl), 2 * a->batch, a->plane_h, a->plane_w, bf16, st);
+      if (e != cudaSuccess) return (int)e;
+    }
     e = launch_render_16(P, L.num_blocks, bf16, st);
   }
   return e == cudaSuccess ? HAV_OK : (int)e;

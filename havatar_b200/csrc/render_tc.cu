@@ -17,6 +17,7 @@
 // so it is folded into the head GEMM as three pre-multiplied columns (fc_rgb.weight @ fc_rgbFeat.weight).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "render_common.cuh"
 #include "render_internal.h"
@@ -89,6 +90,16 @@ __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T: A rows = TMEM lanes, 16-bit elements packed two per 32-bit column
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // no-swizzle K-major shared-memory matrix descriptor: core matrix = 8 rows x 16 bytes, contiguous 128 B;
 // SBO = distance between 8-row groups, LBO = distance between the two 8-wide K chunks of one K = 16 step.
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -108,6 +119,14 @@ __host__ __device__ constexpr uint32_t instr_desc(int n, bool bf16) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),       \
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                     \
       : "r"(taddr))
+#define HAV_TMEM_ST16(taddr, r)                                                                                   \
+  asm volatile(                                                                                                   \
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"    \
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), \
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory")
+#define HAV_TMEM_ST8(taddr, r)                                                                    \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"           \
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory")
 #define HAV_TMEM_LD4(r, taddr)                                                 \
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"    \
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])                \
@@ -141,6 +160,52 @@ __device__ __forceinline__ uint32_t mul2(uint32_t a, uint32_t w) {
   if (kBF16) asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(w));
   else asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(w));
   return d;
+}
+
+
+// relu + 16-bit pack of one 128-column fp32 accumulator row (this thread's TMEM lane) into the A operand of the
+// next layer.  kTS: in place over the accumulator's columns [0,64) as packed pairs, plus the constant bias
+// column pair (1,0) at column 64 (columns 65..71 zero) -- reads of columns [32q, 32q+32) always precede the
+// write of [16q, 16q+16).  !kTS: shared-memory chunks 0..15 (the constant chunk 22/23 carries the bias column).
+template <bool kBF16, bool kTS>
+__device__ __forceinline__ void hidden_epilogue(uint32_t tm_row, uint8_t *Abuf, int t) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t r[32];
+    HAV_TMEM_LD32(r, tm_row + q * 32);
+    tmem_wait_ld();
+    uint32_t v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = pack_relu<kBF16>(__uint_as_float(r[2 * c]), __uint_as_float(r[2 * c + 1]));
+    if (kTS) {
+      HAV_TMEM_ST16(tm_row + q * 16, v);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4 *>(Abuf + (q * 4 + c) * kChunkA + t * 16) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    }
+  }
+  if (kTS) {
+    uint32_t one[8] = {kBF16 ? 0x3F80u : 0x3C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    HAV_TMEM_ST8(tm_row + 64, one);
+    tmem_wait_st();
+    tc_fence_before();
+  } else {
+    tc_fence_before();
+    fence_async_smem();
+  }
+}
+
+// the 8 + 1 K-steps of a hidden-layer GEMM: A = relu(previous accumulator) (TMEM or smem), B = weight matrix at w_addr
+template <bool kTS>
+__device__ __forceinline__ void issue_hidden(uint32_t tm_d, uint32_t tm_a, uint32_t A_addr, uint32_t w_addr, int chunk_b,
+                                             uint32_t idesc) {
+#pragma unroll
+  for (int k = 0; k <= kHid / 16; ++k) {
+    const uint64_t bdesc = smem_desc(w_addr + 2 * k * chunk_b, chunk_b, 128);
+    if (kTS) umma_ts(tm_d, tm_a + k * 8, bdesc, idesc, k > 0);
+    else umma_ss(tm_d, smem_desc(A_addr + (k < kHid / 16 ? 2 * k : kOnesChunk) * kChunkA, kChunkA, 128), bdesc, idesc, k > 0);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -232,7 +297,7 @@ __device__ __forceinline__ void plane_taps(float gx, float gy, int H, int W, int
   off = (img * Hp + ((int)y0f + kPadLo)) * Wp + ((int)x0f + kPadLo);
 }
 
-template <bool kBF16>
+template <bool kBF16, bool kTS>
 __global__ void __launch_bounds__(kThreads, 1) render_tc_kernel(const RenderDev P, int num_ray_blocks) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp = t >> 5, lane = tid & 31;
@@ -390,66 +455,25 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_kernel(const RenderDev 
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-        // ---- epilogue 0: relu -> 16 bit -> A chunks 0..15 (model/nerf_model.py:105-106)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t r[32];
-          HAV_TMEM_LD32(r, tm_acc0 + tm_lane + q * 32);
-          tmem_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 v;
-            v.x = pack_relu<kBF16>(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1]));
-            v.y = pack_relu<kBF16>(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3]));
-            v.z = pack_relu<kBF16>(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5]));
-            v.w = pack_relu<kBF16>(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7]));
-            *reinterpret_cast<uint4 *>(Abuf + (q * 4 + c) * kChunkA + t * 16) = v;
-          }
-        }
-        tc_fence_before();
-        fence_async_smem();
+        // ---- epilogue 0: relu -> 16 bit -> A operand of L1 (model/nerf_model.py:105-106).  TS: written back over
+        //      the accumulator's own columns (two values per column) + the bias column; SS: smem chunks 0..15
+        hidden_epilogue<kBF16, kTS>(tm_acc0 + tm_lane, Abuf, t);
         bar_wg(wg);
         // ---- L1: [128 x 128 (+bias)] x [.. x 128] -> acc1
         if (t == 0) {
           tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < kHid / 16; ++k)
-            umma_ss(tm_acc1, smem_desc(A_addr + 2 * k * kChunkA, kChunkA, 128), smem_desc(W1_addr + 2 * k * kChunkB, kChunkB, 128),
-                    kIdesc128, k > 0);
-          umma_ss(tm_acc1, smem_desc(A_addr + kOnesChunk * kChunkA, kChunkA, 128),
-                  smem_desc(W1_addr + (kHid / 8) * kChunkB, kChunkB, 128), kIdesc128, 1);
+          issue_hidden<kTS>(tm_acc1, tm_acc0, A_addr, W1_addr, kChunkB, kIdesc128);
           umma_commit(bar);
         }
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t r[32];
-          HAV_TMEM_LD32(r, tm_acc1 + tm_lane + q * 32);
-          tmem_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 v;
-            v.x = pack_relu<kBF16>(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1]));
-            v.y = pack_relu<kBF16>(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3]));
-            v.z = pack_relu<kBF16>(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5]));
-            v.w = pack_relu<kBF16>(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7]));
-            *reinterpret_cast<uint4 *>(Abuf + (q * 4 + c) * kChunkA + t * 16) = v;
-          }
-        }
-        tc_fence_before();
-        fence_async_smem();
+        hidden_epilogue<kBF16, kTS>(tm_acc1 + tm_lane, Abuf, t);
         bar_wg(wg);
         // ---- head: [128 x 128 (+bias)] x [.. x 80] -> acc0 cols 0..79
         if (t == 0) {
           tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < kHid / 16; ++k)
-            umma_ss(tm_acc0, smem_desc(A_addr + 2 * k * kChunkA, kChunkA, 128), smem_desc(WH_addr + 2 * k * kChunkBH, kChunkBH, 128),
-                    kIdescH, k > 0);
-          umma_ss(tm_acc0, smem_desc(A_addr + kOnesChunk * kChunkA, kChunkA, 128),
-                  smem_desc(WH_addr + (kHid / 8) * kChunkBH, kChunkBH, 128), kIdescH, 1);
+          issue_hidden<kTS>(tm_acc0, tm_acc1, A_addr, WH_addr, kChunkBH, kIdescH);
           umma_commit(bar);
         }
         mbar_wait(bar, phase);
@@ -559,19 +583,18 @@ cudaError_t launch_pack_planes_16(const float *planes, uint16_t *out, int nimg, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_render_16(const RenderDev &P, int num_ray_blocks, bool bf16, cudaStream_t st) {
-  cudaError_t e;
-  const int grid = tc_num_ctas(num_ray_blocks);
-  if (bf16) {
-    e = cudaFuncSetAttribute(tc::render_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    tc::render_tc_kernel<true><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(P, num_ray_blocks);
-  } else {
-    e = cudaFuncSetAttribute(tc::render_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    tc::render_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, st>>>(P, num_ray_blocks);
-  }
+template <bool kBF16, bool kTS>
+static cudaError_t launch_tc(const RenderDev &P, int num_ray_blocks, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(tc::render_tc_kernel<kBF16, kTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  tc::render_tc_kernel<kBF16, kTS><<<tc_num_ctas(num_ray_blocks), tc::kThreads, tc::kSmemBytes, st>>>(P, num_ray_blocks);
   return cudaGetLastError();
+}
+
+cudaError_t launch_render_16(const RenderDev &P, int num_ray_blocks, bool bf16, cudaStream_t st) {
+  static const bool ss = getenv("HAV_TC_SS") != nullptr;   // debugging aid: hidden activations through smem instead of TMEM
+  if (ss) return bf16 ? launch_tc<true, false>(P, num_ray_blocks, st) : launch_tc<false, false>(P, num_ray_blocks, st);
+  return bf16 ? launch_tc<true, true>(P, num_ray_blocks, st) : launch_tc<false, true>(P, num_ray_blocks, st);
 }
 
 }  // namespace hav

@@ -72,12 +72,14 @@ def _workspace(device, nbytes):
 
 def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, num_coarse, num_fine=0,
                 boxes=None, t_rand=None, noise_coarse=None, u_rand=None, noise_fine=None, precision="fp16",
-                want_z_fine=False):
+                want_z_fine=False, reuse_packed=False, out=None):
     """ray_batch [B,R,8] (o3 d3 near far; extra trailing columns such as the reference's viewdirs are
     ignored), background_prior [B,R,3] or None, inv_head_T [B,4,3], planes [2,B,64,H,W], wvol [1,2,D,H,W],
     weights: mapping with the reference's model_coarse keys (MLP_KEYS).  Random draws are explicit inputs
     (SURVEY.md section 8a quirk v): t_rand [B,R,Sc], noise_* [B,R,S] already scaled by the noise std,
     u_rand [B,R,num_fine]; None switches that randomness off (u_rand None == sample_pdf det=True).
+    reuse_packed=True skips re-packing weights/planes (HAV_RENDER_REUSE_PACKED: same weights, planes, precision
+    and batch as the previous call on this stream).  out = a previous RenderOut to write into (no allocation).
     Returns RenderOut of [B,R,*] tensors (fine slots None when num_fine == 0)."""
     L = _lib.lib()
     if ray_batch.dim() != 3 or ray_batch.shape[-1] < 8:
@@ -97,6 +99,7 @@ def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, 
     a = _lib.RenderArgs()
     a.struct_bytes = C.sizeof(_lib.RenderArgs)
     a.precision = _lib.PRECISIONS[precision]
+    a.flags = 1 if reuse_packed else 0
     a.batch, a.rays, a.num_coarse, a.num_fine = B, R, int(num_coarse), int(num_fine)
     a.plane_c, a.plane_h, a.plane_w = int(planes.shape[2]), int(planes.shape[3]), int(planes.shape[4])
     a.vol_d, a.vol_h, a.vol_w = int(wvol.shape[2]), int(wvol.shape[3]), int(wvol.shape[4])
@@ -120,12 +123,19 @@ def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, 
         keep.append(t)
         setattr(a, name, _ptr(t))
     new = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    prev = out
     out = dict(rgb_coarse=new(B, R, 67), depth_coarse=new(B, R, 1), acc_coarse=new(B, R, 1), weights_max=new(B, R, 1),
                rgb_fine=None, depth_fine=None, acc_fine=None, z_fine=None)
     if num_fine > 0:
         out.update(rgb_fine=new(B, R, 67), depth_fine=new(B, R, 1), acc_fine=new(B, R, 1))
         if want_z_fine:
             out["z_fine"] = new(B, R, Sf)
+    if prev is not None:
+        for k in out:
+            v = getattr(prev, k)
+            if (v is None) != (out[k] is None) or (v is not None and (v.shape != out[k].shape or v.device != dev)):
+                raise _lib.HavError("out.%s does not match this call" % k)
+            out[k] = v
     for k, v in out.items():
         setattr(a, k, _ptr(v))
     with torch.cuda.device(dev):
@@ -154,3 +164,45 @@ def get_rays(height, width, intr, c2w, near, far, device="cuda"):
         _lib.check(L.hav_get_rays(_ptr(out), int(height), int(width), intr_c, c2w_c, float(near), float(far),
                                   C.c_void_p(stream)), "hav_get_rays")
     return out
+
+
+class HostRenderer:
+    """Host-buffer front end of render_rays: the per-frame inputs arrive in (pinned) host memory the way the
+    reference's dataloader hands them over (train_avatar.py:108-120 `.to(device)` per batch) and the rendered maps
+    are returned in pinned host memory (avatarHD_reenactment.py:168 `.cpu()`).  Model constants (MLP weights,
+    skinning-weight volume) stay resident on the device.  Device staging and pinned result buffers are allocated
+    once and reused, so a call is: H2D copies -> one hav_render_forward -> D2H copies -> stream sync."""
+
+    def __init__(self, weights, wvol, num_coarse, num_fine=0, boxes=None, precision="fp16", device="cuda"):
+        self.dev = torch.device(device)
+        self.weights = {k: torch.as_tensor(v).to(self.dev, torch.float32).contiguous() for k, v in weights.items()}
+        self.wvol = torch.as_tensor(wvol).to(self.dev, torch.float32).contiguous()
+        self.num_coarse, self.num_fine, self.boxes, self.precision = num_coarse, num_fine, boxes, precision
+        self._dev_in, self._dev_out, self._host_out = {}, None, None
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def _stage(self, name, host):
+        buf = self._dev_in.get(name)
+        if buf is None or buf.shape != host.shape:
+            buf = torch.empty(host.shape, dtype=torch.float32, device=self.dev)
+            self._dev_in[name] = buf
+        buf.copy_(host, non_blocking=True)
+        self.h2d_bytes += host.numel() * 4
+        return buf
+
+    def __call__(self, ray_batch, background_prior, inv_head_T, planes, **rand):
+        """All arguments are float32 CPU tensors (pinned for async copies).  Returns a dict of pinned CPU tensors."""
+        self.h2d_bytes = self.d2h_bytes = 0
+        args = [self._stage(n, t) for n, t in (("ray_batch", ray_batch), ("background_prior", background_prior),
+                                               ("inv_head_T", inv_head_T), ("planes", planes))]
+        rnd = {k: self._stage(k, v) for k, v in rand.items() if v is not None}
+        self._dev_out = render_rays(*args, self.wvol, self.weights, self.num_coarse, self.num_fine, boxes=self.boxes,
+                                    precision=self.precision, out=self._dev_out, **rnd)
+        if self._host_out is None or self._host_out["rgb_coarse"].shape != self._dev_out.rgb_coarse.shape:
+            self._host_out = {k: torch.empty(v.shape, dtype=torch.float32, pin_memory=True)
+                              for k, v in self._dev_out._asdict().items() if v is not None}
+        for k, h in self._host_out.items():
+            h.copy_(getattr(self._dev_out, k), non_blocking=True)
+            self.d2h_bytes += h.numel() * 4
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self._host_out

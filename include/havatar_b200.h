@@ -43,6 +43,12 @@ extern "C" {
 #define HAV_PREC_BF16 1 /* tcgen05 bf16 operands, fp32 accumulate in TMEM (fast path, fp32 exponent range) */
 #define HAV_PREC_FP16 2 /* tcgen05 fp16 operands (saturating converts), fp32 accumulate: fast path, 8x finer rounding */
 
+/* hav_render_args.flags */
+#define HAV_RENDER_REUSE_PACKED 1 /* the workspace still holds the packed MLP weights and planes written by a previous
+                                     hav_render_forward with the same weights/planes/precision/batch: skip re-packing
+                                     (weights change once per optimiser step, planes once per frame; the reference
+                                     re-renders the same frame in 4096-ray groups, train_avatar.py:182-218) */
+
 int hav_abi_version(void);
 const char *hav_error_string(int code);
 
@@ -87,7 +93,7 @@ typedef struct hav_render_args {
   int32_t plane_c;       /* feature channels per plane (64) */
   int32_t plane_h, plane_w;
   int32_t vol_d, vol_h, vol_w;
-  int32_t flags;         /* reserved, 0 */
+  int32_t flags;         /* HAV_RENDER_* bits, 0 by default */
   float plane_scale[3], plane_trans[3]; /* model_coarse.gridwarper (utils/util.py:214-236) */
   float skin_scale[3], skin_trans[3];   /* headpose_skin_net.gridwarper (model/nerf_trainer.py:29-34) */
 

@@ -71,3 +71,24 @@ def test_feature_interleave_order(golden_dir):
     g = _load(golden_dir, "stages")
     f = ro.plane_features(g["tp_q"][0], g["tp_planes"][:, 0], np.ones(3, np.float32), np.zeros(3, np.float32))
     assert np.abs(f.reshape(-1, 5, 2) - g["tp_y"][0]).max() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["render_c32_s32", "render_hier_det", "render_hier_rand", "render_oddshape"])
+def test_torch_port_matches_reference(golden_dir, name):
+    """oracle/render_oracle_torch.py (the CPU baseline bench.py times) against the same goldens."""
+    from oracle import render_oracle_torch as rt
+
+    g = _load(golden_dir, name)
+    case = json.loads(str(g.pop("case")))
+    sc = synth.scene(batch=case["batch"], crop=tuple(case["crop"]), seed=case["seed"],
+                     plane_hw=tuple(case.get("plane_hw", (128, 128))), vol_dhw=tuple(case.get("vol_dhw", (64, 64, 64))))
+    B, R = sc["ray_batch"].shape[:2]
+    kw = {}
+    if case["rand"]:
+        rnd = synth.randoms(B, R, case["num_coarse"], case["num_fine"], seed=case["seed"] + 7)
+        kw = dict(t_rand=rnd["t_rand"], noise_coarse=rnd["noise_coarse"], u_rand=rnd["u_rand"], noise_fine=rnd["noise_fine"])
+    out = rt.render_rays(sc["ray_batch"], sc["background_prior"], sc["inv_head_T"], sc["planes"], sc["wvol"],
+                         sc["weights"], ro.default_boxes(), case["num_coarse"], case["num_fine"], chunk=100, **kw)
+    for k, ref in g.items():
+        err = np.abs(out[k].reshape(ref.shape) - ref).max()
+        assert err < ATOL, (name, k, err)
