@@ -31,5 +31,6 @@ int tc_scratch_slots(int num_ray_blocks);
 void launch_pack_mlp_16(const hav_render_args *a, uint8_t *wimg, cudaStream_t st);
 cudaError_t launch_pack_planes_16(const float *planes, uint16_t *out, int nimg, int H, int W, bool bf16, cudaStream_t st);
 cudaError_t launch_render_16(const RenderDev &P, int num_ray_blocks, bool bf16, cudaStream_t st);
+cudaError_t launch_render_16_v2(const RenderDev &P, int num_ray_blocks, bool bf16, cudaStream_t st);  // render_tc2.cu
 
 }  // namespace hav
