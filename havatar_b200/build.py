@@ -19,7 +19,7 @@ OBJ = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libhavatar_b200.so")
 SOURCES = ["render_api.cu", "render_simt.cu", "render_tc.cu", "render_tc2.cu", "ops.cu", "modconv.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"] + os.environ.get("HAV_NVCC_DEFS", "").split()
 
 
 def _nvcc():
@@ -47,12 +47,16 @@ def _deps():
     return hdrs + [os.path.join(CSRC, s) for s in _sources()] + [os.path.abspath(__file__)]
 
 
+def _flags_tag():
+    return os.environ.get("HAV_NVCC_DEFS", "")
+
+
 def is_fresh():
     stamp = LIB + ".stamp"
     if not (os.path.exists(LIB) and os.path.exists(stamp)):
         return False
     with open(stamp) as f:
-        return f.read().strip() == _digest(_deps())
+        return f.read().strip() == _digest(_deps()) + _flags_tag()
 
 
 def build_library(force=False, verbose=False):
@@ -80,7 +84,7 @@ def build_library(force=False, verbose=False):
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
     with open(LIB + ".stamp", "w") as f:
-        f.write(_digest(_deps()))
+        f.write(_digest(_deps()) + _flags_tag())
     return LIB
 
 

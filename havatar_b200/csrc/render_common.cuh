@@ -167,9 +167,10 @@ struct Composite {
   float T, acc, depth, wmax;
   __device__ __forceinline__ void reset() { T = 1.0f, acc = 0.0f, depth = 0.0f, wmax = 0.0f; }
   // returns the sample weight w_i = alpha_i * T_i  (:59-60; cumprod_exclusive :4-25)
+  template <bool kFast = false>
   __device__ __forceinline__ float step(float alpha_raw, float noise, float dist, float z) {
     float sigma = fmaxf(alpha_raw + noise, 0.0f);   // :58
-    float alpha = 1.0f - expf(-sigma * dist);       // :59
+    float alpha = 1.0f - (kFast ? __expf(-sigma * dist) : expf(-sigma * dist));       // :59
     float w = alpha * T;
     T *= (1.0f - alpha) + 1e-10f;
     acc += w;                                       // :67
@@ -180,6 +181,8 @@ struct Composite {
 };
 
 __device__ __forceinline__ float sigmoidf_exact(float x) { return 1.0f / (1.0f + expf(-x)); }  // nerf_util.py:45
+// MUFU.EX2 + MUFU.RCP version for the 16-bit tensor-core modes (rel. error ~1e-6, far below the operand rounding)
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
 
 // utils/nerf_util.py:76-117 sample_pdf + model/nerf_trainer.py:166-170 merge, for one ray (one thread).
 //   zc(s)      : coarse depth of sample s (0..Sc-1)

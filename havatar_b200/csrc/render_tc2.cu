@@ -22,6 +22,22 @@ namespace tc2 {
 
 using namespace tc;
 
+// Optional phase timing (build with HAV_NVCC_DEFS=-DHAV_TC_TIMING): thread 0 of pair 0 of CTA 0 accumulates the
+// cycles it spends in each phase into P.zbuf-independent global counters (see scripts/time_phases.py).
+#ifdef HAV_TC_TIMING
+__device__ unsigned long long g_phase_cycles[32];
+#define TICK(var) long long var = clock64()
+#define TOCK(idx, var)                                                        \
+  do {                                                                        \
+    long long _n = clock64();                                                 \
+    if (t == 0 && pair == 0 && blockIdx.x == 0) g_phase_cycles[idx] += (unsigned long long)(_n - var); \
+    var = _n;                                                                 \
+  } while (0)
+#else
+#define TICK(var)
+#define TOCK(idx, var)
+#endif
+
 constexpr int kPairs = 2;
 constexpr int kThreads2 = 512;
 constexpr int kConsumerRegs = 168, kProducerRegs = 88;
@@ -42,6 +58,12 @@ constexpr int kBarXFull = 0, kBarXFree = 1, kBarMma = 2, kBarZFine = 3, kBarsPer
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void bar_named(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // tap base + the four bilinear weights, pre-packed as duplicated 16-bit pairs for the gather's HFMA2s
@@ -70,7 +92,7 @@ __device__ __forceinline__ void producer_loop(const RenderDev &P, int num_ray_bl
   const uint32_t bar_full = bars + kBarXFull * 8, bar_free = bars + kBarXFree * 8, bar_zfine = bars + kBarZFine * 8;
   const int Wp = P.PW + kPadLo + kPadHi;
   const uint4 *planes = reinterpret_cast<const uint4 *>(P.planes_cl);
-  const int sub = lane >> 4, plane = (lane >> 3) & 1, oct = lane & 7;
+  const int oct = lane & 7;
   uint32_t n = 0;          // tiles produced so far by this pair
   uint32_t zfine_phase = 0;
 
@@ -93,6 +115,7 @@ __device__ __forceinline__ void producer_loop(const RenderDev &P, int num_ray_bl
 #pragma unroll 1
       for (int s = 0; s < S; ++s, ++n) {
         uint8_t *stage = stage_base + (n & 1) * kStageBytes2;
+        TICK(tk);
         // ---- row thread: depth, point, skinning warp, tap descriptors, PE
         const float z = pass == 0 ? coarse_z(P, ray, gi, s) : __ldcg(zcol + s * kRaysPerBlock);
         float p[3], pc[3];
@@ -127,29 +150,64 @@ __device__ __forceinline__ void producer_loop(const RenderDev &P, int num_ray_bl
             }
           }
         }
+        TOCK(0, tk);
         bar_named(3 + pair);                                  // tap descriptors of all 128 rows are visible
+        TOCK(1, tk);
         if (n > 0) mbar_wait(bar_free, (n - 1) & 1);          // L0 of the previous tile has finished reading X
+        TOCK(2, tk);
 #pragma unroll
         for (int c = 0; c < 6; ++c)
           *reinterpret_cast<uint4 *>(X + (16 + c) * kChunkA + t * 16) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
-        // ---- cooperative gather: 16 lanes per row (2 planes x 8 channel octets), 2 rows per step
-#pragma unroll 4
-        for (int it = 0; it < 16; ++it) {
-          const int row = warp * 32 + it * 2 + sub;
-          const uint8_t *sp = stage + row * kStageRow;
-          const int off = *reinterpret_cast<const int *>(sp + plane * 4);
-          const uint4 w = *reinterpret_cast<const uint4 *>(sp + 16 + plane * 16);
-          const uint4 *tp = planes + (size_t)off * 8 + oct;
-          const uint4 t00 = __ldg(tp), t01 = __ldg(tp + 8), t10 = __ldg(tp + (size_t)Wp * 8), t11 = __ldg(tp + (size_t)Wp * 8 + 8);
-          uint4 r;
-          r.x = fma2<kBF16>(t11.x, w.w, fma2<kBF16>(t10.x, w.z, fma2<kBF16>(t01.x, w.y, mul2<kBF16>(t00.x, w.x))));
-          r.y = fma2<kBF16>(t11.y, w.w, fma2<kBF16>(t10.y, w.z, fma2<kBF16>(t01.y, w.y, mul2<kBF16>(t00.y, w.x))));
-          r.z = fma2<kBF16>(t11.z, w.w, fma2<kBF16>(t10.z, w.z, fma2<kBF16>(t01.z, w.y, mul2<kBF16>(t00.z, w.x))));
-          r.w = fma2<kBF16>(t11.w, w.w, fma2<kBF16>(t10.w, w.z, fma2<kBF16>(t01.w, w.y, mul2<kBF16>(t00.w, w.x))));
-          *reinterpret_cast<uint4 *>(X + (plane * 8 + oct) * kChunkA + row * 16) = r;
+        // ---- cooperative gather: one step = 4 consecutive rows x 1 plane x 8 channel octets (lane = row-in-group*8 +
+        //      octet).  Neighbouring rays mostly share their texels (a texel spans ~4.5 pixels, and all rays of a tile
+        //      sit at the same depth), so a step's 32 tap loads usually fall into 1-2 128-byte lines instead of 4.
+        //      Software pipelined by hand: the tap loads of step i+1 are in flight while step i is blended.
+        {
+          const int rsub = lane >> 3;
+          const uint8_t *sp0 = stage + (warp * 32 + rsub) * kStageRow;
+          uint8_t *xrow = X + oct * kChunkA + (warp * 32 + rsub) * 16;
+          const size_t row_pitch = (size_t)Wp * 8;
+          uint4 ta[4], tb[4], wa, wb;
+          int offn;
+          // step i: rows 4*(i>>1) .. +3, plane i&1
+          auto load_desc = [&](int i, uint4 &w) {
+            const uint8_t *sp = sp0 + (i >> 1) * 4 * kStageRow;
+            w = *reinterpret_cast<const uint4 *>(sp + 16 + (i & 1) * 16);
+            return *reinterpret_cast<const int *>(sp + (i & 1) * 4);
+          };
+          auto issue = [&](int off, uint4 (&tt)[4]) {
+            const uint4 *tp = planes + (size_t)off * 8 + oct;
+            tt[0] = __ldg(tp), tt[1] = __ldg(tp + 8), tt[2] = __ldg(tp + row_pitch), tt[3] = __ldg(tp + row_pitch + 8);
+          };
+          auto blend = [&](const uint4 (&tt)[4], const uint4 &w, int i) {
+            uint4 r;
+            r.x = fma2<kBF16>(tt[3].x, w.w, fma2<kBF16>(tt[2].x, w.z, fma2<kBF16>(tt[1].x, w.y, mul2<kBF16>(tt[0].x, w.x))));
+            r.y = fma2<kBF16>(tt[3].y, w.w, fma2<kBF16>(tt[2].y, w.z, fma2<kBF16>(tt[1].y, w.y, mul2<kBF16>(tt[0].y, w.x))));
+            r.z = fma2<kBF16>(tt[3].z, w.w, fma2<kBF16>(tt[2].z, w.z, fma2<kBF16>(tt[1].z, w.y, mul2<kBF16>(tt[0].z, w.x))));
+            r.w = fma2<kBF16>(tt[3].w, w.w, fma2<kBF16>(tt[2].w, w.z, fma2<kBF16>(tt[1].w, w.y, mul2<kBF16>(tt[0].w, w.x))));
+            *reinterpret_cast<uint4 *>(xrow + (i & 1) * 8 * kChunkA + (i >> 1) * 64) = r;
+          };
+          issue(load_desc(0, wa), ta);
+          offn = load_desc(1, wb);
+#pragma unroll 1
+          for (int i = 0; i < 16; i += 2) {
+            issue(offn, tb);
+            uint4 wn;
+            if (i + 2 < 16) offn = load_desc(i + 2, wn);
+            blend(ta, wa, i);
+            if (i + 2 < 16) {
+              issue(offn, ta);
+              wa = wn;
+              offn = load_desc(i + 3, wn);
+            }
+            blend(tb, wb, i + 1);
+            wb = wn;
+          }
         }
+        TOCK(3, tk);
         fence_async_smem();
         mbar_arrive(bar_full);
+        TOCK(4, tk);
       }
     }
   }
@@ -160,8 +218,8 @@ __device__ __forceinline__ void producer_loop(const RenderDev &P, int num_ray_bl
 // ------------------------------------------------------------------------------------------------
 template <bool kBF16>
 __device__ __forceinline__ void consumer_loop(const RenderDev &P, int num_ray_blocks, uint32_t smem_base, uint32_t tmem_base,
-                                              int pair, int t) {
-  const int warp = t >> 5;
+                                              int pair, int warp, int t) {
+  const bool issuer = warp == 0;   // `pair` and `warp` are warp-uniform (shuffled from lane 0 by the caller)
   const uint32_t bars = smem_base + kSmBar + pair * kBarsPerPair * 8;
   const uint32_t bar_full = bars + kBarXFull * 8, bar_free = bars + kBarXFree * 8, bar_mma = bars + kBarMma * 8,
                  bar_zfine = bars + kBarZFine * 8;
@@ -198,16 +256,21 @@ __device__ __forceinline__ void consumer_loop(const RenderDev &P, int num_ray_bl
 #pragma unroll 1
       for (int s = 0; s < S; ++s, ++n) {
         // ---- L0: [128 x 192] x [192 x 128] -> acc0, A = X (smem) + the constant bias chunk pair
-        if (t == 0) {
+        TICK(tk);
+        if (issuer) {   // warp-uniform: descriptors stay in uniform registers, one elected lane issues
           mbar_wait(bar_full, n & 1);
+          TOCK(8, tk);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kK0 / 16; ++k) {
-            const uint32_t a_addr = k < kXChunks / 2 ? X_addr + 2 * k * kChunkA : C_addr;
-            umma_ss(tm_acc0, smem_desc(a_addr, kChunkA, 128), smem_desc(W0_addr + 2 * k * kChunkB, kChunkB, 128), kIdesc128, k > 0);
+            for (int k = 0; k < kK0 / 16; ++k) {
+              const uint32_t a_addr = k < kXChunks / 2 ? X_addr + 2 * k * kChunkA : C_addr;
+              umma_ss(tm_acc0, smem_desc(a_addr, kChunkA, 128), smem_desc(W0_addr + 2 * k * kChunkB, kChunkB, 128), kIdesc128, k > 0);
+            }
+            umma_commit(bar_free);
+            umma_commit(bar_mma);
           }
-          umma_commit(bar_free);
-          umma_commit(bar_mma);
+          __syncwarp();
         }
         // depth bookkeeping of this sample while the GEMM runs (nerf_trainer.py:129-141, nerf_util.py:36-38)
         float z_next = 0.0f, dist;
@@ -222,38 +285,54 @@ __device__ __forceinline__ void consumer_loop(const RenderDev &P, int num_ray_bl
         z_cur = z_next;
         const float nz = noise != nullptr ? __ldg(noise + (size_t)gi * S + s) : 0.0f;
 
+        TOCK(9, tk);
         mbar_wait(bar_mma, mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
+        TOCK(10, tk);
         hidden_epilogue<kBF16, true>(tm_acc0 + tm_lane, nullptr, t);
+        TOCK(11, tk);
         bar_named(1 + pair);
-        if (t == 0) {
+        TOCK(12, tk);
+        if (issuer) {
           tc_fence_after();
-          issue_hidden<true>(tm_acc1, tm_acc0, 0, W1_addr, kChunkB, kIdesc128);
-          umma_commit(bar_mma);
+          if (elect_one()) {
+            issue_hidden<true>(tm_acc1, tm_acc0, 0, W1_addr, kChunkB, kIdesc128);
+            umma_commit(bar_mma);
+          }
+          __syncwarp();
         }
+        TOCK(13, tk);
         mbar_wait(bar_mma, mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
+        TOCK(14, tk);
         hidden_epilogue<kBF16, true>(tm_acc1 + tm_lane, nullptr, t);
+        TOCK(15, tk);
         bar_named(1 + pair);
-        if (t == 0) {
+        TOCK(16, tk);
+        if (issuer) {
           tc_fence_after();
-          issue_hidden<true>(tm_acc0, tm_acc1, 0, WH_addr, kChunkBH, kIdescH);
-          umma_commit(bar_mma);
+          if (elect_one()) {
+            issue_hidden<true>(tm_acc0, tm_acc1, 0, WH_addr, kChunkBH, kIdescH);
+            umma_commit(bar_mma);
+          }
+          __syncwarp();
         }
+        TOCK(17, tk);
         mbar_wait(bar_mma, mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
+        TOCK(18, tk);
         // ---- composite (utils/nerf_util.py:28-73): cols 64 = sigma, 65..67 = rgb logits, 0..63 = features
         {
           uint32_t h[4];
           HAV_TMEM_LD4(h, tm_acc0 + tm_lane + kRgbFeat);
           tmem_wait_ld();
-          const float w = cs.step(__uint_as_float(h[0]), nz, dist * ray.dnorm, z);
+          const float w = cs.step<true>(__uint_as_float(h[0]), nz, dist * ray.dnorm, z);
           if (pass == 0 && npass == 2) wcol[s * kRaysPerBlock] = w;
 #pragma unroll
-          for (int j = 0; j < 3; ++j) sums[j] = fmaf(w, sigmoidf_exact(__uint_as_float(h[1 + j])), sums[j]);
+          for (int j = 0; j < 3; ++j) sums[j] = fmaf(w, sigmoidf_fast(__uint_as_float(h[1 + j])), sums[j]);
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             uint32_t r[32];
@@ -263,8 +342,10 @@ __device__ __forceinline__ void consumer_loop(const RenderDev &P, int num_ray_bl
             for (int c = 0; c < 32; ++c) sums[3 + q * 32 + c] = fmaf(w, __uint_as_float(r[c]), sums[3 + q * 32 + c]);
           }
         }
+        TOCK(19, tk);
         tc_fence_before();
         bar_named(1 + pair);   // every row has read the head accumulator before the next L0 overwrites acc0
+        TOCK(20, tk);
       }
       // ---- write the ray (utils/nerf_util.py:62-71)
       if (ray.valid) {
@@ -330,10 +411,11 @@ __global__ void __launch_bounds__(kThreads2, 1) render_tc2_kernel(const RenderDe
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int pair = (tid >> 7) & 1, t = tid & 127;
-  if (tid < 256) {
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform in the compiler's eyes
+  const int pair = (warp_u >> 2) & 1, t = tid & 127;
+  if (warp_u < 8) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
-    consumer_loop<kBF16>(P, num_ray_blocks, smem_base, tmem_base, pair, t);
+    consumer_loop<kBF16>(P, num_ray_blocks, smem_base, tmem_base, pair, warp_u & 3, t);
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
     producer_loop<kBF16>(P, num_ray_blocks, smem, smem_base, pair, t);
@@ -361,6 +443,17 @@ static cudaError_t launch_tc2(const RenderDev &P, int num_ray_blocks, cudaStream
   tc2::render_tc2_kernel<kBF16><<<tc2_num_ctas(num_ray_blocks), tc2::kThreads2, tc2::kSmemBytes2, st>>>(P, num_ray_blocks);
   return cudaGetLastError();
 }
+
+#ifdef HAV_TC_TIMING
+extern "C" int hav_debug_phase_cycles(unsigned long long *out32, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out32, tc2::g_phase_cycles, sizeof(unsigned long long) * 32);
+  if (e == cudaSuccess && reset) {
+    unsigned long long z[32] = {0};
+    e = cudaMemcpyToSymbol(tc2::g_phase_cycles, z, sizeof(z));
+  }
+  return (int)e;
+}
+#endif
 
 cudaError_t launch_render_16_v2(const RenderDev &P, int num_ray_blocks, bool bf16, cudaStream_t st) {
   return bf16 ? launch_tc2<true>(P, num_ray_blocks, st) : launch_tc2<false>(P, num_ray_blocks, st);
