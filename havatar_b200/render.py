@@ -206,3 +206,76 @@ class HostRenderer:
             self.d2h_bytes += h.numel() * 4
         torch.cuda.current_stream(self.dev).synchronize()
         return self._host_out
+
+
+class PipelinedHostRenderer:
+    """HostRenderer with the three legs of a step on three CUDA streams (H2D copy engine, compute, D2H copy engine)
+    and two buffer sets, so that consecutive frames overlap: while frame i renders, frame i+1's inputs upload and
+    frame i-1's maps download.  Every frame still pays its own host->device and device->host copies.
+
+        r = PipelinedHostRenderer(weights, wvol, 64)
+        for frame in frames:
+            done = r.submit(**frame)          # returns the result of the frame submitted one call earlier (or None)
+        last = r.drain()
+    Results are dicts of pinned CPU tensors that stay valid until two more frames have been submitted."""
+
+    DEPTH = 2
+
+    def __init__(self, weights, wvol, num_coarse, num_fine=0, boxes=None, precision="fp16", device="cuda"):
+        self.dev = torch.device(device)
+        self.weights = {k: torch.as_tensor(v).to(self.dev, torch.float32).contiguous() for k, v in weights.items()}
+        self.wvol = torch.as_tensor(wvol).to(self.dev, torch.float32).contiguous()
+        self.num_coarse, self.num_fine, self.boxes, self.precision = num_coarse, num_fine, boxes, precision
+        self.s_h2d, self.s_comp, self.s_d2h = (torch.cuda.Stream(self.dev) for _ in range(3))
+        self.slots = [dict(inp={}, out=None, host=None, ev_in=torch.cuda.Event(), ev_comp=torch.cuda.Event(),
+                           ev_out=torch.cuda.Event(), busy=False) for _ in range(self.DEPTH)]
+        self.i = 0
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def submit(self, ray_batch, background_prior, inv_head_T, planes, **rand):
+        sl = self.slots[self.i % self.DEPTH]
+        prev = self.slots[(self.i - 1) % self.DEPTH] if self.i > 0 else None
+        self.h2d_bytes = self.d2h_bytes = 0
+        host_in = dict(ray_batch=ray_batch, background_prior=background_prior, inv_head_T=inv_head_T, planes=planes)
+        host_in.update({k: v for k, v in rand.items() if v is not None})
+        with torch.cuda.stream(self.s_h2d):
+            if sl["busy"]:
+                self.s_h2d.wait_event(sl["ev_comp"])          # the render that last read these staging buffers
+            for k, h in host_in.items():
+                buf = sl["inp"].get(k)
+                if buf is None or buf.shape != h.shape:
+                    buf = sl["inp"][k] = torch.empty(h.shape, dtype=torch.float32, device=self.dev)
+                buf.copy_(h, non_blocking=True)
+                self.h2d_bytes += h.numel() * 4
+            sl["ev_in"].record(self.s_h2d)
+        with torch.cuda.stream(self.s_comp):
+            self.s_comp.wait_event(sl["ev_in"])
+            if sl["busy"]:
+                self.s_comp.wait_event(sl["ev_out"])          # the download that last read these output buffers
+            a = sl["inp"]
+            sl["out"] = render_rays(a["ray_batch"], a["background_prior"], a["inv_head_T"], a["planes"], self.wvol,
+                                    self.weights, self.num_coarse, self.num_fine, boxes=self.boxes, precision=self.precision,
+                                    out=sl["out"], **{k: a[k] for k in rand if rand[k] is not None})
+            sl["ev_comp"].record(self.s_comp)
+        with torch.cuda.stream(self.s_d2h):
+            self.s_d2h.wait_event(sl["ev_comp"])
+            if sl["host"] is None or sl["host"]["rgb_coarse"].shape != sl["out"].rgb_coarse.shape:
+                sl["host"] = {k: torch.empty(v.shape, dtype=torch.float32, pin_memory=True)
+                              for k, v in sl["out"]._asdict().items() if v is not None}
+            for k, h in sl["host"].items():
+                h.copy_(getattr(sl["out"], k), non_blocking=True)
+                self.d2h_bytes += h.numel() * 4
+            sl["ev_out"].record(self.s_d2h)
+        sl["busy"] = True
+        self.i += 1
+        if prev is not None:
+            prev["ev_out"].synchronize()
+            return prev["host"]
+        return None
+
+    def drain(self):
+        if self.i == 0:
+            return None
+        sl = self.slots[(self.i - 1) % self.DEPTH]
+        sl["ev_out"].synchronize()
+        return sl["host"]
