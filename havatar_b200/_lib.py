@@ -35,6 +35,16 @@ class RenderArgs(C.Structure):
     ]
 
 
+class ConvArgs(C.Structure):
+    """hav_conv_args (include/havatar_b200.h)."""
+    _fields_ = [
+        ("struct_bytes", C.c_uint32), ("precision", C.c_int32), ("batch", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32),
+        ("in_h", C.c_int32), ("in_w", C.c_int32), ("ksize", C.c_int32), ("up", C.c_int32), ("down", C.c_int32),
+        ("act", C.c_int32), ("noise_per_sample", C.c_int32), ("noise_weight", C.c_float),
+        ("x", _fp), ("wpack", _fp), ("in_scale", _fp), ("out_scale", _fp), ("noise", _fp), ("bias", _fp), ("out", _fp),
+    ]
+
+
 # symbol -> (restype, argtypes); tests check that every one of these is exported
 SIGNATURES = {
     "hav_abi_version": (C.c_int, []),
@@ -44,6 +54,10 @@ SIGNATURES = {
     "hav_upfirdn2d": (C.c_int, [_fp, _fp, _fp] + [C.c_int] * 14 + [_fp]),
     "hav_render_workspace_bytes": (C.c_uint64, [C.POINTER(RenderArgs)]),
     "hav_render_forward": (C.c_int, [C.POINTER(RenderArgs), _fp]),
+    "hav_conv_wpack_bytes": (C.c_uint64, [C.c_int, C.c_int, C.c_int]),
+    "hav_conv_pack_weights": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, _fp]),
+    "hav_modconv_demod": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _fp]),
+    "hav_conv2d_forward": (C.c_int, [C.POINTER(ConvArgs), _fp]),
     "hav_get_rays": (C.c_int, [_fp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
                                C.c_float, _fp]),
 }

@@ -1,0 +1,108 @@
+"""Host side of the tensor-core convolution (C ABI: hav_conv2d_forward, hav_conv_pack_weights, hav_modconv_demod).
+
+conv2d() is ModulatedConv2d.forward / EqualConv2d.forward of the reference (model/styleUnet.py:222-297, :108-118)
+with the per-layer elementwise work of StyledConv / ToRGB / ConvLayer fused into the same launch.  Forward only (inference);
+torch is used for device memory and streams.  No CPU fallback."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+class PackedConvWeight:
+    """16-bit weight image of one convolution in the kernel's shared-memory order (hav_conv_pack_weights)."""
+
+    def __init__(self, data, cout, cin, ksize, precision):
+        self.data, self.cout, self.cin, self.ksize, self.precision = data, cout, cin, ksize, precision
+
+
+def _check(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32:
+        raise _lib.HavError("%s must be a float32 CUDA tensor (havatar_b200 has no CPU path)" % name)
+    return t.detach().contiguous()
+
+
+def pack_weights(weight, scale=1.0, flip=False, transpose_io=False, precision="fp16"):
+    """weight [Cout,Cin,k,k] (or [Cin,Cout,k,k] with transpose_io) -> PackedConvWeight holding scale * weight."""
+    L = _lib.lib()
+    w = _check(weight, "weight")
+    if w.dim() != 4 or w.shape[2] != w.shape[3]:
+        raise _lib.HavError("weight must be [Cout,Cin,k,k]")
+    cout, cin = (int(w.shape[1]), int(w.shape[0])) if transpose_io else (int(w.shape[0]), int(w.shape[1]))
+    k = int(w.shape[2])
+    nbytes = int(L.hav_conv_wpack_bytes(cout, cin, k))
+    if nbytes == 0:
+        raise _lib.HavError("unsupported convolution shape (ksize must be 1 or 3)")
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    with torch.cuda.device(w.device):
+        st = torch.cuda.current_stream(w.device).cuda_stream
+        _lib.check(L.hav_conv_pack_weights(C.c_void_p(buf.data_ptr()), C.c_void_p(w.data_ptr()), cout, cin, k, float(scale),
+                                           int(bool(flip)), int(bool(transpose_io)), _lib.PRECISIONS[precision], C.c_void_p(st)),
+                   "hav_conv_pack_weights")
+    return PackedConvWeight(buf, cout, cin, k, precision)
+
+
+def modconv_demod(weight, style, scale, eps=1e-8):
+    """rsqrt(sum((scale * weight * style)^2) + eps) -> [B,Cout]  (model/styleUnet.py:256-258)."""
+    L = _lib.lib()
+    w, s = _check(weight, "weight"), _check(style, "style")
+    cout, cin, k = int(w.shape[0]), int(w.shape[1]), int(w.shape[2])
+    if s.dim() != 2 or s.shape[1] != cin:
+        raise _lib.HavError("style must be [B,Cin]")
+    out = torch.empty((s.shape[0], cout), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        st = torch.cuda.current_stream(w.device).cuda_stream
+        _lib.check(L.hav_modconv_demod(C.c_void_p(out.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(s.data_ptr()),
+                                       int(s.shape[0]), cout, cin, k, float(scale), float(eps), C.c_void_p(st)), "hav_modconv_demod")
+    return out
+
+
+def conv2d(x, packed, in_scale=None, out_scale=None, noise=None, noise_weight=0.0, bias=None, act=False, up=1, down=1):
+    """out = act(conv(x * in_scale[:, :, None, None], W) * out_scale[:, :, None, None] + noise_weight * noise + bias).
+    up=2: conv_transpose2d(stride 2, pad 0) (pack the weight with flip=True); down=2: stride 2, pad 0; else pad k//2."""
+    L = _lib.lib()
+    x = _check(x, "x")
+    B, cin, H, W = [int(v) for v in x.shape]
+    if cin != packed.cin:
+        raise _lib.HavError("x has %d channels, the packed weight expects %d" % (cin, packed.cin))
+    k = packed.ksize
+    if up == 2:
+        Ho, Wo = 2 * H - 1 + k - 1, 2 * W - 1 + k - 1
+    elif down == 2:
+        Ho, Wo = (H - k) // 2 + 1, (W - k) // 2 + 1
+    else:
+        Ho, Wo = H, W
+    a = _lib.ConvArgs()
+    a.struct_bytes = C.sizeof(_lib.ConvArgs)
+    a.precision = _lib.PRECISIONS[packed.precision]
+    a.batch, a.cin, a.cout, a.in_h, a.in_w = B, cin, packed.cout, H, W
+    a.ksize, a.up, a.down, a.act = k, int(up), int(down), int(bool(act))
+    keep = [x, packed.data]
+    a.x, a.wpack = C.c_void_p(x.data_ptr()), C.c_void_p(packed.data.data_ptr())
+    for name, t, shape in (("in_scale", in_scale, (B, cin)), ("out_scale", out_scale, (B, packed.cout)), ("bias", bias, None)):
+        if t is not None:
+            t = _check(t, name)
+            if shape is not None and tuple(t.shape) != shape:
+                raise _lib.HavError("%s must be %s" % (name, shape))
+            if name == "bias" and t.numel() != packed.cout:
+                raise _lib.HavError("bias must have Cout elements")
+            keep.append(t)
+            setattr(a, name, C.c_void_p(t.data_ptr()))
+    if noise is not None:
+        nz = _check(noise, "noise")
+        if nz.numel() == Ho * Wo:
+            a.noise_per_sample = 0
+        elif nz.numel() == B * Ho * Wo:
+            a.noise_per_sample = 1
+        else:
+            raise _lib.HavError("noise must be [1 or B,1,%d,%d]" % (Ho, Wo))
+        a.noise, a.noise_weight = C.c_void_p(nz.data_ptr()), float(noise_weight)
+        keep.append(nz)
+    out = torch.empty((B, packed.cout, Ho, Wo), dtype=torch.float32, device=x.device)
+    a.out = C.c_void_p(out.data_ptr())
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(L.hav_conv2d_forward(C.byref(a), C.c_void_p(st)), "hav_conv2d_forward")
+    del keep
+    return out

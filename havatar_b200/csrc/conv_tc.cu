@@ -1,0 +1,343 @@
+// Tensor-core 2-D convolution for the StyleUNet blocks (model/styleUnet.py): ModulatedConv2d (:165-297), EqualConv2d
+// (:88-123), with the modulation / demodulation / noise / bias / leaky-relu of StyledConv (:565-599), ToRGB (:602-628)
+// and ConvLayer (:326-368) fused around one implicit GEMM on tcgen05.
+//
+// Formulation (the reference's own non-fused branch, styleUnet.py:225-251): the modulated convolution
+//     y[b] = conv(x[b], scale * W * s[b]) * demod[b]          is computed as
+//     y[b, co] = demod[b, co] * sum_{ci,kh,kw} (scale * W[co,ci,kh,kw]) * (s[b,ci] * x[b,ci,...])
+// i.e. ONE shared fp16 weight matrix for the whole batch (no per-sample [B*Cout,Cin,k,k] weights, no grouped conv),
+// s applied while the input tile is staged, demod applied in the epilogue.
+//
+// Implicit GEMM: M = 128 output positions (a 16 x 8 patch), N = up to 128 output channels, K = Cin * k * k.  The input
+// patch with its halo is staged ONCE per 64-channel block into shared memory as [Cin/8][18 x 10 pixels][8] fp16; the
+// A operand of tap (kh,kw) is that same buffer seen through a UMMA descriptor whose start address is shifted by
+// (kh * 10 + kw) pixels and whose 8-row groups (one image row of the patch) are 10 pixels apart -- no im2col copy.
+// Weights arrive per (tap, channel block) as 16 KB bulk copies (cp.async.bulk + mbarrier) from a pre-packed image.
+// up = 2 (conv_transpose2d stride 2, :264-277) runs as the stride-1 convolution of the zero-inserted input with the
+// flipped kernel; down = 2 (:279-287, after the blur) computes stride-1 positions and stores the even ones.  Both
+// waste 4x MMA work on those layers -- polyphase variants are the next step.
+#include "tc_common.cuh"
+
+namespace hav {
+namespace conv {
+
+using namespace tc;
+
+constexpr int kTileH = 16, kTileW = 8;            // output patch = 128 GEMM rows, row m = (m / 8, m % 8)
+constexpr int kCinBlk = 64;                       // channels per staged block (4 K-steps of 16)
+constexpr int kNTileMax = 128;
+constexpr int kBStages = 4;
+constexpr int kBSlotBytes = kNTileMax * kCinBlk * 2;   // 16 KB
+constexpr int kMaxHaloPx = (kTileH + 2) * (kTileW + 2);   // 180
+constexpr int kASlotBytes = (kCinBlk / 8) * kMaxHaloPx * 16;   // 23040
+constexpr int kSmB = 0;
+constexpr int kSmA = kSmB + kBStages * kBSlotBytes;
+constexpr int kSmBar = kSmA + 2 * kASlotBytes;
+constexpr int kSmemBytes = kSmBar + 128;
+constexpr int kThreads = 128;
+
+struct ConvDev {
+  int B, Cin, Cout, H, W, Ho, Wo, k, up, down, pad, act;
+  int n_tile, n_tiles, kblocks, tiles_x, tiles_y;
+  const float *x, *in_scale, *out_scale, *noise, *bias;
+  const uint8_t *wpack;
+  float *out;
+  float noise_weight;
+  int noise_bstride;   // 0 = one noise image broadcast over the batch
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// weights [Cout,Cin,k,k] fp32 -> per (n tile, channel block, tap): [8 chunks][n_tile rows][8] fp16, value scale * w
+// (flipped in kh,kw when flip != 0: the transposed convolution).  Channels / rows beyond Cin / Cout are zero.
+template <bool kBF16>
+__global__ void pack_conv_weights_kernel(const float *__restrict__ w, uint16_t *__restrict__ out, int Cout, int Cin, int k,
+                                         int n_tile, int n_tiles, int kblocks, float scale, int flip, int transpose_io) {
+  const int taps = k * k;
+  const long total = (long)n_tiles * kblocks * taps * (kCinBlk / 8) * n_tile * 8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int e = r % 8; r /= 8;
+    const int n = r % n_tile; r /= n_tile;
+    const int chunk = r % (kCinBlk / 8); r /= (kCinBlk / 8);
+    const int tap = r % taps; r /= taps;
+    const int kb = r % kblocks; r /= kblocks;
+    const int nt = (int)r;
+    const int co = nt * n_tile + n, ci = kb * kCinBlk + chunk * 8 + e;
+    int kh = tap / k, kw = tap % k;
+    if (flip) kh = k - 1 - kh, kw = k - 1 - kw;
+    float v = 0.0f;
+    if (co < Cout && ci < Cin) v = scale * (transpose_io ? w[(((long)ci * Cout + co) * k + kh) * k + kw] : w[(((long)co * Cin + ci) * k + kh) * k + kw]);
+    out[i] = kBF16 ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
+  }
+}
+
+// demod[b,co] = rsqrt(sum_{ci,kh,kw} (scale * W[co,ci,kh,kw] * s[b,ci])^2 + eps)   (styleUnet.py:256-258)
+__global__ void __launch_bounds__(128) modconv_demod_kernel(const float *__restrict__ w, const float *__restrict__ s,
+                                                            float *__restrict__ demod, int Cout, int Cin, int kk, float scale,
+                                                            float eps) {
+  const int co = blockIdx.x, b = blockIdx.y;
+  float acc = 0.0f;
+  for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) {
+    const float *wp = w + ((long)co * Cin + ci) * kk;
+    float q = 0.0f;
+    for (int t = 0; t < kk; ++t) q = fmaf(wp[t], wp[t], q);
+    const float sv = s[(long)b * Cin + ci] * scale;
+    acc = fmaf(q, sv * sv, acc);
+  }
+  __shared__ float red[4];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) demod[(long)b * Cout + co] = rsqrtf(red[0] + red[1] + red[2] + red[3] + eps);
+}
+
+template <bool kBF16>
+__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvDev P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_bfull = smem_base + kSmBar, bar_bfree = bar_bfull + kBStages * 8, bar_afree = bar_bfree + kBStages * 8,
+                 bar_acc = bar_afree + 16;
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kSmBar + 120);
+
+  // tile coordinates: blockIdx.x = spatial tile (b, ty, tx), blockIdx.y = output-channel tile
+  const int nt = blockIdx.y;
+  int sp = blockIdx.x;
+  const int tx = sp % P.tiles_x; sp /= P.tiles_x;
+  const int ty = sp % P.tiles_y;
+  const int b = sp / P.tiles_y;
+  const int vy0 = ty * kTileH, vx0 = tx * kTileW;     // stride-1 output positions of this tile
+  const int hw = kTileW + P.k - 1, hh = kTileH + P.k - 1, halo_px = hh * hw;
+  const int chunk_bytes = halo_px * 16;
+  const int taps = P.k * P.k;
+  const int total_steps = P.kblocks * taps;
+  const uint32_t b_bytes = (uint32_t)P.n_tile * kCinBlk * 2;
+
+  if (warp_u == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + kSmBar + 120), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 32) {
+    for (int i = 0; i < kBStages; ++i) mbar_init(bar_bfull + i * 8, 1), mbar_init(bar_bfree + i * 8, 1);
+    mbar_init(bar_afree, 1), mbar_init(bar_afree + 8, 1), mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  const uint8_t *wsrc = P.wpack + (size_t)nt * P.kblocks * taps * b_bytes;
+  // ---- prologue: the first weight slices are on their way before any staging starts
+  if (tid == 0) {
+    for (int i = 0; i < kBStages && i < total_steps; ++i) {
+      mbar_expect_tx(bar_bfull + i * 8, b_bytes);
+      bulk_g2s(smem_base + kSmB + i * kBSlotBytes, wsrc + (size_t)i * b_bytes, b_bytes, bar_bfull + i * 8);
+    }
+  }
+  const uint32_t idesc = instr_desc(P.n_tile, kBF16);
+  const float *xb = P.x + (size_t)b * P.Cin * P.H * P.W;
+
+  for (int kb = 0; kb < P.kblocks; ++kb) {
+    uint8_t *A = smem + kSmA + (kb & 1) * kASlotBytes;
+    if (kb >= 2) mbar_wait(bar_afree + (kb & 1) * 8, ((kb - 2) >> 1) & 1);   // MMAs of block kb-2 are done with this buffer
+    // ---- stage the halo patch of 64 channels: item = (8-channel chunk, halo pixel), modulation applied on the way in
+    for (int it = tid; it < 8 * halo_px; it += kThreads) {
+      const int chunk = it / halo_px, hp = it - chunk * halo_px;
+      const int py = hp / hw, px = hp - py * hw;
+      int Y = vy0 + py - P.pad, X = vx0 + px - P.pad;
+      bool ok = Y >= 0 && X >= 0;
+      if (P.up == 2) {
+        ok = ok && !(Y & 1) && !(X & 1);
+        Y >>= 1, X >>= 1;
+      }
+      ok = ok && Y < P.H && X < P.W;
+      const int c0 = kb * kCinBlk + chunk * 8;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = c0 + e;
+        float t = 0.0f;
+        if (ok && c < P.Cin) {
+          t = __ldg(xb + ((size_t)c * P.H + Y) * P.W + X);
+          if (P.in_scale != nullptr) t *= __ldg(P.in_scale + (size_t)b * P.Cin + c);
+        }
+        v[e] = t;
+      }
+      *reinterpret_cast<uint4 *>(A + chunk * chunk_bytes + hp * 16) =
+          make_uint4(pack2<kBF16>(v[0], v[1]), pack2<kBF16>(v[2], v[3]), pack2<kBF16>(v[4], v[5]), pack2<kBF16>(v[6], v[7]));
+    }
+    fence_async_smem();
+    __syncthreads();
+    // ---- one elected thread of warp 0: 9 taps x 4 K-steps on this block, refilling the weight ring as slots drain
+    if (warp_u == 0) {
+      if (elect_one()) {
+        tc_fence_after();
+        const uint32_t A_addr = smem_base + kSmA + (kb & 1) * kASlotBytes;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int step = kb * taps + tap, slot = step % kBStages;
+          mbar_wait(bar_bfull + slot * 8, (step / kBStages) & 1);
+          tc_fence_after();
+          const int kh = tap / P.k, kw = tap - kh * P.k;
+          const uint32_t a0 = A_addr + (kh * hw + kw) * 16, b0 = smem_base + kSmB + slot * kBSlotBytes;
+#pragma unroll
+          for (int j = 0; j < kCinBlk / 16; ++j)
+            umma_ss(tmem_acc, smem_desc(a0 + 2 * j * chunk_bytes, chunk_bytes, hw * 16),
+                    smem_desc(b0 + 2 * j * P.n_tile * 16, P.n_tile * 16, 128), idesc, (step | j) != 0);
+          umma_commit(bar_bfree + slot * 8);
+          // refill the slot of the PREVIOUS step (its MMAs have most likely drained by now) with the slice
+          // kBStages steps after it, so one tap of MMAs always stays queued behind the one that is running
+          const int prev = step - 1, nxt = prev + kBStages;
+          if (prev >= 0 && nxt < total_steps) {
+            const int ps = prev % kBStages;
+            mbar_wait(bar_bfree + ps * 8, (prev / kBStages) & 1);
+            mbar_expect_tx(bar_bfull + ps * 8, b_bytes);
+            bulk_g2s(smem_base + kSmB + ps * kBSlotBytes, wsrc + (size_t)nxt * b_bytes, b_bytes, bar_bfull + ps * 8);
+          }
+        }
+        umma_commit(bar_afree + (kb & 1) * 8);
+        if (kb == P.kblocks - 1) umma_commit(bar_acc);
+      }
+      __syncwarp();
+    }
+  }
+  // ---- epilogue: row m = output position (vy0 + m/8, vx0 + m%8); demod, noise, bias, leaky-relu, NCHW store
+  mbar_wait(bar_acc, 0);
+  tc_fence_after();
+  {
+    const int m = tid, vy = vy0 + (m >> 3), vx = vx0 + (m & 7);
+    bool ok;
+    int oy, ox;
+    if (P.down == 2) ok = !(vy & 1) && !(vx & 1), oy = vy >> 1, ox = vx >> 1;
+    else ok = true, oy = vy, ox = vx;
+    ok = ok && oy < P.Ho && ox < P.Wo;
+    float nz = 0.0f;
+    if (ok && P.noise != nullptr) nz = P.noise_weight * __ldg(P.noise + (size_t)b * P.noise_bstride + (size_t)oy * P.Wo + ox);
+    const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16);
+    const size_t plane = (size_t)P.Ho * P.Wo;
+    float *ob = P.out + ((size_t)b * P.Cout) * plane + (size_t)oy * P.Wo + ox;
+    for (int c0 = 0; c0 < P.n_tile; c0 += 16) {
+      uint32_t r[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(trow + c0));
+      tmem_wait_ld();
+      if (ok) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int co = nt * P.n_tile + c0 + j;
+          if (co < P.Cout) {
+            float v = __uint_as_float(r[j]);
+            if (P.out_scale != nullptr) v *= __ldg(P.out_scale + (size_t)b * P.Cout + co);
+            v += nz;
+            if (P.bias != nullptr) v += __ldg(P.bias + co);
+            if (P.act) v = (v > 0.0f ? v : 0.2f * v) * 1.41421356237309515f;
+            ob[(size_t)co * plane] = v;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_u == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(128));
+}
+
+}  // namespace conv
+}  // namespace hav
+
+using namespace hav;
+
+static int conv_n_tile(int cout) {
+  int n = (cout + 15) / 16 * 16;
+  return n < conv::kNTileMax ? n : conv::kNTileMax;
+}
+
+extern "C" uint64_t hav_conv_wpack_bytes(int cout, int cin, int ksize) {
+  if (cout < 1 || cin < 1 || (ksize != 1 && ksize != 3)) return 0;
+  const int n_tile = conv_n_tile(cout), n_tiles = (cout + n_tile - 1) / n_tile, kblocks = (cin + conv::kCinBlk - 1) / conv::kCinBlk;
+  return (uint64_t)n_tiles * kblocks * ksize * ksize * n_tile * conv::kCinBlk * 2;
+}
+
+extern "C" int hav_conv_pack_weights(void *wpack, const float *w, int cout, int cin, int ksize, float scale, int flip,
+                                     int transpose_io, int precision, void *stream) {
+  if (wpack == nullptr || w == nullptr) return HAV_E_NULL;
+  if (cout < 1 || cin < 1 || (ksize != 1 && ksize != 3)) return HAV_E_SHAPE;
+  if (precision != HAV_PREC_FP16 && precision != HAV_PREC_BF16) return HAV_E_VALUE;
+  const int n_tile = conv_n_tile(cout), n_tiles = (cout + n_tile - 1) / n_tile, kblocks = (cin + conv::kCinBlk - 1) / conv::kCinBlk;
+  if (precision == HAV_PREC_BF16)
+    conv::pack_conv_weights_kernel<true><<<296, 256, 0, (cudaStream_t)stream>>>(w, (uint16_t *)wpack, cout, cin, ksize, n_tile, n_tiles,
+                                                                                kblocks, scale, flip, transpose_io);
+  else
+    conv::pack_conv_weights_kernel<false><<<296, 256, 0, (cudaStream_t)stream>>>(w, (uint16_t *)wpack, cout, cin, ksize, n_tile, n_tiles,
+                                                                                 kblocks, scale, flip, transpose_io);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? HAV_OK : (int)e;
+}
+
+extern "C" int hav_modconv_demod(float *demod, const float *w, const float *style, int batch, int cout, int cin, int ksize,
+                                 float scale, float eps, void *stream) {
+  if (demod == nullptr || w == nullptr || style == nullptr) return HAV_E_NULL;
+  if (batch < 1 || cout < 1 || cin < 1 || ksize < 1 || batch > 65535) return HAV_E_SHAPE;
+  conv::modconv_demod_kernel<<<dim3(cout, batch), 128, 0, (cudaStream_t)stream>>>(w, style, demod, cout, cin, ksize * ksize, scale, eps);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? HAV_OK : (int)e;
+}
+
+extern "C" int hav_conv2d_forward(const hav_conv_args *a, void *stream) {
+  if (a == nullptr) return HAV_E_NULL;
+  if (a->struct_bytes != sizeof(hav_conv_args)) return HAV_E_VALUE;
+  if (a->batch < 0 || a->cin < 1 || a->cout < 1 || a->in_h < 1 || a->in_w < 1) return HAV_E_SHAPE;
+  if ((a->ksize != 1 && a->ksize != 3) || (a->up != 1 && a->up != 2) || (a->down != 1 && a->down != 2)) return HAV_E_VALUE;
+  if (a->up == 2 && (a->down == 2 || a->ksize != 3)) return HAV_E_VALUE;
+  if (a->precision != HAV_PREC_FP16 && a->precision != HAV_PREC_BF16) return HAV_E_VALUE;
+  if (a->batch == 0) return HAV_OK;
+  if (a->x == nullptr || a->wpack == nullptr || a->out == nullptr) return HAV_E_NULL;
+  conv::ConvDev P;
+  memset(&P, 0, sizeof(P));
+  P.B = a->batch, P.Cin = a->cin, P.Cout = a->cout, P.H = a->in_h, P.W = a->in_w, P.k = a->ksize, P.up = a->up, P.down = a->down;
+  P.act = a->act;
+  int vh, vw;   // stride-1 output positions
+  if (a->up == 2) {
+    P.pad = a->ksize - 1, vh = 2 * a->in_h - 1 + a->ksize - 1, vw = 2 * a->in_w - 1 + a->ksize - 1;   // conv_transpose2d, stride 2, pad 0
+    P.Ho = vh, P.Wo = vw;
+  } else if (a->down == 2) {
+    P.pad = 0, vh = a->in_h - a->ksize + 1, vw = a->in_w - a->ksize + 1;                                // stride 2, pad 0
+    if (vh < 1 || vw < 1) return HAV_E_SHAPE;
+    P.Ho = (vh + 1) / 2, P.Wo = (vw + 1) / 2;
+  } else {
+    P.pad = a->ksize / 2, vh = a->in_h, vw = a->in_w, P.Ho = vh, P.Wo = vw;
+  }
+  P.n_tile = conv_n_tile(a->cout), P.n_tiles = (a->cout + P.n_tile - 1) / P.n_tile;
+  P.kblocks = (a->cin + conv::kCinBlk - 1) / conv::kCinBlk;
+  P.tiles_x = (vw + conv::kTileW - 1) / conv::kTileW, P.tiles_y = (vh + conv::kTileH - 1) / conv::kTileH;
+  P.x = a->x, P.in_scale = a->in_scale, P.out_scale = a->out_scale, P.noise = a->noise, P.bias = a->bias;
+  P.wpack = (const uint8_t *)a->wpack, P.out = a->out, P.noise_weight = a->noise_weight;
+  P.noise_bstride = a->noise_per_sample ? P.Ho * P.Wo : 0;
+  const long sp_tiles = (long)a->batch * P.tiles_x * P.tiles_y;
+  if (sp_tiles > 2147483647L || P.n_tiles > 65535) return HAV_E_SHAPE;
+  dim3 grid((unsigned)sp_tiles, P.n_tiles);
+  cudaError_t e;
+  if (a->precision == HAV_PREC_BF16) {
+    e = cudaFuncSetAttribute(conv::conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    conv::conv_tc_kernel<true><<<grid, conv::kThreads, conv::kSmemBytes, (cudaStream_t)stream>>>(P);
+  } else {
+    e = cudaFuncSetAttribute(conv::conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    conv::conv_tc_kernel<false><<<grid, conv::kThreads, conv::kSmemBytes, (cudaStream_t)stream>>>(P);
+  }
+  e = cudaGetLastError();
+  return e == cudaSuccess ? HAV_OK : (int)e;
+}

@@ -15,6 +15,8 @@
  *   hav_render_forward   <- model/nerf_trainer.py:120-201       (Trainer.predict_and_render_radiance; the
  *                            reference has no native boundary here -- it is ~140 ATen launches per chunk)
  *   hav_get_rays         <- dataloader/data_util.py:28-56 + dataloader/dataloader.py:174-180
+ *   hav_conv2d_forward   <- model/styleUnet.py:222-297 (ModulatedConv2d.forward) and :108-118 (EqualConv2d.forward): the
+ *                            reference calls cuDNN grouped conv2d / conv_transpose2d through model/op/conv2d_gradfix.py:22-75
  *   hav_pack_planes      <- model/nerf_model.py:85 (plane stacking; layout change for the bf16 path)
  * INTEGRATION.md shows the reference-side binding for each.
  */
@@ -137,6 +139,41 @@ int hav_render_forward(const hav_render_args *args, void *stream);
  */
 int hav_get_rays(float *ray_batch, int height, int width, const float intr[4], const float c2w[12],
                  float near, float far, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-core convolution of the StyleUNet blocks: ModulatedConv2d (model/styleUnet.py:165-297) in the shared-weight
+ * formulation of its non-fused branch (:225-251), EqualConv2d (:88-123), with the surrounding per-layer elementwise work
+ * fused in: out = act( conv(x * in_scale[b,ci], W) * out_scale[b,co] + noise_weight * noise + bias[co] ).
+ *   ksize 1 or 3;  up = 2: conv_transpose2d stride 2, padding 0 (:264-270), output (2H+1) x (2W+1) for ksize 3;
+ *   down = 2: conv2d stride 2, padding 0 (:281-283);  otherwise stride 1, padding ksize/2 (:289-291).
+ *   x [B,Cin,H,W], out [B,Cout,Ho,Wo] float32 NCHW; operands are rounded to 16 bit, accumulation is fp32 (TMEM).
+ * Weights are packed once per weight update with hav_conv_pack_weights (w is [Cout,Cin,k,k], or [Cin,Cout,k,k] when
+ * transpose_io != 0; flip != 0 mirrors the taps, which is what the transposed convolution needs).
+ */
+typedef struct hav_conv_args {
+  uint32_t struct_bytes; /* = sizeof(hav_conv_args) */
+  int32_t precision;     /* HAV_PREC_FP16 or HAV_PREC_BF16: must match the packed weights */
+  int32_t batch, cin, cout, in_h, in_w;
+  int32_t ksize, up, down;
+  int32_t act;              /* 0: none, 1: leaky-relu(0.2) * sqrt(2) (model/op/fused_act.py:103-122) */
+  int32_t noise_per_sample; /* 0: noise is [1,1,Ho,Wo] broadcast over the batch, 1: [B,1,Ho,Wo] */
+  float noise_weight;       /* NoiseInjection.weight (model/styleUnet.py:300-310) */
+  const float *x;
+  const void *wpack;        /* hav_conv_wpack_bytes(cout, cin, ksize) bytes written by hav_conv_pack_weights */
+  const float *in_scale;    /* [B,Cin] modulation s, or NULL */
+  const float *out_scale;   /* [B,Cout] demodulation, or NULL */
+  const float *noise;       /* or NULL */
+  const float *bias;        /* [Cout] or NULL */
+  float *out;
+} hav_conv_args;
+
+uint64_t hav_conv_wpack_bytes(int cout, int cin, int ksize);
+int hav_conv_pack_weights(void *wpack, const float *w, int cout, int cin, int ksize, float scale, int flip, int transpose_io,
+                          int precision, void *stream);
+/* demod[b,co] = rsqrt(sum_{ci,kh,kw} (scale * w[co,ci,kh,kw] * style[b,ci])^2 + eps)   (model/styleUnet.py:256-258) */
+int hav_modconv_demod(float *demod, const float *w, const float *style, int batch, int cout, int cin, int ksize, float scale,
+                      float eps, void *stream);
+int hav_conv2d_forward(const hav_conv_args *args, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,93 @@
+"""Tensor-core convolution (hav_conv2d_forward) against a plain PyTorch fp32 reference of the same op, and the fused
+modulated form against the reference's own formulation (model/styleUnet.py:253-297 restated with torch ops).
+Operands are rounded to fp16, accumulation is fp32: tolerance 1e-2 relative to the output scale.  pytest -m gpu."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from havatar_b200 import conv
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,k", [(1, 64, 128, 32, 32, 3), (2, 512, 512, 16, 16, 3), (1, 7, 256, 40, 24, 3),
+                                              (2, 128, 12, 32, 32, 1), (1, 1024, 512, 8, 8, 3), (1, 64, 64, 13, 9, 3)])
+def test_plain_conv_matches_torch(B, Cin, Cout, H, W, k):
+    torch.manual_seed(0)
+    x = torch.randn(B, Cin, H, W, device="cuda")
+    w = torch.randn(Cout, Cin, k, k, device="cuda")
+    scale = 1 / math.sqrt(Cin * k * k)
+    bias = torch.randn(Cout, device="cuda")
+    ref = F.conv2d(x, w * scale, bias=bias, padding=k // 2)
+    got = conv.conv2d(x, conv.pack_weights(w, scale), bias=bias)
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < 1e-2
+    # bias + leaky-relu * sqrt(2) epilogue (ConvLayer: EqualConv2d -> FusedLeakyReLU, styleUnet.py:352-366)
+    ref2 = F.leaky_relu(F.conv2d(x, w * scale, padding=k // 2) + bias.view(1, -1, 1, 1), 0.2) * math.sqrt(2)
+    got2 = conv.conv2d(x, conv.pack_weights(w, scale), bias=bias, act=True)
+    assert rel_err(got2, ref2) < 1e-2
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H", [(1, 64, 64, 16), (2, 512, 256, 8), (1, 128, 128, 33)])
+def test_strided_and_transposed(B, Cin, Cout, H):
+    torch.manual_seed(1)
+    x = torch.randn(B, Cin, H, H, device="cuda")
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda")
+    scale = 1 / math.sqrt(Cin * 9)
+    ref = F.conv2d(x, w * scale, stride=2, padding=0)
+    got = conv.conv2d(x, conv.pack_weights(w, scale), down=2)
+    assert got.shape == ref.shape and rel_err(got, ref) < 1e-2
+    ref = F.conv_transpose2d(x, (w * scale).transpose(0, 1), stride=2, padding=0)
+    got = conv.conv2d(x, conv.pack_weights(w, scale, flip=True), up=2)
+    assert got.shape == ref.shape and rel_err(got, ref) < 1e-2
+
+
+@pytest.mark.parametrize("upsample", [False, True])
+@pytest.mark.parametrize("demodulate", [True, False])
+def test_modulated_conv_matches_reference_formulation(upsample, demodulate):
+    """ModulatedConv2d fused branch (styleUnet.py:253-297): per-sample weights + grouped conv, in torch fp32."""
+    torch.manual_seed(2)
+    B, Cin, Cout, H, k = 2, 128, 64, 16, 3 if demodulate else 1
+    if upsample and k == 1:
+        pytest.skip("ToRGB is never an upsampling conv")
+    x = torch.randn(B, Cin, H, H, device="cuda")
+    W = torch.randn(1, Cout, Cin, k, k, device="cuda")
+    s = torch.randn(B, Cin, device="cuda") * 0.3 + 1.0
+    scale = 1 / math.sqrt(Cin * k * k)
+    weight = scale * W * s.view(B, 1, Cin, 1, 1)
+    if demodulate:
+        demod = torch.rsqrt(weight.pow(2).sum([2, 3, 4]) + 1e-8)
+        weight = weight * demod.view(B, Cout, 1, 1, 1)
+    if upsample:
+        wt = weight.transpose(1, 2).reshape(B * Cin, Cout, k, k)
+        ref = F.conv_transpose2d(x.view(1, B * Cin, H, H), wt, padding=0, stride=2, groups=B)
+        ref = ref.view(B, Cout, ref.shape[-2], ref.shape[-1])
+    else:
+        ref = F.conv2d(x.view(1, B * Cin, H, H), weight.view(B * Cout, Cin, k, k), padding=k // 2, groups=B).view(B, Cout, H, H)
+    noise = torch.randn(1, 1, ref.shape[-2], ref.shape[-1], device="cuda")
+    bias = torch.randn(Cout, device="cuda")
+    ref = F.leaky_relu(ref + 0.37 * noise + bias.view(1, -1, 1, 1), 0.2) * math.sqrt(2)
+    d = conv.modconv_demod(W[0], s, scale) if demodulate else None
+    if demodulate:
+        assert torch.allclose(d, demod, rtol=1e-5, atol=1e-7)
+    got = conv.conv2d(x, conv.pack_weights(W[0], scale, flip=upsample), in_scale=s, out_scale=d, noise=noise, noise_weight=0.37,
+                      bias=bias, act=True, up=2 if upsample else 1)
+    assert got.shape == ref.shape and rel_err(got, ref) < 1e-2
+
+
+def test_full_size_layer_linearity():
+    """256x256, 128 -> 128 channels (the largest SWGAN_unet decoder layer at 128 -> 512): conv is linear in x."""
+    torch.manual_seed(3)
+    x1 = torch.randn(1, 128, 256, 256, device="cuda")
+    x2 = torch.randn(1, 128, 256, 256, device="cuda")
+    pw = conv.pack_weights(torch.randn(128, 128, 3, 3, device="cuda"), 1 / math.sqrt(128 * 9))
+    y = conv.conv2d(x1 + x2, pw)
+    y12 = conv.conv2d(x1, pw) + conv.conv2d(x2, pw)
+    assert rel_err(y, y12) < 5e-3
+    assert torch.isfinite(y).all()
