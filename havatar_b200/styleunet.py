@@ -1,0 +1,528 @@
+"""StyleUNet on the B200 kernels: drop-in, checkpoint-compatible mirrors of the reference's model/styleUnet.py networks.
+
+    SWGAN_unet     <- model/styleUnet.py:1190-1410  (HD upsampler, avatarHD_reenactment.py:139-167)
+    StyleGAN_zxc   <- model/styleUnet.py:631-878    (plane generators XY_gen / YZ_gen, model/nerf_model.py:39-42, :58-86)
+
+Same constructor arguments, same `forward` signatures and the same state_dict keys / shapes, so `load_state_dict` of a
+reference checkpoint works unchanged.  Forward (inference) only: every convolution runs on the tcgen05 implicit-GEMM kernel
+(havatar_b200/conv.py) in the shared-weight formulation of ModulatedConv2d's own non-fused branch (styleUnet.py:225-251),
+with modulation, demodulation, noise, bias and leaky-relu fused into that launch where the layer has no blur in between;
+blur / up / down / Haar go through the upfirdn2d kernel, the style MLP's activation through fused_bias_act.
+torch is used for parameters, device memory, concatenation and the [B,64] style MLP matmuls.  No CPU fallback.
+"""
+import math
+import random
+
+import torch
+from torch import nn
+
+from . import conv as hconv
+from .op import fused_leaky_relu, upfirdn2d
+
+
+def _fir(taps, gain=1.0):
+    k = torch.tensor(taps, dtype=torch.float32)
+    k = k[None, :] * k[:, None]
+    return k / k.sum() * gain
+
+
+class PixelNorm(nn.Module):
+    def forward(self, x):
+        return x * torch.rsqrt(torch.mean(x * x, dim=1, keepdim=True) + 1e-8)
+
+
+class Blur(nn.Module):
+    """styleUnet.py:70-86."""
+
+    def __init__(self, taps, pad, upsample_factor=1):
+        super().__init__()
+        self.register_buffer("kernel", _fir(taps, float(upsample_factor ** 2)))
+        self.pad = pad
+
+    def forward(self, x):
+        return upfirdn2d(x, self.kernel, pad=self.pad)
+
+
+class Upsample(nn.Module):
+    """styleUnet.py:28-46."""
+
+    def __init__(self, taps, factor=2):
+        super().__init__()
+        self.factor = factor
+        self.register_buffer("kernel", _fir(taps, float(factor ** 2)))
+        p = len(taps) - factor
+        self.pad = ((p + 1) // 2 + factor - 1, p // 2)
+
+    def forward(self, x):
+        return upfirdn2d(x, self.kernel, up=self.factor, down=1, pad=self.pad)
+
+
+class Downsample(nn.Module):
+    """styleUnet.py:49-67."""
+
+    def __init__(self, taps, factor=2):
+        super().__init__()
+        self.factor = factor
+        self.register_buffer("kernel", _fir(taps))
+        p = len(taps) - factor
+        self.pad = ((p + 1) // 2, p // 2)
+
+    def forward(self, x):
+        return upfirdn2d(x, self.kernel, up=1, down=self.factor, pad=self.pad)
+
+
+def _haar():
+    s = 1 / math.sqrt(2)
+    lo, hi = torch.tensor([[s, s]]), torch.tensor([[-s, s]])
+    return lo.T * lo, hi.T * lo, lo.T * hi, hi.T * hi      # ll, lh, hl, hh (styleUnet.py:371-381)
+
+
+class HaarTransform(nn.Module):
+    def __init__(self, in_channels):
+        super().__init__()
+        for n, k in zip(("ll", "lh", "hl", "hh"), _haar()):
+            self.register_buffer(n, k)
+
+    def forward(self, x):
+        return torch.cat([upfirdn2d(x, k, down=2) for k in (self.ll, self.lh, self.hl, self.hh)], 1)
+
+
+class InverseHaarTransform(nn.Module):
+    def __init__(self, in_channels):
+        super().__init__()
+        ll, lh, hl, hh = _haar()
+        for n, k in zip(("ll", "lh", "hl", "hh"), (ll, -lh, -hl, hh)):
+            self.register_buffer(n, k)
+
+    def forward(self, x):
+        parts = x.chunk(4, 1)
+        out = None
+        for p, k in zip(parts, (self.ll, self.lh, self.hl, self.hh)):
+            y = upfirdn2d(p.contiguous(), k, up=2, pad=(1, 0, 1, 0))
+            out = y if out is None else out + y
+        return out
+
+
+class _PackCache:
+    """Packed 16-bit weight image of a conv parameter, rebuilt when the parameter is modified in place or replaced."""
+
+    def __init__(self):
+        self.key, self.packed = None, None
+
+    def get(self, weight, scale, flip):
+        key = (weight.data_ptr(), weight._version, str(weight.device), flip)
+        if key != self.key:
+            w = weight.detach()
+            if w.dim() == 5:
+                w = w[0]
+            self.packed = hconv.pack_weights(w.float(), scale, flip=flip)
+            self.key = key
+        return self.packed
+
+
+class EqualConv2d(nn.Module):
+    """styleUnet.py:88-123; forward is driven by ConvLayer so that the activation fuses into the conv launch."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, stride=1, padding=0, bias=True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(out_channel, in_channel, kernel_size, kernel_size))
+        self.scale = 1 / math.sqrt(in_channel * kernel_size ** 2)
+        self.stride, self.padding = stride, padding
+        self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
+        self._cache = _PackCache()
+
+    def run(self, x, bias=None, act=False):
+        b = bias if bias is not None else self.bias
+        return hconv.conv2d(x, self._cache.get(self.weight, self.scale, False), bias=b, act=act, down=self.stride)
+
+    def forward(self, x):
+        return self.run(x)
+
+
+class _ActBias(nn.Module):
+    """FusedLeakyReLU's parameter holder (state_dict key `bias`, model/op/fused_act.py:90-104); applied inside the conv launch."""
+
+    def __init__(self, channel, bias=True):
+        super().__init__()
+        self.bias = nn.Parameter(torch.zeros(channel)) if bias else None
+
+    def forward(self, x):
+        return fused_leaky_relu(x, self.bias)
+
+
+class ConvLayer(nn.Sequential):
+    """styleUnet.py:326-368: [Blur] -> EqualConv2d -> [FusedLeakyReLU]; here blur, then ONE conv launch with bias + lrelu fused."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, downsample=False, blur_kernel=(1, 3, 3, 1), bias=True, activate=True):
+        layers = []
+        if downsample:
+            p = (len(blur_kernel) - 2) + (kernel_size - 1)
+            layers.append(Blur(list(blur_kernel), pad=((p + 1) // 2, p // 2)))
+            stride, padding = 2, 0
+        else:
+            stride, padding = 1, kernel_size // 2
+        layers.append(EqualConv2d(in_channel, out_channel, kernel_size, padding=padding, stride=stride, bias=bias and not activate))
+        if activate:
+            layers.append(_ActBias(out_channel, bias=bias))
+        super().__init__(*layers)
+        self.activate = activate
+
+    def forward(self, x):
+        mods = list(self)
+        if isinstance(mods[0], Blur):
+            x = mods[0](x)
+            mods = mods[1:]
+        act_bias = mods[1].bias if self.activate else None
+        return mods[0].run(x, bias=act_bias, act=self.activate)
+
+
+class EqualLinear(nn.Module):
+    """styleUnet.py:126-162."""
+
+    def __init__(self, in_dim, out_dim, bias=True, bias_init=0, lr_mul=1, activation=None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(out_dim, in_dim).div_(lr_mul))
+        self.bias = nn.Parameter(torch.zeros(out_dim).fill_(bias_init)) if bias else None
+        self.activation = activation
+        self.scale = (1 / math.sqrt(in_dim)) * lr_mul
+        self.lr_mul = lr_mul
+
+    def forward(self, x):
+        if self.activation:
+            return fused_leaky_relu(torch.nn.functional.linear(x, self.weight * self.scale).contiguous(), self.bias * self.lr_mul)
+        return torch.nn.functional.linear(x, self.weight * self.scale, bias=self.bias * self.lr_mul)
+
+
+class ModulatedConv2d(nn.Module):
+    """styleUnet.py:165-297.  run() adds the StyledConv / ToRGB epilogue to the same launch when no blur follows."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, style_dim, demodulate=True, upsample=False, downsample=False,
+                 blur_kernel=(1, 3, 3, 1), fused=True):
+        super().__init__()
+        if downsample:
+            raise NotImplementedError("ModulatedConv2d(downsample=True) is never instantiated by the reference networks")
+        self.eps = 1e-8
+        self.kernel_size, self.in_channel, self.out_channel = kernel_size, in_channel, out_channel
+        self.upsample, self.downsample = upsample, downsample
+        if upsample:
+            p = (len(blur_kernel) - 2) - (kernel_size - 1)
+            self.blur = Blur(list(blur_kernel), pad=((p + 1) // 2 + 1, p // 2 + 1), upsample_factor=2)
+        self.scale = 1 / math.sqrt(in_channel * kernel_size ** 2)
+        self.padding = kernel_size // 2
+        self.weight = nn.Parameter(torch.randn(1, out_channel, in_channel, kernel_size, kernel_size))
+        self.modulation = EqualLinear(style_dim, in_channel, bias_init=1)
+        self.demodulate = demodulate
+        self.fused = fused
+        self._cache = _PackCache()
+
+    def run(self, x, style, noise=None, noise_weight=0.0, bias=None, act=False):
+        s = self.modulation(style).contiguous()
+        d = hconv.modconv_demod(self.weight.detach()[0], s, self.scale, self.eps) if self.demodulate else None
+        packed = self._cache.get(self.weight, self.scale, self.upsample)
+        if not self.upsample:
+            return hconv.conv2d(x, packed, in_scale=s, out_scale=d, noise=noise, noise_weight=noise_weight, bias=bias, act=act)
+        y = self.blur(hconv.conv2d(x, packed, in_scale=s, out_scale=d, up=2))      # convT stride 2 -> 4x4 blur (:264-277)
+        if noise is not None:
+            y = y + noise_weight * noise
+        if act:
+            return fused_leaky_relu(y, bias)
+        return y if bias is None else y + bias.view(1, -1, 1, 1)
+
+    def forward(self, x, style):
+        return self.run(x, style)
+
+
+class NoiseInjection(nn.Module):
+    """styleUnet.py:300-310 (parameter holder; the addition happens in the conv epilogue)."""
+
+    def __init__(self):
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(1))
+        self._key, self._val = None, 0.0
+
+    def value(self):
+        key = (self.weight.data_ptr(), self.weight._version)
+        if key != self._key:                      # one device->host read per weight update, not per forward
+            self._val, self._key = float(self.weight.detach().cpu()), key
+        return self._val
+
+    def forward(self, image, noise=None):
+        if noise is None:
+            b, _, h, w = image.shape
+            noise = image.new_empty(b, 1, h, w).normal_()
+        return image + self.weight * noise
+
+
+class ConstantInput(nn.Module):
+    def __init__(self, channel, size=4):
+        super().__init__()
+        self.input = nn.Parameter(torch.randn(1, channel, size, size))
+
+    def forward(self, x):
+        return self.input.repeat(x.shape[0], 1, 1, 1)
+
+
+class StyledConv(nn.Module):
+    """styleUnet.py:565-599: modulated conv -> noise -> bias + leaky-relu, one launch (two + blur when upsampling)."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, style_dim, upsample=False, blur_kernel=(1, 3, 3, 1), demodulate=True):
+        super().__init__()
+        self.conv = ModulatedConv2d(in_channel, out_channel, kernel_size, style_dim, upsample=upsample, blur_kernel=blur_kernel,
+                                    demodulate=demodulate)
+        self.noise = NoiseInjection()
+        self.activate = _ActBias(out_channel)
+
+    def forward(self, x, style, noise=None):
+        if noise is None:     # fresh N(0,1) per call, like NoiseInjection.forward (:306-309)
+            r = x.shape[-1] * 2 if self.conv.upsample else x.shape[-1]
+            rh = x.shape[-2] * 2 if self.conv.upsample else x.shape[-2]
+            noise = x.new_empty(x.shape[0], 1, rh, r).normal_()
+        return self.conv.run(x, style, noise=noise, noise_weight=self.noise.value(), bias=self.activate.bias, act=True)
+
+
+class ToRGB(nn.Module):
+    """styleUnet.py:602-628."""
+
+    def __init__(self, in_channel, style_dim, out_channel=12, upsample=True, blur_kernel=(1, 3, 3, 1), use_wt=True):
+        super().__init__()
+        self.use_wt = use_wt
+        if upsample:
+            self.upsample = Upsample(list(blur_kernel))
+            if use_wt:
+                self.iwt = InverseHaarTransform(3)
+                self.dwt = HaarTransform(3)
+        self.out_channel = out_channel if use_wt else out_channel // 4
+        self.conv = ModulatedConv2d(in_channel, self.out_channel, 1, style_dim, demodulate=False)
+        self.bias = nn.Parameter(torch.zeros(1, self.out_channel, 1, 1))
+
+    def forward(self, x, style, skip=None):
+        out = self.conv.run(x, style, bias=self.bias.view(-1))
+        if skip is not None:
+            skip = self.dwt(self.upsample(self.iwt(skip))) if self.use_wt else self.upsample(skip)
+            out = out + skip
+        return out
+
+
+class ConvBlock(nn.Module):
+    def __init__(self, in_channel, out_channel, blur_kernel=(1, 3, 3, 1), downsample=True):
+        super().__init__()
+        self.conv1 = ConvLayer(in_channel, in_channel, 3)
+        self.conv2 = ConvLayer(in_channel, out_channel, 3, downsample=downsample)
+
+    def forward(self, x):
+        return self.conv2(self.conv1(x))
+
+
+class FromRGB(nn.Module):
+    """styleUnet.py:439-467."""
+
+    def __init__(self, out_channel, in_channel, downsample=True, blur_kernel=(1, 3, 3, 1), use_wt=True):
+        super().__init__()
+        self.use_wt = use_wt
+        self.downsample = downsample
+        if downsample:
+            self.downsample = Downsample(list(blur_kernel))
+            if use_wt:
+                self.iwt = InverseHaarTransform(in_channel)
+                self.dwt = HaarTransform(in_channel)
+        self.in_channel = in_channel * 4 if use_wt else in_channel
+        self.conv = ConvLayer(self.in_channel, out_channel, 1)
+
+    def forward(self, x, skip=None):
+        if self.downsample:
+            x = self.dwt(self.downsample(self.iwt(x))) if self.use_wt else self.downsample(x)
+        out = self.conv(x)
+        if skip is not None:
+            out = out + skip
+        return x, out
+
+
+_CHANNELS = lambda m: {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * m, 128: 128 * m, 256: 64 * m, 512: 32 * m, 1024: 16 * m}
+
+
+def _style_mlp(in_dim, dim, n_mlp, lr_mlp):
+    layers = [PixelNorm(), EqualLinear(in_dim, dim, lr_mul=lr_mlp, activation="fused_lrelu")]
+    layers += [EqualLinear(dim, dim, lr_mul=lr_mlp, activation="fused_lrelu") for _ in range(n_mlp - 1)]
+    return nn.Sequential(*layers)
+
+
+def _latents(styles, n_latent, inject_index):
+    """styleUnet.py:1363-1377 / :823-838: one style -> repeated; two -> mixed at inject_index."""
+    if len(styles) < 2:
+        return styles[0].unsqueeze(1).repeat(1, n_latent, 1) if styles[0].ndim < 3 else styles[0]
+    if inject_index is None:
+        inject_index = random.randint(1, n_latent - 1)
+    a = styles[0].unsqueeze(1).repeat(1, inject_index, 1)
+    b = styles[1].unsqueeze(1).repeat(1, n_latent - inject_index, 1)
+    return torch.cat([a, b], 1)
+
+
+class _CondEncoder:
+    """The shared condition-image encoder of both networks (styleUnet.py:1379-1388, :847-856)."""
+
+    @staticmethod
+    def run(net, cond_img):
+        cond_out = net.conv_in(cond_img)
+        feats = [cond_out]
+        for from_rgb, cond_conv in zip(net.from_rgbs, net.cond_convs):
+            cond_img, cond_out = from_rgb(cond_img, cond_out)
+            cond_out = cond_conv(cond_out)
+            feats.append(cond_out)
+        return feats
+
+
+class SWGAN_unet(nn.Module):
+    """styleUnet.py:1190-1410."""
+
+    def __init__(self, inp_size, inp_ch, out_ch, out_size, style_dim, n_mlp, middle_size=8, c_dim=0, channel_multiplier=2,
+                 blur_kernel=(1, 3, 3, 1), lr_mlp=0.01):
+        super().__init__()
+        self.inp_size, self.style_dim = inp_size, style_dim
+        self.middle_log_size = int(math.log(middle_size, 2))
+        self.style = _style_mlp(style_dim + c_dim, style_dim, n_mlp, lr_mlp)
+        self.channels = _CHANNELS(channel_multiplier)
+        self.log_size = int(math.log(out_size, 2)) - 1
+        in_channel = self.channels[inp_size // 2]
+        self.from_rgbs, self.cond_convs, self.comb_convs = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+        self.comb_convs.append(ConvLayer(in_channel * 2, in_channel, 3))
+        self.conv_in = ConvLayer(inp_ch, in_channel, 3, downsample=True)
+        for i in range(int(math.log(inp_size, 2)) - 2, self.middle_log_size - 1, -1):
+            out_channel = self.channels[2 ** i]
+            self.from_rgbs.append(FromRGB(in_channel, inp_ch, downsample=True, use_wt=False))
+            self.cond_convs.append(ConvBlock(in_channel, out_channel, blur_kernel))
+            self.comb_convs.append(ConvLayer(out_channel * (2 if i > self.middle_log_size else 1), out_channel, 3))
+            in_channel = out_channel
+        self.convs, self.to_rgbs, self.noises = nn.ModuleList(), nn.ModuleList(), nn.Module()
+        in_channel = self.channels[middle_size]
+        self.num_layers = (self.log_size - self.middle_log_size) * 2
+        for layer_idx in range(self.num_layers):
+            res = (layer_idx + 8) // 2
+            self.noises.register_buffer(f"noise_{layer_idx}", torch.randn(1, 1, 2 ** res, 2 ** res))
+        for i in range(self.middle_log_size + 1, self.log_size + 1):
+            out_channel = self.channels[2 ** i]
+            self.convs.append(StyledConv(in_channel, out_channel, 3, style_dim, upsample=True, blur_kernel=blur_kernel))
+            self.convs.append(StyledConv(out_channel, out_channel, 3, style_dim, blur_kernel=blur_kernel))
+            self.to_rgbs.append(ToRGB(in_channel=out_channel, style_dim=style_dim, out_channel=out_ch * 4))
+            in_channel = out_channel
+        self.iwt = InverseHaarTransform(3)
+        self.n_latent = self.log_size * 2 - (self.middle_log_size * 2 - 1) + 1
+
+    def make_noise(self, device, zero_noise=False):
+        f = torch.zeros if zero_noise else torch.randn
+        return [f(1, 1, 2 ** i, 2 ** i, device=device) for i in range(self.middle_log_size + 1, self.log_size + 1) for _ in range(2)]
+
+    def get_latent(self, x):
+        return self.style(x)
+
+    @torch.no_grad()
+    def forward(self, styles, condition_img, cond=None, return_latents=False, inject_index=None, truncation=1,
+                truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True):
+        if not input_is_latent:
+            styles = [self.style(s if cond is None else torch.cat([s, cond], dim=-1)) for s in styles]
+        if noise is None:
+            noise = [None] * self.num_layers if randomize_noise else [getattr(self.noises, f"noise_{i}") for i in range(self.num_layers)]
+        if truncation < 1:
+            styles = [truncation_latent + truncation * (s - truncation_latent) for s in styles]
+        latent = _latents(styles, self.n_latent, inject_index)
+        feats = _CondEncoder.run(self, condition_img)
+        i, skip, out = 0, None, None
+        for conv1, conv2, n1, n2, to_rgb in zip(self.convs[::2], self.convs[1::2], noise[::2], noise[1::2], self.to_rgbs):
+            if i == 0:
+                out = self.comb_convs[-1](feats[-1])
+            elif i < 2 * len(self.comb_convs):
+                out = self.comb_convs[-1 - (i // 2)](torch.cat([out, feats[-1 - (i // 2)]], dim=1))
+            out = conv1(out, latent[:, i], noise=n1)
+            out = conv2(out, latent[:, i + 1], noise=n2)
+            skip = to_rgb(out, latent[:, i + 2], skip)
+            i += 2
+        return self.iwt(skip)
+
+
+class StyleGAN_zxc(nn.Module):
+    """styleUnet.py:631-878, the configuration the plane generators use (model/nerf_model.py:39-42): condition-image
+    encoder (inp_size > 0) and no_skip=True (1x1 conv_out instead of the ToRGB pyramid)."""
+
+    def __init__(self, out_ch, out_size, style_dim, mlp_dim=32, n_mlp=0, middle_size=8, inject_layers=(), zero_latent=False,
+                 zero_noise=False, no_skip=False, channel_multiplier=2, blur_kernel=(1, 3, 3, 1), lr_mlp=0.01, n_latent=None,
+                 inp_size=0, inp_ch=0, pass_kernel=False):
+        super().__init__()
+        if not (inp_size > 0 and no_skip):
+            raise NotImplementedError("only the plane-generator configuration (inp_size > 0, no_skip=True) is built")
+        self.no_skip, self.style_dim = no_skip, mlp_dim
+        self.middle_log_size = int(math.log(middle_size, 2))
+        self.cond_img_enc, self.n_mlp = True, n_mlp
+        if n_mlp > 0:
+            self.style = _style_mlp(style_dim, mlp_dim, n_mlp, lr_mlp)
+        self.channels = _CHANNELS(channel_multiplier)
+        self.log_size = int(math.log(out_size, 2))
+        in_channel = self.channels[inp_size // 2]
+        self.from_rgbs, self.cond_convs, self.comb_convs = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+        self.comb_convs.append(ConvLayer(in_channel * 2, in_channel, 3))
+        self.conv_in = ConvLayer(inp_ch, in_channel, 3, downsample=True)
+        for i in range(int(math.log(inp_size, 2)) - 2, self.middle_log_size, -1):
+            out_channel = self.channels[2 ** i]
+            self.from_rgbs.append(FromRGB(in_channel, inp_ch, downsample=True, use_wt=False))
+            self.cond_convs.append(ConvBlock(in_channel, out_channel, blur_kernel))
+            self.comb_convs.append(ConvLayer(out_channel * 2, out_channel, 3))
+            in_channel = out_channel
+        self.convs, self.to_rgbs, self.noises = nn.ModuleList(), nn.ModuleList(), nn.Module()
+        self.input = ConstantInput(self.channels[middle_size], size=middle_size)
+        self.conv1 = StyledConv(self.channels[middle_size], self.channels[middle_size], 3, self.style_dim, blur_kernel=blur_kernel)
+        self.conv_out = ConvLayer(self.channels[out_size], out_ch, 1)
+        in_channel = self.channels[middle_size]
+        self.num_layers = (self.log_size - self.middle_log_size) * 2 + 1
+        for layer_idx in range(self.num_layers):
+            res = (layer_idx + 8) // 2
+            self.noises.register_buffer(f"noise_{layer_idx}", torch.randn(1, 1, 2 ** res, 2 ** res))
+        for i in range(self.middle_log_size + 1, self.log_size + 1):
+            out_channel = self.channels[2 ** i]
+            self.convs.append(StyledConv(in_channel, out_channel, 3, self.style_dim, upsample=True, blur_kernel=blur_kernel))
+            self.convs.append(StyledConv(out_channel, out_channel, 3, self.style_dim, blur_kernel=blur_kernel))
+            self.to_rgbs.append(None)
+            in_channel = out_channel
+        self.n_latent = self.log_size * 2 - (self.middle_log_size * 2 - 1) + 1 if n_latent is None else n_latent
+        # zero_noise: every layer's noise is zero except the first, a fixed draw that is NOT in the state_dict (:746-751)
+        self.zero_noise = self.make_noise(zero_noise=True) if zero_noise else None
+        if zero_latent:
+            self.register_buffer("zero_latents", torch.zeros(1, self.n_latent, self.style_dim))
+        else:
+            self.zero_latents = None
+
+    def make_noise(self, zero_noise=False):
+        f = torch.zeros if zero_noise else torch.randn
+        noises = [torch.randn(1, 1, 2 ** self.middle_log_size, 2 ** self.middle_log_size)]
+        for i in range(self.middle_log_size + 1, self.log_size + 1):
+            noises += [f(1, 1, 2 ** i, 2 ** i), f(1, 1, 2 ** i, 2 ** i)]
+        return noises
+
+    @torch.no_grad()
+    def forward(self, styles, cond_feats, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
+                input_is_latent=False, noise=None, randomize_noise=True, **kwargs):
+        dev = cond_feats.device
+        batch = cond_feats.shape[0]
+        if self.zero_latents is None:
+            if not input_is_latent:
+                styles = [self.style(s) for s in styles]
+            if truncation < 1:
+                styles = [truncation_latent + truncation * (s - truncation_latent) for s in styles]
+            latent = _latents(styles, self.n_latent, inject_index)
+        else:
+            latent = self.zero_latents.expand(batch, -1, -1)
+        if self.zero_noise is None:
+            if noise is None:
+                noise = [None] * self.num_layers if randomize_noise else [getattr(self.noises, f"noise_{i}") for i in range(self.num_layers)]
+        else:
+            if any(n.device != dev for n in self.zero_noise):
+                self.zero_noise = [n.to(dev) for n in self.zero_noise]
+            noise = self.zero_noise
+        feats = _CondEncoder.run(self, cond_feats)
+        out = self.conv1(self.input(latent), latent[:, 0], noise=noise[0])
+        i = 1
+        for conv1, conv2, n1, n2 in zip(self.convs[::2], self.convs[1::2], noise[1::2], noise[2::2]):
+            if 1 < i <= 2 * len(feats) + 1:
+                out = self.comb_convs[-(i // 2)](torch.cat([out, feats[-(i // 2)]], dim=1))
+            out = conv1(out, latent[:, i], noise=n1)
+            out = conv2(out, latent[:, i + 1], noise=n2)
+            i += 2
+        image = self.conv_out(out)
+        return (image, latent) if return_latents else (image, None)

@@ -125,3 +125,39 @@ def randoms(batch, rays, num_coarse, num_fine, seed=7, noise_std=0.1):
         "noise_coarse": (n_coarse * F32(noise_std)).astype(F32),  # ... * radiance_field_noise_std
         "noise_fine": (n_fine * F32(noise_std)).astype(F32),
     }
+
+
+# ------------------------------------------------------------------------------------------------
+# StyleUNet fixtures: order-independent, name-keyed parameter values so that the reference module (built by
+# oracle/gen_golden.py) and havatar_b200.styleunet get bit-identical weights without shipping a state_dict
+# ------------------------------------------------------------------------------------------------
+_FIXED = (".kernel", ".ll", ".lh", ".hl", ".hh")
+
+
+def named_normal(name, shape, seed=0):
+    import zlib
+
+    rs = np.random.RandomState((zlib.crc32(name.encode()) + 7919 * seed) & 0x7FFFFFFF)
+    return rs.standard_normal(tuple(shape)).astype(F32)
+
+
+def styleunet_state(shapes, seed=0):
+    """shapes: {state_dict key: shape}.  Returns {key: float32 array} for every learnable / random entry (the fixed FIR
+    and Haar buffers are left at their constructor values).  Scales follow the reference initialisers."""
+    out = {}
+    for name, shape in shapes.items():
+        if name.endswith(_FIXED):
+            continue
+        n = named_normal(name, shape, seed)
+        if name.endswith("modulation.bias"):
+            v = 1.0 + 0.1 * n                      # EqualLinear(bias_init=1), model/styleUnet.py:214
+        elif name.endswith("noise.weight"):
+            v = 0.1 * n                            # NoiseInjection.weight (zero-initialised in the reference; nonzero so it is exercised)
+        elif name.startswith("style.") and name.endswith(".weight"):
+            v = 100.0 * n                          # randn / lr_mul, lr_mlp = 0.01 (styleUnet.py:131)
+        elif name.endswith("bias"):
+            v = 0.1 * n
+        else:
+            v = n
+        out[name] = v.astype(F32)
+    return out

@@ -195,6 +195,48 @@ def gen_ops(torch):
     print("ops", len(out))
 
 
+STYLEUNET_CASES = {
+    # SWGAN_unet at reduced size (same code path as the shipped 128 -> 512: encoder 16,8 -> decoder 16,32,64 -> IWT 128)
+    "swgan_32_128": dict(net="SWGAN_unet", kw=dict(inp_size=32, inp_ch=8, out_ch=3, out_size=128, style_dim=64, n_mlp=4), batch=2, seed=1),
+    # plane generator configuration of model/nerf_model.py:39-42 at reduced size (cond 64x64, planes 32x32)
+    "zxc_64_32": dict(net="StyleGAN_zxc", kw=dict(out_ch=16, out_size=32, style_dim=44, middle_size=16, zero_latent=False,
+                                                   zero_noise=True, no_skip=True, n_mlp=4, inp_size=64, inp_ch=7), batch=2, seed=2),
+}
+
+
+def styleunet_inputs(case, net):
+    """Deterministic inputs of a STYLEUNET_CASES entry (shared with tests/test_styleunet_gpu.py)."""
+    kw, B, seed = case["kw"], case["batch"], case["seed"]
+    sd = synth.styleunet_state({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed)
+    style = synth.named_normal("input.style", (B, kw["style_dim"]), seed)
+    cond = synth.named_normal("input.cond", (B, kw["inp_ch"], kw["inp_size"], kw["inp_size"]), seed)
+    if case["net"] == "SWGAN_unet":
+        noise = [synth.named_normal("input.noise%d" % i, (1, 1, 2 ** r, 2 ** r), seed)
+                 for i, r in enumerate(r for r in range(net.middle_log_size + 1, net.log_size + 1) for _ in range(2))]
+    else:
+        noise = [synth.named_normal("input.noise0", (1, 1, 2 ** net.middle_log_size, 2 ** net.middle_log_size), seed)]
+    return sd, style, cond, noise
+
+
+def gen_styleunet(torch):
+    import model.styleUnet as ref
+
+    for name, case in STYLEUNET_CASES.items():
+        net = getattr(ref, case["net"])(**case["kw"])
+        sd, style, cond, noise = styleunet_inputs(case, net)
+        missing = net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+        assert not missing.unexpected_keys and all(k.endswith(synth._FIXED) for k in missing.missing_keys), missing
+        with torch.no_grad():
+            if case["net"] == "SWGAN_unet":
+                out = net([torch.from_numpy(style)], torch.from_numpy(cond), noise=[torch.from_numpy(n) for n in noise])
+            else:
+                net.zero_noise[0] = torch.from_numpy(noise[0])        # the fixed first-layer draw (styleUnet.py:748)
+                out, _ = net([torch.from_numpy(style)], torch.from_numpy(cond))
+        keys = json.dumps({k: list(v.shape) for k, v in net.state_dict().items()})
+        np.savez_compressed(os.path.join(GOLD, "styleunet_%s.npz" % name), out=out.numpy(), state_dict_shapes=keys)
+        print(name, tuple(out.shape), "abs mean %.3f max %.3f" % (out.abs().mean(), out.abs().max()))
+
+
 def main():
     from oracle import ref_shim
 
@@ -206,6 +248,7 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     gen_stages(torch)
     gen_ops(torch)
+    gen_styleunet(torch)
     from model.nerf_trainer import Trainer
 
     trainer = Trainer(cfg, 4)
