@@ -33,7 +33,8 @@ constexpr int kASlotBytes = (kCinBlk / 8) * kMaxHaloPx * 16;   // 23040
 constexpr int kSmB = 0;
 constexpr int kSmA = kSmB + kBStages * kBSlotBytes;
 constexpr int kSmBar = kSmA + 2 * kASlotBytes;
-constexpr int kSmemBytes = kSmBar + 128;
+constexpr int kSmScale = kSmBar + 128;
+constexpr int kSmemBytes = kSmScale + 2 * kCinBlk * 4;
 constexpr int kThreads = 128;
 
 struct ConvDev {
@@ -48,6 +49,9 @@ struct ConvDev {
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_conv(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
@@ -99,26 +103,29 @@ __global__ void __launch_bounds__(128) modconv_demod_kernel(const float *__restr
   if (threadIdx.x == 0) demod[(long)b * Cout + co] = rsqrtf(red[0] + red[1] + red[2] + red[3] + eps);
 }
 
-template <bool kBF16>
-__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvDev P) {
+// CTA = 8 staging / epilogue warps + 1 control warp (weight ring + MMA issue).  The control warp never stages, so the
+// halo patch of channel block kb+1 is being written while the tensor core works through the 9 taps of block kb.
+constexpr int kStageThreads = 256;
+constexpr int kThreadsV2 = kStageThreads + 32;
+
+template <bool kBF16, int KS>
+__global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const int tid = threadIdx.x;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_bfull = smem_base + kSmBar, bar_bfree = bar_bfull + kBStages * 8, bar_afree = bar_bfree + kBStages * 8,
-                 bar_acc = bar_afree + 16;
+                 bar_afull = bar_afree + 16, bar_acc = bar_afull + 16;
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kSmBar + 120);
+  float *sscale = reinterpret_cast<float *>(smem + kSmScale);   // [2][64] modulation of the staged channel block
 
-  // tile coordinates: blockIdx.x = spatial tile (b, ty, tx), blockIdx.y = output-channel tile
   const int nt = blockIdx.y;
   int sp = blockIdx.x;
   const int tx = sp % P.tiles_x; sp /= P.tiles_x;
   const int ty = sp % P.tiles_y;
   const int b = sp / P.tiles_y;
-  const int vy0 = ty * kTileH, vx0 = tx * kTileW;     // stride-1 output positions of this tile
-  const int hw = kTileW + P.k - 1, hh = kTileH + P.k - 1, halo_px = hh * hw;
-  const int chunk_bytes = halo_px * 16;
-  const int taps = P.k * P.k;
+  const int vy0 = ty * kTileH, vx0 = tx * kTileW;
+  constexpr int hw = kTileW + KS - 1, hh = kTileH + KS - 1, halo_px = hh * hw, chunk_bytes = halo_px * 16, taps = KS * KS;
   const int total_steps = P.kblocks * taps;
   const uint32_t b_bytes = (uint32_t)P.n_tile * kCinBlk * 2;
 
@@ -129,121 +136,131 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvDev P) {
   if (tid == 32) {
     for (int i = 0; i < kBStages; ++i) mbar_init(bar_bfull + i * 8, 1), mbar_init(bar_bfree + i * 8, 1);
     mbar_init(bar_afree, 1), mbar_init(bar_afree + 8, 1), mbar_init(bar_acc, 1);
+    mbar_init(bar_afull, kStageThreads), mbar_init(bar_afull + 8, kStageThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
-
   const uint8_t *wsrc = P.wpack + (size_t)nt * P.kblocks * taps * b_bytes;
-  // ---- prologue: the first weight slices are on their way before any staging starts
-  if (tid == 0) {
-    for (int i = 0; i < kBStages && i < total_steps; ++i) {
-      mbar_expect_tx(bar_bfull + i * 8, b_bytes);
-      bulk_g2s(smem_base + kSmB + i * kBSlotBytes, wsrc + (size_t)i * b_bytes, b_bytes, bar_bfull + i * 8);
-    }
-  }
-  const uint32_t idesc = instr_desc(P.n_tile, kBF16);
-  const float *xb = P.x + (size_t)b * P.Cin * P.H * P.W;
 
-  for (int kb = 0; kb < P.kblocks; ++kb) {
-    uint8_t *A = smem + kSmA + (kb & 1) * kASlotBytes;
-    if (kb >= 2) mbar_wait(bar_afree + (kb & 1) * 8, ((kb - 2) >> 1) & 1);   // MMAs of block kb-2 are done with this buffer
-    // ---- stage the halo patch of 64 channels: item = (8-channel chunk, halo pixel), modulation applied on the way in
-    for (int it = tid; it < 8 * halo_px; it += kThreads) {
-      const int chunk = it / halo_px, hp = it - chunk * halo_px;
-      const int py = hp / hw, px = hp - py * hw;
-      int Y = vy0 + py - P.pad, X = vx0 + px - P.pad;
-      bool ok = Y >= 0 && X >= 0;
-      if (P.up == 2) {
-        ok = ok && !(Y & 1) && !(X & 1);
-        Y >>= 1, X >>= 1;
+  if (warp_u == kStageThreads / 32) {
+    // ================= control warp =================
+    if (elect_one()) {
+      for (int i = 0; i < kBStages && i < total_steps; ++i) {
+        mbar_expect_tx(bar_bfull + i * 8, b_bytes);
+        bulk_g2s(smem_base + kSmB + i * kBSlotBytes, wsrc + (size_t)i * b_bytes, b_bytes, bar_bfull + i * 8);
       }
-      ok = ok && Y < P.H && X < P.W;
-      const int c0 = kb * kCinBlk + chunk * 8;
-      float v[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int c = c0 + e;
-        float t = 0.0f;
-        if (ok && c < P.Cin) {
-          t = __ldg(xb + ((size_t)c * P.H + Y) * P.W + X);
-          if (P.in_scale != nullptr) t *= __ldg(P.in_scale + (size_t)b * P.Cin + c);
-        }
-        v[e] = t;
-      }
-      *reinterpret_cast<uint4 *>(A + chunk * chunk_bytes + hp * 16) =
-          make_uint4(pack2<kBF16>(v[0], v[1]), pack2<kBF16>(v[2], v[3]), pack2<kBF16>(v[4], v[5]), pack2<kBF16>(v[6], v[7]));
-    }
-    fence_async_smem();
-    __syncthreads();
-    // ---- one elected thread of warp 0: 9 taps x 4 K-steps on this block, refilling the weight ring as slots drain
-    if (warp_u == 0) {
-      if (elect_one()) {
+      const uint32_t idesc = instr_desc(P.n_tile, kBF16);
+      for (int kb = 0; kb < P.kblocks; ++kb) {
+        mbar_wait_spin(bar_afull + (kb & 1) * 8, (kb >> 1) & 1);
         tc_fence_after();
         const uint32_t A_addr = smem_base + kSmA + (kb & 1) * kASlotBytes;
+#pragma unroll 1
         for (int tap = 0; tap < taps; ++tap) {
           const int step = kb * taps + tap, slot = step % kBStages;
-          mbar_wait(bar_bfull + slot * 8, (step / kBStages) & 1);
+          mbar_wait_spin(bar_bfull + slot * 8, (step / kBStages) & 1);
           tc_fence_after();
-          const int kh = tap / P.k, kw = tap - kh * P.k;
+          const int kh = tap / KS, kw = tap - kh * KS;
           const uint32_t a0 = A_addr + (kh * hw + kw) * 16, b0 = smem_base + kSmB + slot * kBSlotBytes;
 #pragma unroll
           for (int j = 0; j < kCinBlk / 16; ++j)
             umma_ss(tmem_acc, smem_desc(a0 + 2 * j * chunk_bytes, chunk_bytes, hw * 16),
                     smem_desc(b0 + 2 * j * P.n_tile * 16, P.n_tile * 16, 128), idesc, (step | j) != 0);
           umma_commit(bar_bfree + slot * 8);
-          // refill the slot of the PREVIOUS step (its MMAs have most likely drained by now) with the slice
-          // kBStages steps after it, so one tap of MMAs always stays queued behind the one that is running
+          // refill the slot of the PREVIOUS step (drained, or about to be) with the slice kBStages steps after it
           const int prev = step - 1, nxt = prev + kBStages;
           if (prev >= 0 && nxt < total_steps) {
             const int ps = prev % kBStages;
-            mbar_wait(bar_bfree + ps * 8, (prev / kBStages) & 1);
+            mbar_wait_spin(bar_bfree + ps * 8, (prev / kBStages) & 1);
             mbar_expect_tx(bar_bfull + ps * 8, b_bytes);
             bulk_g2s(smem_base + kSmB + ps * kBSlotBytes, wsrc + (size_t)nxt * b_bytes, b_bytes, bar_bfull + ps * 8);
           }
         }
         umma_commit(bar_afree + (kb & 1) * 8);
-        if (kb == P.kblocks - 1) umma_commit(bar_acc);
       }
-      __syncwarp();
+      umma_commit(bar_acc);
     }
-  }
-  // ---- epilogue: row m = output position (vy0 + m/8, vx0 + m%8); demod, noise, bias, leaky-relu, NCHW store
-  mbar_wait(bar_acc, 0);
-  tc_fence_after();
-  {
-    const int m = tid, vy = vy0 + (m >> 3), vx = vx0 + (m & 7);
-    bool ok;
-    int oy, ox;
-    if (P.down == 2) ok = !(vy & 1) && !(vx & 1), oy = vy >> 1, ox = vx >> 1;
-    else ok = true, oy = vy, ox = vx;
-    ok = ok && oy < P.Ho && ox < P.Wo;
-    float nz = 0.0f;
-    if (ok && P.noise != nullptr) nz = P.noise_weight * __ldg(P.noise + (size_t)b * P.noise_bstride + (size_t)oy * P.Wo + ox);
-    const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16);
-    const size_t plane = (size_t)P.Ho * P.Wo;
-    float *ob = P.out + ((size_t)b * P.Cout) * plane + (size_t)oy * P.Wo + ox;
-    for (int c0 = 0; c0 < P.n_tile; c0 += 16) {
-      uint32_t r[16];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-          : "r"(trow + c0));
-      tmem_wait_ld();
-      if (ok) {
+    __syncwarp();
+  } else {
+    // ================= staging warps =================
+    const float *xb = P.x + (size_t)b * P.Cin * P.H * P.W;
+    const size_t cstride = (size_t)P.H * P.W;
+    for (int kb = 0; kb < P.kblocks; ++kb) {
+      uint8_t *A = smem + kSmA + (kb & 1) * kASlotBytes;
+      float *sc = sscale + (kb & 1) * kCinBlk;
+      if (kb >= 2) mbar_wait_spin(bar_afree + (kb & 1) * 8, ((kb - 2) >> 1) & 1);   // MMAs of block kb-2 are done with this buffer
+      if (tid < kCinBlk) {
+        const int c = kb * kCinBlk + tid;
+        sc[tid] = (c < P.Cin) ? (P.in_scale != nullptr ? __ldg(P.in_scale + (size_t)b * P.Cin + c) : 1.0f) : 0.0f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kStageThreads) : "memory");
+      // item = (8-channel chunk, halo pixel); consecutive threads take consecutive halo pixels of one chunk
+      int hp = tid, chunk = 0;
+      while (hp >= halo_px) hp -= halo_px, ++chunk;
+#pragma unroll 1
+      for (; chunk < 8;) {
+        const int py = hp / hw, px = hp - py * hw;
+        int Y = vy0 + py - P.pad, X = vx0 + px - P.pad;
+        bool ok = Y >= 0 && X >= 0;
+        if (P.up == 2) {
+          ok = ok && !(Y & 1) && !(X & 1);
+          Y >>= 1, X >>= 1;
+        }
+        ok = ok && Y < P.H && X < P.W;
+        const int c0 = kb * kCinBlk + chunk * 8;
+        float v[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int co = nt * P.n_tile + c0 + j;
-          if (co < P.Cout) {
-            float v = __uint_as_float(r[j]);
-            if (P.out_scale != nullptr) v *= __ldg(P.out_scale + (size_t)b * P.Cout + co);
-            v += nz;
-            if (P.bias != nullptr) v += __ldg(P.bias + co);
-            if (P.act) v = (v > 0.0f ? v : 0.2f * v) * 1.41421356237309515f;
-            ob[(size_t)co * plane] = v;
+        for (int e = 0; e < 8; ++e) v[e] = (ok && c0 + e < P.Cin) ? __ldg(xb + (size_t)(c0 + e) * cstride + (size_t)Y * P.W + X) : 0.0f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= sc[chunk * 8 + e];
+        *reinterpret_cast<uint4 *>(A + chunk * chunk_bytes + hp * 16) =
+            make_uint4(pack2<kBF16>(v[0], v[1]), pack2<kBF16>(v[2], v[3]), pack2<kBF16>(v[4], v[5]), pack2<kBF16>(v[6], v[7]));
+        hp += kStageThreads;
+        while (hp >= halo_px) hp -= halo_px, ++chunk;
+      }
+      fence_async_smem();
+      mbar_arrive_conv(bar_afull + (kb & 1) * 8);
+    }
+    // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., column half w/4.  Row m = position (vy0 + m/8, vx0 + m%8)
+    mbar_wait_spin(bar_acc, 0);
+    tc_fence_after();
+    {
+      const int wq = warp_u & 3, half = warp_u >> 2;
+      const int m = wq * 32 + (tid & 31), vy = vy0 + (m >> 3), vx = vx0 + (m & 7);
+      bool ok;
+      int oy, ox;
+      if (P.down == 2) ok = !(vy & 1) && !(vx & 1), oy = vy >> 1, ox = vx >> 1;
+      else ok = true, oy = vy, ox = vx;
+      ok = ok && oy < P.Ho && ox < P.Wo;
+      float nz = 0.0f;
+      if (ok && P.noise != nullptr) nz = P.noise_weight * __ldg(P.noise + (size_t)b * P.noise_bstride + (size_t)oy * P.Wo + ox);
+      const uint32_t trow = tmem_acc + ((uint32_t)(wq * 32) << 16);
+      const size_t plane = (size_t)P.Ho * P.Wo;
+      float *ob = P.out + ((size_t)b * P.Cout) * plane + (size_t)oy * P.Wo + ox;
+      const int cols_half = ((P.n_tile / 16 + 1) / 2) * 16;
+      const int c_beg = half * cols_half, c_end = min(P.n_tile, c_beg + cols_half);
+      for (int c0 = c_beg; c0 < c_end; c0 += 16) {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(trow + c0));
+        tmem_wait_ld();
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = nt * P.n_tile + c0 + j;
+            if (co < P.Cout) {
+              float v = __uint_as_float(r[j]);
+              if (P.out_scale != nullptr) v *= __ldg(P.out_scale + (size_t)b * P.Cout + co);
+              v += nz;
+              if (P.bias != nullptr) v += __ldg(P.bias + co);
+              if (P.act) v = (v > 0.0f ? v : 0.2f * v) * 1.41421356237309515f;
+              ob[(size_t)co * plane] = v;
+            }
           }
         }
       }
@@ -329,15 +346,16 @@ extern "C" int hav_conv2d_forward(const hav_conv_args *a, void *stream) {
   if (sp_tiles > 2147483647L || P.n_tiles > 65535) return HAV_E_SHAPE;
   dim3 grid((unsigned)sp_tiles, P.n_tiles);
   cudaError_t e;
-  if (a->precision == HAV_PREC_BF16) {
-    e = cudaFuncSetAttribute(conv::conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv::kSmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    conv::conv_tc_kernel<true><<<grid, conv::kThreads, conv::kSmemBytes, (cudaStream_t)stream>>>(P);
-  } else {
-    e = cudaFuncSetAttribute(conv::conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv::kSmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    conv::conv_tc_kernel<false><<<grid, conv::kThreads, conv::kSmemBytes, (cudaStream_t)stream>>>(P);
-  }
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, conv::kSmemBytes);
+    if (er != cudaSuccess) return er;
+    kern<<<grid, conv::kThreadsV2, conv::kSmemBytes, (cudaStream_t)stream>>>(P);
+    return cudaGetLastError();
+  };
+  const bool bf = a->precision == HAV_PREC_BF16;
+  if (a->ksize == 3) e = bf ? launch(conv::conv_tc_kernel<true, 3>) : launch(conv::conv_tc_kernel<false, 3>);
+  else e = bf ? launch(conv::conv_tc_kernel<true, 1>) : launch(conv::conv_tc_kernel<false, 1>);
+  if (e != cudaSuccess) return (int)e;
   e = cudaGetLastError();
   return e == cudaSuccess ? HAV_OK : (int)e;
 }

@@ -21,5 +21,15 @@ for _ in range(n):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 gf = {(128, 512): 176.3, (512, 1024): 352.3}.get((inp, out), 0) * B
+from havatar_b200.graph import GraphedForward
+g = GraphedForward(lambda st, c: net([st], c, noise=noise), s, x)
+yg = g(s, x); torch.cuda.synchronize()
+print("graph vs eager max diff", float((yg - y).abs().max()))
+e0.record()
+for _ in range(n):
+    yg = g(s, x)
+e1.record(); torch.cuda.synchronize()
+msg = e0.elapsed_time(e1) / n
+print("  CUDA graph replay: %.3f ms  %.1f frames/s  %.1f TFLOP/s" % (msg, B * 1e3 / msg, gf / msg))
 print("SWGAN_unet %d->%d B=%d: %.3f ms/frame-batch  %.1f frames/s  %.1f TFLOP/s (reference FLOP count)  out %s finite=%s" % (
     inp, out, B, ms, B * 1e3 / ms, gf / ms, tuple(y.shape), bool(torch.isfinite(y).all())))
