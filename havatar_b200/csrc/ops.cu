@@ -125,6 +125,105 @@ __global__ void __launch_bounds__(256) upfirdn2d_kernel(float *__restrict__ out,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Specialised upfirdn2d for the shapes the StyleUNet actually uses (minor == 1, square up/down):
+//   <1,1,4,4> Blur, <1,2,4,4> Downsample, <2,1,4,4> Upsample, <1,2,2,2> Haar analysis, <2,1,2,2> Haar synthesis.
+// Compile-time taps (fully unrolled), compile-time window pitch (no div/mod by runtime values), one thread = a strip
+// of 4 horizontally adjacent outputs that shares its window reads, 128-bit stores when the row pitch allows.
+// Same arithmetic as the generic kernel: out = sum over the taps that land on a real input sample.
+// ------------------------------------------------------------------------------------------------
+template <int UP, int DOWN, int KH, int KW>
+struct UfdFast {
+  static constexpr int kWinH = ((kTileH - 1) * DOWN + KH - 1) / UP + 2;
+  static constexpr int kWinW = ((kTileW - 1) * DOWN + KW - 1) / UP + 2;
+  static constexpr int kSmemFloats = KH * KW + kWinH * kWinW;
+};
+
+template <int UP, int DOWN, int KH, int KW>
+__global__ void __launch_bounds__(256) upfirdn2d_fast_kernel(float *__restrict__ out, const float *__restrict__ x,
+                                                             const float *__restrict__ kernel, UfdParams p, int tiles_x) {
+  using F = UfdFast<UP, DOWN, KH, KW>;
+  __shared__ float sk[KH * KW];
+  __shared__ float sw[F::kWinH * F::kWinW];
+  const int img = blockIdx.y;
+  const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
+  const int oy0 = tile_y * kTileH, ox0 = tile_x * kTileW;
+  if (threadIdx.x < KH * KW) {
+    const int ky = threadIdx.x / KW, kx = threadIdx.x % KW;
+    sk[threadIdx.x] = __ldg(kernel + (KH - 1 - ky) * KW + (KW - 1 - kx));
+  }
+  const int iy0 = ceil_div(oy0 * DOWN - p.pad_y0, UP), ix0 = ceil_div(ox0 * DOWN - p.pad_x0, UP);
+  const float *xin = x + (size_t)img * p.in_h * p.in_w;
+  for (int i = threadIdx.x; i < F::kWinH * F::kWinW; i += 256) {
+    const int wy = i / F::kWinW, wx = i - wy * F::kWinW;
+    const int iy = iy0 + wy, ix = ix0 + wx;
+    sw[i] = (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) ? __ldg(xin + (size_t)iy * p.in_w + ix) : 0.0f;
+  }
+  __syncthreads();
+  float kreg[KH * KW];
+#pragma unroll
+  for (int i = 0; i < KH * KW; ++i) kreg[i] = sk[i];
+  float *oimg = out + (size_t)img * p.out_h * p.out_w;
+  const bool vec_ok = (p.out_w & 3) == 0;
+  // strips of 4 outputs: (kTileH * kTileW / 4) strips per tile, 2 per thread
+  for (int sidx = threadIdx.x; sidx < kTileH * kTileW / 4; sidx += 256) {
+    const int ty = sidx / (kTileW / 4), oy = oy0 + ty, ox = ox0 + (sidx - ty * (kTileW / 4)) * 4;
+    if (oy >= p.out_h || ox >= p.out_w) continue;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int Y0 = oy * DOWN - p.pad_y0;
+    if (UP == 1) {
+      const int wy0 = Y0 - iy0, wx0 = ox * DOWN - p.pad_x0 - ix0;
+      constexpr int NX = 3 * DOWN + KW;   // window columns a strip touches
+#pragma unroll
+      for (int ky = 0; ky < KH; ++ky) {
+        float row[NX];
+#pragma unroll
+        for (int c = 0; c < NX; ++c) row[c] = sw[(wy0 + ky) * F::kWinW + wx0 + c];
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+          for (int kx = 0; kx < KW; ++kx) acc[o] = fmaf(row[o * DOWN + kx], kreg[ky * KW + kx], acc[o]);
+      }
+    } else {
+      // UP == 2, DOWN == 1: tap ky contributes when (Y0 + ky) is even; KH / 2 taps per dimension
+      const int ky_first = Y0 & 1;                       // (-Y0) mod 2
+#pragma unroll
+      for (int a = 0; a < KH / 2; ++a) {
+        const int ky = ky_first + 2 * a;
+        const int wy = ((Y0 + ky) >> 1) - iy0;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int X0 = (ox + o) - p.pad_x0, kx_first = X0 & 1;
+#pragma unroll
+          for (int c = 0; c < KW / 2; ++c) {
+            const int kx = kx_first + 2 * c;
+            acc[o] = fmaf(sw[wy * F::kWinW + ((X0 + kx) >> 1) - ix0], kreg[ky * KW + kx], acc[o]);
+          }
+        }
+      }
+    }
+    float *op = oimg + (size_t)oy * p.out_w + ox;
+    if (vec_ok && ox + 3 < p.out_w) {
+      *reinterpret_cast<float4 *>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+        if (ox + o < p.out_w) op[o] = acc[o];
+    }
+  }
+}
+
+template <int UP, int DOWN, int KH, int KW>
+static cudaError_t launch_ufd_fast(float *out, const float *x, const float *kernel, const UfdParams &p, int64_t imgs, cudaStream_t st) {
+  const int tiles_x = (p.out_w + kTileW - 1) / kTileW, tiles_y = (p.out_h + kTileH - 1) / kTileH;
+  for (int64_t i0 = 0; i0 < imgs; i0 += 65535) {
+    const int ny = (int)((imgs - i0) < 65535 ? (imgs - i0) : 65535);
+    upfirdn2d_fast_kernel<UP, DOWN, KH, KW><<<dim3(tiles_x * tiles_y, ny), 256, 0, st>>>(
+        out + (size_t)i0 * p.out_h * p.out_w, x + (size_t)i0 * p.in_h * p.in_w, kernel, p, tiles_x);
+  }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // ray generation (dataloader/data_util.py:28-56)
 // ------------------------------------------------------------------------------------------------
 struct RayGen {
@@ -196,6 +295,18 @@ extern "C" int hav_upfirdn2d(float *out, const float *x, const float *kernel, in
   p.up_x = up_x, p.up_y = up_y, p.down_x = down_x, p.down_y = down_y, p.pad_x0 = pad_x0, p.pad_y0 = pad_y0;
   p.win_h = ((kTileH - 1) * down_y + kh - 1) / up_y + 2;
   p.win_w = ((kTileW - 1) * down_x + kw - 1) / up_x + 2;
+  if (minor == 1 && up_x == up_y && down_x == down_y && kh == kw && pad_x0 >= 0 && pad_y0 >= 0) {
+    // the StyleUNet's own shapes (model/styleUnet.py:29-87, 371-422) take the specialised kernels
+    cudaError_t fe = cudaErrorInvalidValue;
+    const int64_t n_img = (int64_t)major;
+    if (up_x == 1 && down_x == 1 && kh == 4) fe = launch_ufd_fast<1, 1, 4, 4>(out, x, kernel, p, n_img, (cudaStream_t)stream);
+    else if (up_x == 1 && down_x == 2 && kh == 4) fe = launch_ufd_fast<1, 2, 4, 4>(out, x, kernel, p, n_img, (cudaStream_t)stream);
+    else if (up_x == 2 && down_x == 1 && kh == 4) fe = launch_ufd_fast<2, 1, 4, 4>(out, x, kernel, p, n_img, (cudaStream_t)stream);
+    else if (up_x == 1 && down_x == 2 && kh == 2) fe = launch_ufd_fast<1, 2, 2, 2>(out, x, kernel, p, n_img, (cudaStream_t)stream);
+    else if (up_x == 2 && down_x == 1 && kh == 2) fe = launch_ufd_fast<2, 1, 2, 2>(out, x, kernel, p, n_img, (cudaStream_t)stream);
+    if (fe == cudaSuccess) return HAV_OK;
+    if (fe != cudaErrorInvalidValue) return (int)fe;
+  }
   const size_t smem = (size_t)(kMaxTaps * kMaxTaps + p.win_h * p.win_w) * sizeof(float);
   if (smem > 200 * 1024) return HAV_E_SHAPE;
   cudaError_t e = cudaFuncSetAttribute(upfirdn2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -68,4 +68,9 @@ def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
         pad = (pad[0], pad[1], pad[0], pad[1])
     if not input.is_cuda:
         raise RuntimeError("havatar_b200.op.upfirdn2d needs CUDA tensors (no CPU fallback)")
+    if not (torch.is_grad_enabled() and input.requires_grad):
+        # inference: straight to the kernel, no autograd bookkeeping (the flipped gradient kernel is not needed)
+        _, channel, in_h, in_w = input.shape
+        out = upfirdn2d_op.upfirdn2d(input.reshape(-1, in_h, in_w, 1), kernel, up[0], up[1], down[0], down[1], *pad)
+        return out.view(-1, channel, out.shape[1], out.shape[2])
     return _UpFirDn2d.apply(input, kernel, tuple(up), tuple(down), tuple(pad))

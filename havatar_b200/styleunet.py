@@ -186,11 +186,22 @@ class EqualLinear(nn.Module):
         self.activation = activation
         self.scale = (1 / math.sqrt(in_dim)) * lr_mul
         self.lr_mul = lr_mul
+        self._key, self._w, self._b = None, None, None
+
+    def _scaled(self):
+        """weight * scale and bias * lr_mul, recomputed only when a parameter changes (two launches saved per call)."""
+        key = (self.weight.data_ptr(), self.weight._version, None if self.bias is None else (self.bias.data_ptr(), self.bias._version))
+        if key != self._key:
+            self._w = (self.weight.detach() * self.scale).contiguous()
+            self._b = None if self.bias is None else (self.bias.detach() * self.lr_mul).contiguous()
+            self._key = key
+        return self._w, self._b
 
     def forward(self, x):
+        w, b = self._scaled()
         if self.activation:
-            return fused_leaky_relu(torch.nn.functional.linear(x, self.weight * self.scale).contiguous(), self.bias * self.lr_mul)
-        return torch.nn.functional.linear(x, self.weight * self.scale, bias=self.bias * self.lr_mul)
+            return fused_leaky_relu(torch.nn.functional.linear(x, w).contiguous(), b)
+        return torch.nn.functional.linear(x, w, bias=b)
 
 
 class ModulatedConv2d(nn.Module):
