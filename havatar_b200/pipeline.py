@@ -1,0 +1,59 @@
+"""The reference's HD inference frame on the B200 kernels (avatarHD_reenactment.py:149-170):
+
+    condition renderings -> XY_gen / YZ_gen plane generators (model/nerf_model.py:58-86)
+                         -> fused volumetric render of the full frame (model/nerf_trainer.py:94-118, mode 'validation')
+                         -> SWGAN_unet upsampler on the 64 feature channels (avatarHD_reenactment.py:167)
+
+AvatarHD owns the three networks + the radiance MLP weights and a skinning-weight volume; `frame()` is one frame,
+`graphed()` returns a CUDA-graph replay of it for fixed shapes.  Inference only."""
+import torch
+
+from . import render as hrender
+from . import styleunet
+from .graph import GraphedForward
+
+
+class AvatarHD(torch.nn.Module):
+    def __init__(self, mlp_weights, wvol, render_size=128, out_size=512, plane_res=128, cond_size=256, feat_dim=64, latent_dim=32,
+                 num_coarse=64, num_fine=0, precision="fp16", boxes=None):
+        super().__init__()
+        style_in = latent_dim + 12                      # latent code | inv_head_T flattened (model/nerf_trainer.py:17-18,39)
+        self.XY_gen = styleunet.StyleGAN_zxc(out_ch=feat_dim, out_size=plane_res, style_dim=style_in, middle_size=16, zero_latent=False,
+                                             zero_noise=True, no_skip=True, n_mlp=4, inp_size=cond_size, inp_ch=7)
+        self.YZ_gen = styleunet.StyleGAN_zxc(out_ch=feat_dim, out_size=plane_res, style_dim=style_in, middle_size=16, zero_latent=False,
+                                             zero_noise=True, no_skip=True, n_mlp=4, inp_size=cond_size, inp_ch=13)
+        self.upsampler = styleunet.SWGAN_unet(inp_size=render_size, inp_ch=feat_dim, out_ch=3, out_size=out_size, style_dim=64, n_mlp=4,
+                                              middle_size=8)
+        self.mlp = torch.nn.ParameterDict({k.replace(".", "__"): torch.nn.Parameter(torch.as_tensor(v).float(), requires_grad=False)
+                                           for k, v in mlp_weights.items()})
+        self.register_buffer("wvol", torch.as_tensor(wvol).float())
+        self.render_size, self.num_coarse, self.num_fine, self.precision, self.boxes = render_size, num_coarse, num_fine, precision, boxes
+        self._noise = None
+
+    def planes(self, latent_code, inv_head_T, front, left, right):
+        """set_conditional_embedding (model/nerf_model.py:58-86): left view flipped along W, its mask channel dropped."""
+        lat = [torch.cat([latent_code, inv_head_T.reshape(inv_head_T.shape[0], -1)], dim=-1)]
+        left = left.flip(dims=[3])
+        if left.shape[1] > 3:
+            left = left[:, :-1]
+        xy, _ = self.XY_gen(lat, front.contiguous())
+        yz, _ = self.YZ_gen(lat, torch.cat([left, right], dim=1).contiguous())
+        return torch.stack([xy, yz], dim=0)
+
+    @torch.no_grad()
+    def frame(self, ray_batch, background, latent_code, inv_head_T, front, left, right, style):
+        B, R = ray_batch.shape[:2]
+        h = w = self.render_size
+        planes = self.planes(latent_code, inv_head_T, front, left, right)
+        weights = {k.replace("__", "."): v for k, v in self.mlp.items()}
+        o = hrender.render_rays(ray_batch, background, inv_head_T, planes, self.wvol, weights, self.num_coarse, self.num_fine,
+                                boxes=self.boxes, precision=self.precision)
+        rgb = o.rgb_fine if self.num_fine > 0 else o.rgb_coarse
+        render = rgb.view(B, h, w, 67).permute(0, 3, 1, 2).contiguous()              # nerf_trainer.py:111-113
+        if self._noise is None or self._noise[0].device != render.device:
+            self._noise = self.upsampler.make_noise(render.device)
+        image = self.upsampler([style], render[:, 3:].contiguous(), noise=self._noise)   # avatarHD_reenactment.py:167
+        return image, render[:, :3]
+
+    def graphed(self, *example):
+        return GraphedForward(lambda *a: self.frame(*a), *example)
