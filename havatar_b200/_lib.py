@@ -54,7 +54,7 @@ SIGNATURES = {
     "hav_upfirdn2d": (C.c_int, [_fp, _fp, _fp] + [C.c_int] * 14 + [_fp]),
     "hav_render_workspace_bytes": (C.c_uint64, [C.POINTER(RenderArgs)]),
     "hav_render_forward": (C.c_int, [C.POINTER(RenderArgs), _fp]),
-    "hav_conv_wpack_bytes": (C.c_uint64, [C.c_int, C.c_int, C.c_int]),
+    "hav_conv_wpack_bytes": (C.c_uint64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "hav_conv_pack_weights": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, _fp]),
     "hav_modconv_demod": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _fp]),
     "hav_conv2d_forward": (C.c_int, [C.POINTER(ConvArgs), _fp]),

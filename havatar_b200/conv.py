@@ -13,8 +13,8 @@ from . import _lib
 class PackedConvWeight:
     """16-bit weight image of one convolution in the kernel's shared-memory order (hav_conv_pack_weights)."""
 
-    def __init__(self, data, cout, cin, ksize, precision):
-        self.data, self.cout, self.cin, self.ksize, self.precision = data, cout, cin, ksize, precision
+    def __init__(self, data, cout, cin, ksize, precision, up=1):
+        self.data, self.cout, self.cin, self.ksize, self.precision, self.up = data, cout, cin, ksize, precision, up
 
 
 def _check(t, name):
@@ -23,24 +23,25 @@ def _check(t, name):
     return t.detach().contiguous()
 
 
-def pack_weights(weight, scale=1.0, flip=False, transpose_io=False, precision="fp16"):
-    """weight [Cout,Cin,k,k] (or [Cin,Cout,k,k] with transpose_io) -> PackedConvWeight holding scale * weight."""
+def pack_weights(weight, scale=1.0, up=1, transpose_io=False, precision="fp16"):
+    """weight [Cout,Cin,k,k] (or [Cin,Cout,k,k] with transpose_io) -> PackedConvWeight holding scale * weight, laid out for
+    conv2d(..., up=up) (the transposed convolution uses 64-channel tiles and four phase accumulators)."""
     L = _lib.lib()
     w = _check(weight, "weight")
     if w.dim() != 4 or w.shape[2] != w.shape[3]:
         raise _lib.HavError("weight must be [Cout,Cin,k,k]")
     cout, cin = (int(w.shape[1]), int(w.shape[0])) if transpose_io else (int(w.shape[0]), int(w.shape[1]))
     k = int(w.shape[2])
-    nbytes = int(L.hav_conv_wpack_bytes(cout, cin, k))
+    nbytes = int(L.hav_conv_wpack_bytes(cout, cin, k, int(up)))
     if nbytes == 0:
         raise _lib.HavError("unsupported convolution shape (ksize must be 1 or 3)")
     buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
     with torch.cuda.device(w.device):
         st = torch.cuda.current_stream(w.device).cuda_stream
         _lib.check(L.hav_conv_pack_weights(C.c_void_p(buf.data_ptr()), C.c_void_p(w.data_ptr()), cout, cin, k, float(scale),
-                                           int(bool(flip)), int(bool(transpose_io)), _lib.PRECISIONS[precision], C.c_void_p(st)),
+                                           int(up), int(bool(transpose_io)), _lib.PRECISIONS[precision], C.c_void_p(st)),
                    "hav_conv_pack_weights")
-    return PackedConvWeight(buf, cout, cin, k, precision)
+    return PackedConvWeight(buf, cout, cin, k, precision, int(up))
 
 
 def modconv_demod(weight, style, scale, eps=1e-8):
@@ -60,13 +61,15 @@ def modconv_demod(weight, style, scale, eps=1e-8):
 
 def conv2d(x, packed, in_scale=None, out_scale=None, noise=None, noise_weight=0.0, bias=None, act=False, up=1, down=1):
     """out = act(conv(x * in_scale[:, :, None, None], W) * out_scale[:, :, None, None] + noise_weight * noise + bias).
-    up=2: conv_transpose2d(stride 2, pad 0) (pack the weight with flip=True); down=2: stride 2, pad 0; else pad k//2."""
+    up=2: conv_transpose2d(stride 2, pad 0) (pack the weight with up=2); down=2: stride 2, pad 0; else pad k//2."""
     L = _lib.lib()
     x = _check(x, "x")
     B, cin, H, W = [int(v) for v in x.shape]
     if cin != packed.cin:
         raise _lib.HavError("x has %d channels, the packed weight expects %d" % (cin, packed.cin))
     k = packed.ksize
+    if int(up) != packed.up:
+        raise _lib.HavError("weights were packed for up=%d" % packed.up)
     if up == 2:
         Ho, Wo = 2 * H - 1 + k - 1, 2 * W - 1 + k - 1
     elif down == 2:

@@ -13,9 +13,11 @@
 // A operand of tap (kh,kw) is that same buffer seen through a UMMA descriptor whose start address is shifted by
 // (kh * 10 + kw) pixels and whose 8-row groups (one image row of the patch) are 10 pixels apart -- no im2col copy.
 // Weights arrive per (tap, channel block) as 16 KB bulk copies (cp.async.bulk + mbarrier) from a pre-packed image.
-// up = 2 (conv_transpose2d stride 2, :264-277) runs as the stride-1 convolution of the zero-inserted input with the
-// flipped kernel; down = 2 (:279-287, after the blur) computes stride-1 positions and stores the even ones.  Both
-// waste 4x MMA work on those layers -- polyphase variants are the next step.
+// up = 2 (conv_transpose2d stride 2, :264-277) is polyphase: a tile is 128 INPUT positions (i,j); the four output
+// parities out[2i+a, 2j+b] are four accumulators (TMEM column blocks) fed by the taps with kh = a (mod 2), kw = b (mod 2)
+// reading x[i - kh/2, j - kw/2] -- 9 tap-GEMMs per tile like a plain 3x3 conv, no multiplications by inserted zeros.
+// down = 2 (:279-287, after the blur) computes stride-1 positions and stores the even ones (4x MMA work on the few
+// encoder layers that use it; a space-to-depth variant is the next step).
 #include "tc_common.cuh"
 
 namespace hav {
@@ -39,7 +41,7 @@ constexpr int kThreads = 128;
 
 struct ConvDev {
   int B, Cin, Cout, H, W, Ho, Wo, k, up, down, pad, act;
-  int n_tile, n_tiles, kblocks, tiles_x, tiles_y;
+  int n_tile, n_tiles, kblocks, tiles_x, tiles_y, tmem_cols;
   const float *x, *in_scale, *out_scale, *noise, *bias;
   const uint8_t *wpack;
   float *out;
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(128) modconv_demod_kernel(const float *__restr
 constexpr int kStageThreads = 256;
 constexpr int kThreadsV2 = kStageThreads + 32;
 
-template <bool kBF16, int KS>
+template <bool kBF16, int KS, bool UPP>
 __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
@@ -125,12 +127,14 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
   const int ty = sp % P.tiles_y;
   const int b = sp / P.tiles_y;
   const int vy0 = ty * kTileH, vx0 = tx * kTileW;
-  constexpr int hw = kTileW + KS - 1, hh = kTileH + KS - 1, halo_px = hh * hw, chunk_bytes = halo_px * 16, taps = KS * KS;
+  // staged patch: plain conv = tile + (KS-1) halo; polyphase transposed conv = tile + one row above / column left
+  constexpr int hw = UPP ? kTileW + 1 : kTileW + KS - 1, hh = UPP ? kTileH + 1 : kTileH + KS - 1;
+  constexpr int halo_px = hh * hw, chunk_bytes = halo_px * 16, taps = KS * KS;
   const int total_steps = P.kblocks * taps;
   const uint32_t b_bytes = (uint32_t)P.n_tile * kCinBlk * 2;
 
   if (warp_u == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + kSmBar + 120), "r"(128));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + kSmBar + 120), "r"(P.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 32) {
@@ -163,11 +167,20 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
           mbar_wait_spin(bar_bfull + slot * 8, (step / kBStages) & 1);
           tc_fence_after();
           const int kh = tap / KS, kw = tap - kh * KS;
-          const uint32_t a0 = A_addr + (kh * hw + kw) * 16, b0 = smem_base + kSmB + slot * kBSlotBytes;
+          const uint32_t b0 = smem_base + kSmB + slot * kBSlotBytes;
+          uint32_t a0, d0;
+          bool fresh;   // first contribution to its accumulator
+          if (UPP) {    // out[2i+a, 2j+b] += x[i - kh/2, j - kw/2] * W[kh,kw],  a = kh & 1, b = kw & 1
+            a0 = A_addr + ((1 - (kh >> 1)) * hw + (1 - (kw >> 1))) * 16;
+            d0 = tmem_acc + (((kh & 1) << 1) | (kw & 1)) * P.n_tile;
+            fresh = kb == 0 && kh < 2 && kw < 2;
+          } else {
+            a0 = A_addr + (kh * hw + kw) * 16, d0 = tmem_acc, fresh = step == 0;
+          }
 #pragma unroll
           for (int j = 0; j < kCinBlk / 16; ++j)
-            umma_ss(tmem_acc, smem_desc(a0 + 2 * j * chunk_bytes, chunk_bytes, hw * 16),
-                    smem_desc(b0 + 2 * j * P.n_tile * 16, P.n_tile * 16, 128), idesc, (step | j) != 0);
+            umma_ss(d0, smem_desc(a0 + 2 * j * chunk_bytes, chunk_bytes, hw * 16),
+                    smem_desc(b0 + 2 * j * P.n_tile * 16, P.n_tile * 16, 128), idesc, !(fresh && j == 0));
           umma_commit(bar_bfree + slot * 8);
           // refill the slot of the PREVIOUS step (drained, or about to be) with the slice kBStages steps after it
           const int prev = step - 1, nxt = prev + kBStages;
@@ -202,13 +215,8 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
 #pragma unroll 1
       for (; chunk < 8;) {
         const int py = hp / hw, px = hp - py * hw;
-        int Y = vy0 + py - P.pad, X = vx0 + px - P.pad;
-        bool ok = Y >= 0 && X >= 0;
-        if (P.up == 2) {
-          ok = ok && !(Y & 1) && !(X & 1);
-          Y >>= 1, X >>= 1;
-        }
-        ok = ok && Y < P.H && X < P.W;
+        const int Y = vy0 + py - P.pad, X = vx0 + px - P.pad;
+        const bool ok = Y >= 0 && X >= 0 && Y < P.H && X < P.W;
         const int c0 = kb * kCinBlk + chunk * 8;
         float v[8];
 #pragma unroll
@@ -223,43 +231,48 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
       fence_async_smem();
       mbar_arrive_conv(bar_afull + (kb & 1) * 8);
     }
-    // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., column half w/4.  Row m = position (vy0 + m/8, vx0 + m%8)
+    // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., column half w/4.  Row m = tile position (vy0 + m/8, vx0 + m%8);
+    //      polyphase: accumulator block ph = 2a+b holds output (2i+a, 2j+b)
     mbar_wait_spin(bar_acc, 0);
     tc_fence_after();
     {
       const int wq = warp_u & 3, half = warp_u >> 2;
       const int m = wq * 32 + (tid & 31), vy = vy0 + (m >> 3), vx = vx0 + (m & 7);
-      bool ok;
-      int oy, ox;
-      if (P.down == 2) ok = !(vy & 1) && !(vx & 1), oy = vy >> 1, ox = vx >> 1;
-      else ok = true, oy = vy, ox = vx;
-      ok = ok && oy < P.Ho && ox < P.Wo;
-      float nz = 0.0f;
-      if (ok && P.noise != nullptr) nz = P.noise_weight * __ldg(P.noise + (size_t)b * P.noise_bstride + (size_t)oy * P.Wo + ox);
       const uint32_t trow = tmem_acc + ((uint32_t)(wq * 32) << 16);
       const size_t plane = (size_t)P.Ho * P.Wo;
-      float *ob = P.out + ((size_t)b * P.Cout) * plane + (size_t)oy * P.Wo + ox;
       const int cols_half = ((P.n_tile / 16 + 1) / 2) * 16;
       const int c_beg = half * cols_half, c_end = min(P.n_tile, c_beg + cols_half);
-      for (int c0 = c_beg; c0 < c_end; c0 += 16) {
-        uint32_t r[16];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-            : "r"(trow + c0));
-        tmem_wait_ld();
-        if (ok) {
+#pragma unroll 1
+      for (int ph = 0; ph < (UPP ? 4 : 1); ++ph) {
+        bool ok;
+        int oy, ox;
+        if (UPP) ok = true, oy = 2 * vy + (ph >> 1), ox = 2 * vx + (ph & 1);
+        else if (P.down == 2) ok = !(vy & 1) && !(vx & 1), oy = vy >> 1, ox = vx >> 1;
+        else ok = true, oy = vy, ox = vx;
+        ok = ok && oy < P.Ho && ox < P.Wo;
+        float nz = 0.0f;
+        if (ok && P.noise != nullptr) nz = P.noise_weight * __ldg(P.noise + (size_t)b * P.noise_bstride + (size_t)oy * P.Wo + ox);
+        float *ob = P.out + ((size_t)b * P.Cout) * plane + (size_t)oy * P.Wo + ox;
+        for (int c0 = c_beg; c0 < c_end; c0 += 16) {
+          uint32_t r[16];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              : "r"(trow + ph * P.n_tile + c0));
+          tmem_wait_ld();
+          if (ok) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int co = nt * P.n_tile + c0 + j;
-            if (co < P.Cout) {
-              float v = __uint_as_float(r[j]);
-              if (P.out_scale != nullptr) v *= __ldg(P.out_scale + (size_t)b * P.Cout + co);
-              v += nz;
-              if (P.bias != nullptr) v += __ldg(P.bias + co);
-              if (P.act) v = (v > 0.0f ? v : 0.2f * v) * 1.41421356237309515f;
-              ob[(size_t)co * plane] = v;
+            for (int j = 0; j < 16; ++j) {
+              const int co = nt * P.n_tile + c0 + j;
+              if (co < P.Cout) {
+                float v = __uint_as_float(r[j]);
+                if (P.out_scale != nullptr) v *= __ldg(P.out_scale + (size_t)b * P.Cout + co);
+                v += nz;
+                if (P.bias != nullptr) v += __ldg(P.bias + co);
+                if (P.act) v = (v > 0.0f ? v : 0.2f * v) * 1.41421356237309515f;
+                ob[(size_t)co * plane] = v;
+              }
             }
           }
         }
@@ -268,7 +281,7 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp_u == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(128));
+  if (warp_u == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(P.tmem_cols));
 }
 
 }  // namespace conv
@@ -276,23 +289,26 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
 
 using namespace hav;
 
-static int conv_n_tile(int cout) {
+// output channels per CTA: 128 for the plain convolution, 64 for the polyphase transposed convolution (4 accumulators)
+static int conv_n_tile(int cout, int up) {
+  const int cap = up == 2 ? 64 : conv::kNTileMax;
   int n = (cout + 15) / 16 * 16;
-  return n < conv::kNTileMax ? n : conv::kNTileMax;
+  return n < cap ? n : cap;
 }
 
-extern "C" uint64_t hav_conv_wpack_bytes(int cout, int cin, int ksize) {
-  if (cout < 1 || cin < 1 || (ksize != 1 && ksize != 3)) return 0;
-  const int n_tile = conv_n_tile(cout), n_tiles = (cout + n_tile - 1) / n_tile, kblocks = (cin + conv::kCinBlk - 1) / conv::kCinBlk;
+extern "C" uint64_t hav_conv_wpack_bytes(int cout, int cin, int ksize, int up) {
+  if (cout < 1 || cin < 1 || (ksize != 1 && ksize != 3) || (up != 1 && up != 2)) return 0;
+  const int n_tile = conv_n_tile(cout, up), n_tiles = (cout + n_tile - 1) / n_tile, kblocks = (cin + conv::kCinBlk - 1) / conv::kCinBlk;
   return (uint64_t)n_tiles * kblocks * ksize * ksize * n_tile * conv::kCinBlk * 2;
 }
 
-extern "C" int hav_conv_pack_weights(void *wpack, const float *w, int cout, int cin, int ksize, float scale, int flip,
+extern "C" int hav_conv_pack_weights(void *wpack, const float *w, int cout, int cin, int ksize, float scale, int up,
                                      int transpose_io, int precision, void *stream) {
   if (wpack == nullptr || w == nullptr) return HAV_E_NULL;
-  if (cout < 1 || cin < 1 || (ksize != 1 && ksize != 3)) return HAV_E_SHAPE;
+  if (cout < 1 || cin < 1 || (ksize != 1 && ksize != 3) || (up != 1 && up != 2)) return HAV_E_SHAPE;
   if (precision != HAV_PREC_FP16 && precision != HAV_PREC_BF16) return HAV_E_VALUE;
-  const int n_tile = conv_n_tile(cout), n_tiles = (cout + n_tile - 1) / n_tile, kblocks = (cin + conv::kCinBlk - 1) / conv::kCinBlk;
+  const int flip = 0;
+  const int n_tile = conv_n_tile(cout, up), n_tiles = (cout + n_tile - 1) / n_tile, kblocks = (cin + conv::kCinBlk - 1) / conv::kCinBlk;
   if (precision == HAV_PREC_BF16)
     conv::pack_conv_weights_kernel<true><<<296, 256, 0, (cudaStream_t)stream>>>(w, (uint16_t *)wpack, cout, cin, ksize, n_tile, n_tiles,
                                                                                 kblocks, scale, flip, transpose_io);
@@ -327,8 +343,8 @@ extern "C" int hav_conv2d_forward(const hav_conv_args *a, void *stream) {
   P.act = a->act;
   int vh, vw;   // stride-1 output positions
   if (a->up == 2) {
-    P.pad = a->ksize - 1, vh = 2 * a->in_h - 1 + a->ksize - 1, vw = 2 * a->in_w - 1 + a->ksize - 1;   // conv_transpose2d, stride 2, pad 0
-    P.Ho = vh, P.Wo = vw;
+    P.pad = 1, vh = a->in_h + 1, vw = a->in_w + 1;      // polyphase tiles run over input positions 0..H (conv_transpose2d, stride 2, pad 0)
+    P.Ho = 2 * a->in_h + 1, P.Wo = 2 * a->in_w + 1;
   } else if (a->down == 2) {
     P.pad = 0, vh = a->in_h - a->ksize + 1, vw = a->in_w - a->ksize + 1;                                // stride 2, pad 0
     if (vh < 1 || vw < 1) return HAV_E_SHAPE;
@@ -336,8 +352,13 @@ extern "C" int hav_conv2d_forward(const hav_conv_args *a, void *stream) {
   } else {
     P.pad = a->ksize / 2, vh = a->in_h, vw = a->in_w, P.Ho = vh, P.Wo = vw;
   }
-  P.n_tile = conv_n_tile(a->cout), P.n_tiles = (a->cout + P.n_tile - 1) / P.n_tile;
+  P.n_tile = conv_n_tile(a->cout, a->up), P.n_tiles = (a->cout + P.n_tile - 1) / P.n_tile;
   P.kblocks = (a->cin + conv::kCinBlk - 1) / conv::kCinBlk;
+  {
+    const int need = (a->up == 2 ? 4 : 1) * P.n_tile;
+    P.tmem_cols = 32;
+    while (P.tmem_cols < need) P.tmem_cols *= 2;
+  }
   P.tiles_x = (vw + conv::kTileW - 1) / conv::kTileW, P.tiles_y = (vh + conv::kTileH - 1) / conv::kTileH;
   P.x = a->x, P.in_scale = a->in_scale, P.out_scale = a->out_scale, P.noise = a->noise, P.bias = a->bias;
   P.wpack = (const uint8_t *)a->wpack, P.out = a->out, P.noise_weight = a->noise_weight;
@@ -353,8 +374,9 @@ extern "C" int hav_conv2d_forward(const hav_conv_args *a, void *stream) {
     return cudaGetLastError();
   };
   const bool bf = a->precision == HAV_PREC_BF16;
-  if (a->ksize == 3) e = bf ? launch(conv::conv_tc_kernel<true, 3>) : launch(conv::conv_tc_kernel<false, 3>);
-  else e = bf ? launch(conv::conv_tc_kernel<true, 1>) : launch(conv::conv_tc_kernel<false, 1>);
+  if (a->up == 2) e = bf ? launch(conv::conv_tc_kernel<true, 3, true>) : launch(conv::conv_tc_kernel<false, 3, true>);
+  else if (a->ksize == 3) e = bf ? launch(conv::conv_tc_kernel<true, 3, false>) : launch(conv::conv_tc_kernel<false, 3, false>);
+  else e = bf ? launch(conv::conv_tc_kernel<true, 1, false>) : launch(conv::conv_tc_kernel<false, 1, false>);
   if (e != cudaSuccess) return (int)e;
   e = cudaGetLastError();
   return e == cudaSuccess ? HAV_OK : (int)e;

@@ -109,13 +109,13 @@ class _PackCache:
     def __init__(self):
         self.key, self.packed = None, None
 
-    def get(self, weight, scale, flip):
-        key = (weight.data_ptr(), weight._version, str(weight.device), flip)
+    def get(self, weight, scale, up):
+        key = (weight.data_ptr(), weight._version, str(weight.device), up)
         if key != self.key:
             w = weight.detach()
             if w.dim() == 5:
                 w = w[0]
-            self.packed = hconv.pack_weights(w.float(), scale, flip=flip)
+            self.packed = hconv.pack_weights(w.float(), scale, up=2 if up else 1)
             self.key = key
         return self.packed
 

@@ -147,8 +147,8 @@ int hav_get_rays(float *ray_batch, int height, int width, const float intr[4], c
  *   ksize 1 or 3;  up = 2: conv_transpose2d stride 2, padding 0 (:264-270), output (2H+1) x (2W+1) for ksize 3;
  *   down = 2: conv2d stride 2, padding 0 (:281-283);  otherwise stride 1, padding ksize/2 (:289-291).
  *   x [B,Cin,H,W], out [B,Cout,Ho,Wo] float32 NCHW; operands are rounded to 16 bit, accumulation is fp32 (TMEM).
- * Weights are packed once per weight update with hav_conv_pack_weights (w is [Cout,Cin,k,k], or [Cin,Cout,k,k] when
- * transpose_io != 0; flip != 0 mirrors the taps, which is what the transposed convolution needs).
+ * Weights are packed once per weight update with hav_conv_pack_weights for the SAME `up` they will be used with
+ * (w is [Cout,Cin,k,k], or [Cin,Cout,k,k] -- conv_transpose2d's own layout -- when transpose_io != 0).
  */
 typedef struct hav_conv_args {
   uint32_t struct_bytes; /* = sizeof(hav_conv_args) */
@@ -159,7 +159,7 @@ typedef struct hav_conv_args {
   int32_t noise_per_sample; /* 0: noise is [1,1,Ho,Wo] broadcast over the batch, 1: [B,1,Ho,Wo] */
   float noise_weight;       /* NoiseInjection.weight (model/styleUnet.py:300-310) */
   const float *x;
-  const void *wpack;        /* hav_conv_wpack_bytes(cout, cin, ksize) bytes written by hav_conv_pack_weights */
+  const void *wpack;        /* hav_conv_wpack_bytes(cout, cin, ksize, up) bytes written by hav_conv_pack_weights */
   const float *in_scale;    /* [B,Cin] modulation s, or NULL */
   const float *out_scale;   /* [B,Cout] demodulation, or NULL */
   const float *noise;       /* or NULL */
@@ -167,8 +167,8 @@ typedef struct hav_conv_args {
   float *out;
 } hav_conv_args;
 
-uint64_t hav_conv_wpack_bytes(int cout, int cin, int ksize);
-int hav_conv_pack_weights(void *wpack, const float *w, int cout, int cin, int ksize, float scale, int flip, int transpose_io,
+uint64_t hav_conv_wpack_bytes(int cout, int cin, int ksize, int up);
+int hav_conv_pack_weights(void *wpack, const float *w, int cout, int cin, int ksize, float scale, int up, int transpose_io,
                           int precision, void *stream);
 /* demod[b,co] = rsqrt(sum_{ci,kh,kw} (scale * w[co,ci,kh,kw] * style[b,ci])^2 + eps)   (model/styleUnet.py:256-258) */
 int hav_modconv_demod(float *demod, const float *w, const float *style, int batch, int cout, int cin, int ksize, float scale,

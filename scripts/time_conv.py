@@ -5,7 +5,7 @@ import torch
 from havatar_b200 import conv
 def bench(B, Cin, Cout, H, k, up=1, down=1, n=20):
     x = torch.randn(B, Cin, H, H, device="cuda"); w = torch.randn(Cout, Cin, k, k, device="cuda")
-    pw = conv.pack_weights(w, 1 / math.sqrt(Cin * k * k), flip=(up == 2))
+    pw = conv.pack_weights(w, 1 / math.sqrt(Cin * k * k), up=up)
     for _ in range(3): y = conv.conv2d(x, pw, up=up, down=down)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -44,7 +44,7 @@ def test_strided_and_transposed(B, Cin, Cout, H):
     got = conv.conv2d(x, conv.pack_weights(w, scale), down=2)
     assert got.shape == ref.shape and rel_err(got, ref) < 1e-2
     ref = F.conv_transpose2d(x, (w * scale).transpose(0, 1), stride=2, padding=0)
-    got = conv.conv2d(x, conv.pack_weights(w, scale, flip=True), up=2)
+    got = conv.conv2d(x, conv.pack_weights(w, scale, up=2), up=2)
     assert got.shape == ref.shape and rel_err(got, ref) < 1e-2
 
 
@@ -76,7 +76,7 @@ def test_modulated_conv_matches_reference_formulation(upsample, demodulate):
     d = conv.modconv_demod(W[0], s, scale) if demodulate else None
     if demodulate:
         assert torch.allclose(d, demod, rtol=1e-5, atol=1e-7)
-    got = conv.conv2d(x, conv.pack_weights(W[0], scale, flip=upsample), in_scale=s, out_scale=d, noise=noise, noise_weight=0.37,
+    got = conv.conv2d(x, conv.pack_weights(W[0], scale, up=2 if upsample else 1), in_scale=s, out_scale=d, noise=noise, noise_weight=0.37,
                       bias=bias, act=True, up=2 if upsample else 1)
     assert got.shape == ref.shape and rel_err(got, ref) < 1e-2
 
