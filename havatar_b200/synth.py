@@ -153,11 +153,35 @@ def styleunet_state(shapes, seed=0):
             v = 1.0 + 0.1 * n                      # EqualLinear(bias_init=1), model/styleUnet.py:214
         elif name.endswith("noise.weight"):
             v = 0.1 * n                            # NoiseInjection.weight (zero-initialised in the reference; nonzero so it is exercised)
-        elif name.startswith("style.") and name.endswith(".weight"):
+        elif (name.startswith("style.") or ".style." in name) and name.endswith(".weight"):
             v = 100.0 * n                          # randn / lr_mul, lr_mlp = 0.01 (styleUnet.py:131)
         elif name.endswith("bias"):
             v = 0.1 * n
         else:
             v = n
         out[name] = v.astype(F32)
+    return out
+
+
+def trainer_state(shapes, seed=0):
+    """Name-keyed values for every entry of a Trainer state_dict (reference model/nerf_trainer.py:12-36): StyleGAN_zxc
+    generators via styleunet_state, the radiance MLP via mlp_weights, VolumeDecoder convolutions ~N(0, 0.05^2),
+    latent codes ~N(0, 0.1^2).  Box-warp and identity buffers keep their constructor values."""
+    gen = {k: v for k, v in shapes.items() if ".XY_gen." in k or ".YZ_gen." in k}
+    out = styleunet_state(gen, seed)
+    mlp = mlp_weights(seed)
+    for name, shape in shapes.items():
+        if name in gen or name.endswith(("scale_factor", "trans_factor", "identity_trans")):
+            continue
+        short = name.replace("model_coarse.", "")
+        if short in mlp:
+            out[name] = mlp[short]
+        elif name == "latent_codes":
+            out[name] = (0.1 * named_normal(name, shape, seed)).astype(F32)
+        elif name.endswith("init_lc"):
+            out[name] = np.abs(named_normal(name, shape, seed)).astype(F32) % F32(1.0)
+        elif name.endswith("bias"):
+            out[name] = (0.05 * named_normal(name, shape, seed)).astype(F32)
+        else:
+            out[name] = (0.05 * named_normal(name, shape, seed)).astype(F32)
     return out

@@ -1,0 +1,219 @@
+"""Drop-in for the reference's render orchestrator `model/nerf_trainer.py::Trainer` on the B200 kernels.
+
+Same constructor (`Trainer(cfg, latent_codes_size=0, freeze_motion=True)`), same `forward(**data)` keys and return
+tuples (model/nerf_trainer.py:94-118), same attributes the entry scripts touch (`latent_codes`, `model_coarse`,
+`headpose_skin_net.{fix_canonical_W, canonical_Wvolume}`; avatarHD_reenactment.py:138-144), and the same state_dict
+keys / shapes, so `load_state_dict(ckpt['nerf_render'])` works.  What differs is underneath:
+
+  set_conditional_embedding  -> styleunet.StyleGAN_zxc on the tcgen05 convolution kernel
+  nerf_forward's chunk loop + predict_and_render_radiance (:38-92, :120-201) -> ONE hav_render_forward over all rays
+  the reference's torch.rand / torch.randn draws -> generated here in the reference's order and handed to the kernel
+
+Forward only (inference / validation renders): outputs are detached; training needs the fused backward.
+The skinning-weight VolumeDecoder (model/network/voxel_encoder.py:150-179) is input independent; it is evaluated with
+torch once per weight version and cached."""
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import render as hrender
+from . import styleunet
+
+
+def _box_warp(xb, yb, zb):
+    """utils/util.py:179-186."""
+    out_s, out_t = [], []
+    for lo, hi in (xb, yb, zb):
+        f = 2.0 / (float(hi) - float(lo))
+        out_s.append(f)
+        out_t.append(-(f * (float(lo) + float(hi)) * 0.5))
+    return out_s, out_t
+
+
+class _BoxWarp(nn.Module):
+    """UniformBoxWarp_new (utils/util.py:214-236): buffers scale_factor / trans_factor [1,3]."""
+
+    def __init__(self, scales, trans):
+        super().__init__()
+        self.register_buffer("scale_factor", torch.tensor(scales, dtype=torch.float32).reshape(1, 3))
+        self.register_buffer("trans_factor", torch.tensor(trans, dtype=torch.float32).reshape(1, 3))
+
+    def forward(self, x):
+        return x * self.scale_factor + self.trans_factor
+
+
+class _UpConv3D(nn.Module):
+    """UpConv3DBlock(up_mode='upsample') (voxel_encoder.py:183-211): keys up.1.{weight,bias}."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.up = nn.Sequential(nn.Upsample(mode="trilinear", scale_factor=2, align_corners=False),
+                                nn.Conv3d(cin, cout, kernel_size=3, padding=1, stride=1))
+        self.norm = nn.InstanceNorm3d(cout, affine=False)
+
+    def forward(self, x):
+        return self.norm(self.up(x))
+
+
+class VolumeDecoder(nn.Module):
+    """voxel_encoder.py:150-179 (plain torch: evaluated once per weight update, not on the per-frame path)."""
+
+    def __init__(self, num_in=1024, num_out=1, final_res=64):
+        super().__init__()
+        self.register_buffer("init_lc", torch.rand(1, num_in, 1, 1, 1))
+        n, lg = int(math.log2(final_res)), int(math.log2(num_in))
+        self.filters = nn.ModuleList([_UpConv3D(2 ** (lg - i), 2 ** (lg - i - 1)) for i in range(n)])
+        self.final_conv = nn.Conv3d(2 ** (lg - n), num_out, bias=True, kernel_size=3, padding=1, stride=1)
+        for m in self.modules():
+            if isinstance(m, nn.Conv3d):
+                nn.init.xavier_normal_(m.weight.data, gain=0.02)
+                nn.init.constant_(m.bias.data, 0.0)
+
+    def forward(self):
+        x = self.init_lc
+        for f in self.filters:
+            x = torch.relu(f(x))
+        x = torch.sigmoid(self.final_conv(x))
+        return torch.cat([x, 1 - x], dim=1)
+
+
+class SkinningField(nn.Module):
+    """Deformation_Field_new (model/Skinning_Field.py:43-98) as a parameter / volume holder: the warp itself runs inside
+    the fused render kernel."""
+
+    def __init__(self, gridwarper):
+        super().__init__()
+        self.canonical_Wvolume = VolumeDecoder(num_in=1024, num_out=1, final_res=64)
+        self.gridwarper = gridwarper
+        self.register_buffer("identity_trans", torch.eye(4, dtype=torch.float32)[:, :-1])
+        self.fix_canoW = False
+        self.canonical_W = None
+        self._key, self._vol = None, None
+
+    def fix_canonical_W(self):
+        """Skinning_Field.py:57-62: freeze the volume and pin the head region to the head bone."""
+        with torch.no_grad():
+            w = self.canonical_Wvolume().detach()
+            w[:, 1:, :, 0, :] = 1.0
+            w[:, 1:, :1, : w.shape[-1] // 8, :] = 1.0
+            self.canonical_W = torch.cat([1 - w[:, 1:], w[:, 1:]], dim=1).contiguous()
+        self.fix_canoW = True
+
+    def volume(self):
+        """[1,2,D,H,W] skinning-weight volume for the kernel (Skinning_Field.py:79), cached per weight version."""
+        if self.fix_canoW:
+            return self.canonical_W
+        key = tuple((p.data_ptr(), p._version) for p in self.canonical_Wvolume.parameters())
+        if key != self._key:
+            with torch.no_grad():
+                self._vol = self.canonical_Wvolume().detach().contiguous()
+            self._key = key
+        return self._vol
+
+
+class PlaneNeRF(nn.Module):
+    """ConditionalTriplaneNeRFModel_multiRender_split_view (model/nerf_model.py:10-117), default enc_mode='split'."""
+
+    def __init__(self, XYZ_bounding, latent_code_dim, feat_dim=64, plane_res=128):
+        super().__init__()
+        self.XY_gen = styleunet.StyleGAN_zxc(out_ch=feat_dim, out_size=plane_res, style_dim=latent_code_dim, middle_size=16,
+                                             zero_latent=False, zero_noise=True, no_skip=True, n_mlp=4, inp_size=256, inp_ch=7)
+        self.YZ_gen = styleunet.StyleGAN_zxc(out_ch=feat_dim, out_size=plane_res, style_dim=latent_code_dim, middle_size=16,
+                                             zero_latent=False, zero_noise=True, no_skip=True, n_mlp=4, inp_size=256, inp_ch=13)
+        s, t = _box_warp(*XYZ_bounding)
+        self.gridwarper = _BoxWarp(s, t)
+        self.layers_xyz = nn.ModuleList([nn.Linear(2 * feat_dim + 48, 128), nn.Linear(128, 128)])
+        self.fc_alpha = nn.Linear(128, 1)
+        self.fc_rgbFeat = nn.Linear(128, 64)
+        self.fc_rgb = nn.Linear(64, 3)
+        self.triPlane_embeddings = None
+
+    @torch.no_grad()
+    def set_conditional_embedding(self, front_render_cond, left_render_cond, right_render_cond, latents, cond_c):
+        """model/nerf_model.py:58-86."""
+        lat = [torch.cat([latents, cond_c.reshape(latents.shape[0], -1)], -1)]
+        left = left_render_cond.flip(dims=[3])
+        if left.shape[1] > 3:
+            left = left[:, :-1]
+        xy, _ = self.XY_gen(lat, front_render_cond.contiguous())
+        yz, _ = self.YZ_gen(lat, torch.cat([left, right_render_cond], dim=1).contiguous())
+        self.triPlane_embeddings = torch.stack([xy, yz], dim=0)
+
+    def mlp_weights(self):
+        return {"layers_xyz.0.weight": self.layers_xyz[0].weight, "layers_xyz.0.bias": self.layers_xyz[0].bias,
+                "layers_xyz.1.weight": self.layers_xyz[1].weight, "layers_xyz.1.bias": self.layers_xyz[1].bias,
+                "fc_alpha.weight": self.fc_alpha.weight, "fc_alpha.bias": self.fc_alpha.bias,
+                "fc_rgbFeat.weight": self.fc_rgbFeat.weight, "fc_rgbFeat.bias": self.fc_rgbFeat.bias,
+                "fc_rgb.weight": self.fc_rgb.weight, "fc_rgb.bias": self.fc_rgb.bias}
+
+
+class Trainer(nn.Module):
+    def __init__(self, cfg, latent_codes_size=0, freeze_motion=True, precision="fp16"):
+        super().__init__()
+        self.cfg = cfg
+        ld = cfg.experiment.latent_code_dim
+        self.latent_codes = nn.Parameter(torch.zeros(latent_codes_size, ld)) if latent_codes_size > 0 else None
+        code_dim = ld + (12 if cfg.experiment.cond_pose else 0) + (52 if cfg.experiment.cond_expr else 0)
+        if code_dim != ld + 12:
+            raise NotImplementedError("only the shipped conditioning (cond_pose=True, cond_expr=False) is built")
+        bounds = [list(b) for b in cfg.models.coarse.XYZ_bounding]
+        self.model_coarse = PlaneNeRF(bounds, code_dim)
+        self.render_size, self.gen_size = cfg.models.StyleUnet.inp_size, cfg.models.StyleUnet.out_size
+        yb = [0.3 * float(bounds[1][1]), float(bounds[1][1])]                 # nerf_trainer.py:29-34
+        s, t = _box_warp(bounds[0], yb, bounds[2])
+        self.headpose_skin_net = SkinningField(_BoxWarp(s, t))
+        self.precision = precision
+
+    def _boxes(self):
+        g, h = self.model_coarse.gridwarper, self.headpose_skin_net.gridwarper
+        f = lambda b: [float(v) for v in b.detach().cpu().reshape(-1)]
+        key = (g.scale_factor.data_ptr(), g.scale_factor._version, h.scale_factor._version)
+        if getattr(self, "_box_key", None) != key:
+            self._box_val, self._box_key = (f(g.scale_factor), f(g.trans_factor), f(h.scale_factor), f(h.trans_factor)), key
+        return self._box_val
+
+    @torch.no_grad()
+    def nerf_forward(self, **inputs):
+        """model/nerf_trainer.py:38-92 without the chunk loop; returns the 7-tuple of predict_and_render_radiance."""
+        opt = getattr(self.cfg.nerf, inputs["mode"])
+        inv_head_T = inputs["inv_head_T"]
+        self.model_coarse.set_conditional_embedding(inputs["front_render_cond"], inputs["left_render_cond"],
+                                                    inputs["right_render_cond"], inputs["latent_code"],
+                                                    inv_head_T.reshape(inv_head_T.shape[0], -1))
+        ray_batch, bg = inputs["ray_batch"], inputs["background_prior"]
+        B, R = ray_batch.shape[:2]
+        dev = ray_batch.device
+        nc, nf = int(opt.num_coarse), int(opt.num_fine)
+        rnd = {}
+        if opt.perturb:                                                           # :132-139, utils/nerf_util.py:93-96
+            rnd["t_rand"] = torch.rand(B, R, nc, dtype=torch.float32, device=dev)
+            if nf > 0:
+                rnd["u_rand"] = torch.rand([B * R, nf], dtype=torch.float32).to(dev).view(B, R, nf)   # CPU generator, like the reference
+        std = float(opt.radiance_field_noise_std)
+        if std > 0.0:                                                             # utils/nerf_util.py:47-57
+            rnd["noise_coarse"] = torch.randn(B, R, nc, device=dev) * std
+            if nf > 0:
+                rnd["noise_fine"] = torch.randn(B, R, (nc + 1) // 2 + nf, device=dev) * std
+        o = hrender.render_rays(ray_batch, bg, inv_head_T, self.model_coarse.triPlane_embeddings, self.headpose_skin_net.volume(),
+                                self.model_coarse.mlp_weights(), nc, nf, boxes=self._boxes(), precision=self.precision, **rnd)
+        return o.rgb_coarse, o.depth_coarse, o.acc_coarse, o.weights_max, o.rgb_fine, o.depth_fine, o.acc_fine
+
+    @torch.no_grad()
+    def forward(self, **data):
+        """model/nerf_trainer.py:94-118 (including its quirk ii: slots 1 and 5 of the long tuple are both depth_fine)."""
+        ray_batch = data["ray_batch"]
+        B = ray_batch.shape[0]
+        latent_code = self.latent_codes[data["fidx"]] if data["mode"] == "train" else self.latent_codes[0:1]
+        latent_code_loss = torch.square(latent_code - self.latent_codes.mean(dim=0, keepdims=True)).mean()
+        rgb_c, _, acc_c, weights, rgb_f, depth_f, acc_f = self.nerf_forward(
+            ray_batch=ray_batch, background_prior=data["background_prior"], latent_code=latent_code, inv_head_T=data["inv_head_T"],
+            front_render_cond=data["front_render_cond"], left_render_cond=data["left_render_cond"],
+            right_render_cond=data["right_render_cond"], mode=data["mode"])
+        if data["render_full_img"]:
+            render = rgb_f if rgb_f is not None else rgb_c
+            mask = acc_f if acc_f is not None else acc_c
+            s = self.render_size
+            return (render.reshape(B, s, s, -1).permute(0, 3, 1, 2), mask.reshape(B, s, s, -1).permute(0, 3, 1, 2), latent_code_loss)
+        return rgb_c, depth_f, acc_c, weights, rgb_f, depth_f, acc_f, latent_code_loss

@@ -237,6 +237,40 @@ def gen_styleunet(torch):
         print(name, tuple(out.shape), "abs mean %.3f max %.3f" % (out.abs().mean(), out.abs().max()))
 
 
+def trainer_inputs(seed=3, render_size=128, batch=1):
+    """Deterministic inputs of the Trainer golden (shared with tests/test_trainer.py)."""
+    sc = synth.scene(batch=batch, height=render_size, width=render_size, seed=seed)
+    conds = {k: np.abs(synth.named_normal("input." + k, (batch, 7, 256, 256), seed)).astype(np.float32) % np.float32(1.0)
+             for k in ("front_render_cond", "left_render_cond", "right_render_cond")}
+    noise0 = {g: synth.named_normal("input.%s.noise0" % g, (1, 1, 16, 16), seed) for g in ("XY_gen", "YZ_gen")}
+    return sc, conds, noise0
+
+
+def gen_trainer(torch):
+    """Whole-orchestrator golden: the unmodified reference Trainer.forward (mode 'validation', full 128x128 frame,
+    hierarchical 64 + 16, perturb off) on CPU.  Stores every 4th pixel of the [1,67,128,128] render and the mask."""
+    from oracle import ref_shim
+    from model.nerf_trainer import Trainer
+
+    cfg = ref_shim.load_cfg()
+    cfg.nerf.validation.perturb = False
+    net = Trainer(cfg, 4)
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    sd = synth.trainer_state(shapes, seed=3)
+    missing = net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    assert not missing.unexpected_keys, missing
+    sc, conds, noise0 = trainer_inputs()
+    net.model_coarse.XY_gen.zero_noise[0] = torch.from_numpy(noise0["XY_gen"])
+    net.model_coarse.YZ_gen.zero_noise[0] = torch.from_numpy(noise0["YZ_gen"])
+    with torch.no_grad():
+        render, mask, lat = net(mode="validation", fidx=None, render_full_img=True, ray_batch=torch.from_numpy(sc["ray_batch"]),
+                                background_prior=torch.from_numpy(sc["background_prior"]), inv_head_T=torch.from_numpy(sc["inv_head_T"]),
+                                **{k: torch.from_numpy(v) for k, v in conds.items()})
+    print("trainer", tuple(render.shape), tuple(mask.shape), float(lat), "acc mean %.3f" % float(mask.mean()))
+    np.savez_compressed(os.path.join(GOLD, "trainer_validation.npz"), render=render.numpy()[:, :, ::4, ::4], mask=mask.numpy()[:, :, ::4, ::4],
+                        latent_code_loss=np.float32(lat), state_dict_shapes=json.dumps({k: list(v) for k, v in shapes.items()}))
+
+
 def main():
     from oracle import ref_shim
 
@@ -249,6 +283,7 @@ def main():
     gen_stages(torch)
     gen_ops(torch)
     gen_styleunet(torch)
+    gen_trainer(torch)
     from model.nerf_trainer import Trainer
 
     trainer = Trainer(cfg, 4)

@@ -1,0 +1,63 @@
+"""Drop-in Trainer (havatar_b200/trainer.py): checkpoint compatibility on CPU and whole-orchestrator parity on the GPU with
+the unmodified reference Trainer.forward run on CPU (tests/golden/trainer_validation.npz, oracle/gen_golden.py::gen_trainer)."""
+import json
+import os
+from types import SimpleNamespace as NS
+
+import numpy as np
+import pytest
+import torch
+
+from havatar_b200 import synth, trainer
+from oracle.gen_golden import trainer_inputs
+
+
+def shipped_cfg(perturb=False):
+    """The fields of config/singleview_512_base.yml the orchestrator reads."""
+    mode = lambda: NS(num_coarse=64, num_fine=16, perturb=perturb, radiance_field_noise_std=0.0, chunksize=4096)
+    return NS(experiment=NS(latent_code_dim=32, cond_pose=True, cond_expr=False, model_mode=None),
+              models=NS(coarse=NS(XYZ_bounding=[[-1.5, 1.5], [-1.6, 1.4], [-1.6, 1.2]]), StyleUnet=NS(inp_size=128, out_size=512)),
+              nerf=NS(train=mode(), validation=mode()))
+
+
+def test_state_dict_is_checkpoint_compatible(golden_dir):
+    g = np.load(os.path.join(golden_dir, "trainer_validation.npz"))
+    want = {k: tuple(v) for k, v in json.loads(str(g["state_dict_shapes"])).items()}
+    net = trainer.Trainer(shipped_cfg(), 4)
+    got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert got == want
+    assert abs(sum(p.numel() for p in net.parameters()) / 1e6 - 80.86) < 0.01      # SURVEY.md section 5 probe
+
+
+@pytest.mark.gpu
+def test_validation_forward_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "trainer_validation.npz"))
+    net = trainer.Trainer(shipped_cfg(), 4)
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    sd = synth.trainer_state(shapes, seed=3)
+    missing = net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    assert not missing.unexpected_keys
+    net = net.cuda()
+    sc, conds, noise0 = trainer_inputs()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    net.model_coarse.XY_gen.zero_noise[0] = t(noise0["XY_gen"])
+    net.model_coarse.YZ_gen.zero_noise[0] = t(noise0["YZ_gen"])
+    render, mask, lat = net(mode="validation", fidx=None, render_full_img=True, ray_batch=t(sc["ray_batch"]),
+                            background_prior=t(sc["background_prior"]), inv_head_T=t(sc["inv_head_T"]),
+                            **{k: t(v) for k, v in conds.items()})
+    torch.cuda.synchronize()
+    assert render.shape == (1, 67, 128, 128) and mask.shape == (1, 1, 128, 128)
+    assert abs(float(lat) - float(g["latent_code_loss"])) < 1e-7
+    r, m = render.cpu().numpy()[:, :, ::4, ::4], mask.cpu().numpy()[:, :, ::4, ::4]
+    # fp16 operands through two 20-conv plane generators and the radiance MLP: 3e-2 of the output range (stated)
+    assert np.abs(m - g["mask"]).max() < 3e-2, float(np.abs(m - g["mask"]).max())
+    err = np.abs(r - g["render"]).max() / np.abs(g["render"]).max()
+    assert err < 3e-2, float(err)
+    # the frozen-volume path of inference (avatarHD_reenactment.py:144)
+    net.headpose_skin_net.fix_canonical_W()
+    w = net.headpose_skin_net.volume()
+    assert w.shape == (1, 2, 64, 64, 64) and float((w[:, 0] + w[:, 1] - 1).abs().max()) < 1e-6
+    assert float(w[0, 1, :, 0, :].min()) == 1.0
+    render2, _, _ = net(mode="validation", fidx=None, render_full_img=True, ray_batch=t(sc["ray_batch"]),
+                        background_prior=t(sc["background_prior"]), inv_head_T=t(sc["inv_head_T"]), **{k: t(v) for k, v in conds.items()})
+    assert torch.isfinite(render2).all()
