@@ -449,6 +449,48 @@ class SWGAN_unet(nn.Module):
         return self.iwt(skip)
 
 
+class Discriminator(nn.Module):
+    """styleUnet.py:470-562 (wavelet discriminator of stage two, train_avatarHD.py:112).  Forward only: the GAN losses need
+    first- and second-order gradients through it (utils/styleUnet_util.py:65-79), which need the convolution backward."""
+
+    def __init__(self, size, img_channel=6, channel_multiplier=2, blur_kernel=(1, 3, 3, 1), c_dim=0):
+        super().__init__()
+        if c_dim > 0:
+            raise NotImplementedError("pose-conditioned discriminator (c_dim > 0) is not used by the reference scripts")
+        channels = _CHANNELS(channel_multiplier)
+        self.dwt = HaarTransform(img_channel)
+        self.from_rgbs, self.convs = nn.ModuleList(), nn.ModuleList()
+        log_size = int(math.log(size, 2)) - 1
+        in_channel = channels[size]
+        for i in range(log_size, 2, -1):
+            out_channel = channels[2 ** (i - 1)]
+            self.from_rgbs.append(FromRGB(in_channel, img_channel, downsample=i != log_size))
+            self.convs.append(ConvBlock(in_channel, out_channel, blur_kernel))
+            in_channel = out_channel
+        self.from_rgbs.append(FromRGB(channels[4], img_channel))
+        self.stddev_group, self.stddev_feat = 4, 1
+        self.final_conv = ConvLayer(in_channel + 1, channels[4], 3)
+        self.final_linear = nn.Sequential(EqualLinear(channels[4] * 4 * 4, channels[4], activation="fused_lrelu"),
+                                          EqualLinear(channels[4], 1))
+        self.c_dim = c_dim
+
+    @torch.no_grad()
+    def forward(self, x, flat_pose=None):
+        x = self.dwt(x)
+        out = None
+        for from_rgb, block in zip(self.from_rgbs, self.convs):
+            x, out = from_rgb(x, out)
+            out = block(out)
+        _, out = self.from_rgbs[-1](x, out)
+        b, c, h, w = out.shape
+        group = min(b, self.stddev_group)                                  # minibatch standard deviation (:539-545)
+        sd = out.view(group, -1, self.stddev_feat, c // self.stddev_feat, h, w)
+        sd = torch.sqrt(sd.var(0, unbiased=False) + 1e-8).mean([2, 3, 4], keepdims=True).squeeze(2)
+        out = torch.cat([out, sd.repeat(group, 1, h, w)], 1).contiguous()
+        out = self.final_conv(out)
+        return self.final_linear(out.view(b, -1))
+
+
 class StyleGAN_zxc(nn.Module):
     """styleUnet.py:631-878, the configuration the plane generators use (model/nerf_model.py:39-42): condition-image
     encoder (inp_size > 0) and no_skip=True (1x1 conv_out instead of the ToRGB pyramid)."""

@@ -199,6 +199,8 @@ STYLEUNET_CASES = {
     # SWGAN_unet at reduced size (same code path as the shipped 128 -> 512: encoder 16,8 -> decoder 16,32,64 -> IWT 128)
     "swgan_32_128": dict(net="SWGAN_unet", kw=dict(inp_size=32, inp_ch=8, out_ch=3, out_size=128, style_dim=64, n_mlp=4), batch=2, seed=1),
     # plane generator configuration of model/nerf_model.py:39-42 at reduced size (cond 64x64, planes 32x32)
+    # wavelet discriminator (stage two), reduced size
+    "disc_64": dict(net="Discriminator", kw=dict(size=64, img_channel=3), batch=4, seed=4),
     "zxc_64_32": dict(net="StyleGAN_zxc", kw=dict(out_ch=16, out_size=32, style_dim=44, middle_size=16, zero_latent=False,
                                                    zero_noise=True, no_skip=True, n_mlp=4, inp_size=64, inp_ch=7), batch=2, seed=2),
 }
@@ -208,6 +210,8 @@ def styleunet_inputs(case, net):
     """Deterministic inputs of a STYLEUNET_CASES entry (shared with tests/test_styleunet_gpu.py)."""
     kw, B, seed = case["kw"], case["batch"], case["seed"]
     sd = synth.styleunet_state({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed)
+    if case["net"] == "Discriminator":
+        return sd, None, synth.named_normal("input.image", (B, kw["img_channel"], kw["size"], kw["size"]), seed), None
     style = synth.named_normal("input.style", (B, kw["style_dim"]), seed)
     cond = synth.named_normal("input.cond", (B, kw["inp_ch"], kw["inp_size"], kw["inp_size"]), seed)
     if case["net"] == "SWGAN_unet":
@@ -229,6 +233,8 @@ def gen_styleunet(torch):
         with torch.no_grad():
             if case["net"] == "SWGAN_unet":
                 out = net([torch.from_numpy(style)], torch.from_numpy(cond), noise=[torch.from_numpy(n) for n in noise])
+            elif case["net"] == "Discriminator":
+                out = net(torch.from_numpy(cond))
             else:
                 net.zero_noise[0] = torch.from_numpy(noise[0])        # the fixed first-layer draw (styleUnet.py:748)
                 out, _ = net([torch.from_numpy(style)], torch.from_numpy(cond))

@@ -46,6 +46,8 @@ def test_forward_matches_reference_golden(golden_dir, name):
     t = lambda a: torch.from_numpy(a).cuda()
     if case["net"] == "SWGAN_unet":
         out = net([t(style)], t(cond), noise=[t(n) for n in noise])
+    elif case["net"] == "Discriminator":
+        out = net(t(cond))
     else:
         net.zero_noise[0] = t(noise[0])
         out, _ = net([t(style)], t(cond))
