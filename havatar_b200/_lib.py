@@ -41,6 +41,7 @@ class ConvArgs(C.Structure):
         ("struct_bytes", C.c_uint32), ("precision", C.c_int32), ("batch", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32),
         ("in_h", C.c_int32), ("in_w", C.c_int32), ("ksize", C.c_int32), ("up", C.c_int32), ("down", C.c_int32),
         ("act", C.c_int32), ("noise_per_sample", C.c_int32), ("noise_weight", C.c_float),
+        ("in_layout", C.c_int32), ("out_layout", C.c_int32),
         ("x", _fp), ("wpack", _fp), ("in_scale", _fp), ("out_scale", _fp), ("noise", _fp), ("bias", _fp), ("out", _fp),
     ]
 
@@ -51,6 +52,7 @@ SIGNATURES = {
     "hav_error_string": (C.c_char_p, [C.c_int]),
     "hav_fused_bias_act": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                      C.c_float, C.c_float, _fp]),
+    "hav_upfirdn2d_cl": (C.c_int, [_fp, _fp, _fp] + [C.c_int] * 12 + [_fp, C.c_float, C.c_int, _fp, C.c_int, _fp]),
     "hav_upfirdn2d": (C.c_int, [_fp, _fp, _fp] + [C.c_int] * 14 + [_fp]),
     "hav_render_workspace_bytes": (C.c_uint64, [C.POINTER(RenderArgs)]),
     "hav_render_forward": (C.c_int, [C.POINTER(RenderArgs), _fp]),

@@ -59,12 +59,31 @@ def modconv_demod(weight, style, scale, eps=1e-8):
     return out
 
 
-def conv2d(x, packed, in_scale=None, out_scale=None, noise=None, noise_weight=0.0, bias=None, act=False, up=1, down=1):
+def is_cl(t):
+    """Channels-last fp16 hand-over tensors ([B,H,W,C] torch.float16) are told apart from NCHW fp32 ones by dtype."""
+    return t.dtype == torch.float16
+
+
+def to_nchw(t):
+    return t.permute(0, 3, 1, 2).float().contiguous() if is_cl(t) else t
+
+
+def conv2d(x, packed, in_scale=None, out_scale=None, noise=None, noise_weight=0.0, bias=None, act=False, up=1, down=1, out_cl=False):
     """out = act(conv(x * in_scale[:, :, None, None], W) * out_scale[:, :, None, None] + noise_weight * noise + bias).
-    up=2: conv_transpose2d(stride 2, pad 0) (pack the weight with up=2); down=2: stride 2, pad 0; else pad k//2."""
+    up=2: conv_transpose2d(stride 2, pad 0) (pack the weight with up=2); down=2: stride 2, pad 0; else pad k//2.
+    x is NCHW float32, or channels-last float16 [B,H,W,C] (the internal hand-over layout); out_cl selects the output layout."""
     L = _lib.lib()
-    x = _check(x, "x")
-    B, cin, H, W = [int(v) for v in x.shape]
+    in_cl = is_cl(x)
+    if in_cl:
+        if not x.is_cuda or x.dim() != 4:
+            raise _lib.HavError("channels-last input must be a [B,H,W,C] float16 CUDA tensor")
+        x = x.detach().contiguous()
+        B, H, W, cin = [int(v) for v in x.shape]
+    else:
+        x = _check(x, "x")
+        B, cin, H, W = [int(v) for v in x.shape]
+    if (in_cl or out_cl) and packed.precision != "fp16":
+        raise _lib.HavError("channels-last tensors need fp16-packed weights")
     if cin != packed.cin:
         raise _lib.HavError("x has %d channels, the packed weight expects %d" % (cin, packed.cin))
     k = packed.ksize
@@ -102,10 +121,47 @@ def conv2d(x, packed, in_scale=None, out_scale=None, noise=None, noise_weight=0.
             raise _lib.HavError("noise must be [1 or B,1,%d,%d]" % (Ho, Wo))
         a.noise, a.noise_weight = C.c_void_p(nz.data_ptr()), float(noise_weight)
         keep.append(nz)
-    out = torch.empty((B, packed.cout, Ho, Wo), dtype=torch.float32, device=x.device)
+    a.in_layout, a.out_layout = int(in_cl), int(bool(out_cl))
+    if out_cl:
+        out = torch.empty((B, Ho, Wo, packed.cout), dtype=torch.float16, device=x.device)
+    else:
+        out = torch.empty((B, packed.cout, Ho, Wo), dtype=torch.float32, device=x.device)
     a.out = C.c_void_p(out.data_ptr())
     with torch.cuda.device(x.device):
         st = torch.cuda.current_stream(x.device).cuda_stream
         _lib.check(L.hav_conv2d_forward(C.byref(a), C.c_void_p(st)), "hav_conv2d_forward")
     del keep
+    return out
+
+
+def upfirdn2d_cl(x, kernel, up=1, down=1, pad=(0, 0), noise=None, noise_weight=0.0, bias=None, act=False):
+    """upfirdn2d on a channels-last float16 tensor [B,H,W,C] with the StyledConv tail fused in:
+    act(fir(x) + noise_weight * noise + bias) (C ABI: hav_upfirdn2d_cl)."""
+    L = _lib.lib()
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float16 and x.dim() == 4):
+        raise _lib.HavError("x must be a [B,H,W,C] float16 CUDA tensor")
+    x = x.detach().contiguous()
+    k = _check(kernel, "kernel")
+    if len(pad) == 2:
+        pad = (pad[0], pad[1], pad[0], pad[1])
+    B, H, W, Cc = [int(v) for v in x.shape]
+    kh, kw = int(k.shape[0]), int(k.shape[1])
+    Ho = (H * up + pad[2] + pad[3] - kh + down) // down
+    Wo = (W * up + pad[0] + pad[1] - kw + down) // down
+    out = torch.empty((B, Ho, Wo, Cc), dtype=torch.float16, device=x.device)
+    nz = None if noise is None else _check(noise, "noise")
+    per_sample = 0
+    if nz is not None:
+        if nz.numel() == B * Ho * Wo and B > 1:
+            per_sample = 1
+        elif nz.numel() != Ho * Wo:
+            raise _lib.HavError("noise must be [1 or B,1,%d,%d]" % (Ho, Wo))
+    bs = None if bias is None else _check(bias, "bias")
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(L.hav_upfirdn2d_cl(C.c_void_p(out.data_ptr()), C.c_void_p(x.data_ptr()), C.c_void_p(k.data_ptr()), B, H, W, Cc, kh, kw,
+                                      int(up), int(down), int(pad[0]), int(pad[1]), int(pad[2]), int(pad[3]),
+                                      C.c_void_p(nz.data_ptr()) if nz is not None else None, float(noise_weight), per_sample,
+                                      C.c_void_p(bs.data_ptr()) if bs is not None else None, int(bool(act)), C.c_void_p(st)),
+                   "hav_upfirdn2d_cl")
     return out

@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(128) modconv_demod_kernel(const float *__restr
 constexpr int kStageThreads = 256;
 constexpr int kThreadsV2 = kStageThreads + 32;
 
-template <bool kBF16, int KS, bool UPP>
+// INCL / OUTCL: input / output tensor is channels-last fp16 ([B,H,W,C] half) instead of NCHW fp32
+template <bool kBF16, int KS, bool UPP, bool INCL, bool OUTCL>
 __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
@@ -199,12 +200,20 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
   } else {
     // ================= staging warps =================
     const float *xb = P.x + (size_t)b * P.Cin * P.H * P.W;
+    const uint16_t *xcl = reinterpret_cast<const uint16_t *>(P.x);
     const size_t cstride = (size_t)P.H * P.W;
     for (int kb = 0; kb < P.kblocks; ++kb) {
       uint8_t *A = smem + kSmA + (kb & 1) * kASlotBytes;
       float *sc = sscale + (kb & 1) * kCinBlk;
       if (kb >= 2) mbar_wait_spin(bar_afree + (kb & 1) * 8, ((kb - 2) >> 1) & 1);   // MMAs of block kb-2 are done with this buffer
-      if (tid < kCinBlk) {
+      if (INCL) {
+        if (tid < kCinBlk / 2 && P.in_scale != nullptr) {   // packed fp16 pairs (c, c+1)
+          const int c = kb * kCinBlk + 2 * tid;
+          const float s0 = c < P.Cin ? __ldg(P.in_scale + (size_t)b * P.Cin + c) : 0.0f;
+          const float s1 = c + 1 < P.Cin ? __ldg(P.in_scale + (size_t)b * P.Cin + c + 1) : 0.0f;
+          reinterpret_cast<uint32_t *>(sc)[tid] = pack2<false>(s0, s1);
+        }
+      } else if (tid < kCinBlk) {
         const int c = kb * kCinBlk + tid;
         sc[tid] = (c < P.Cin) ? (P.in_scale != nullptr ? __ldg(P.in_scale + (size_t)b * P.Cin + c) : 1.0f) : 0.0f;
       }
@@ -218,13 +227,25 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
         const int Y = vy0 + py - P.pad, X = vx0 + px - P.pad;
         const bool ok = Y >= 0 && X >= 0 && Y < P.H && X < P.W;
         const int c0 = kb * kCinBlk + chunk * 8;
-        float v[8];
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (INCL) {
+          // channels-last fp16: the 8 channels of this unit are one aligned 16-byte load; modulate as packed pairs
+          if (ok && c0 < P.Cin) {
+            u = __ldg(reinterpret_cast<const uint4 *>(xcl + (((size_t)b * P.H + Y) * P.W + X) * P.Cin + c0));
+            if (P.in_scale != nullptr) {
+              const uint32_t *sh = reinterpret_cast<const uint32_t *>(sc) + chunk * 4;   // 4 packed pairs of this chunk
+              u.x = mul2<false>(u.x, sh[0]), u.y = mul2<false>(u.y, sh[1]), u.z = mul2<false>(u.z, sh[2]), u.w = mul2<false>(u.w, sh[3]);
+            }
+          }
+        } else {
+          float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (ok && c0 + e < P.Cin) ? __ldg(xb + (size_t)(c0 + e) * cstride + (size_t)Y * P.W + X) : 0.0f;
+          for (int e = 0; e < 8; ++e) v[e] = (ok && c0 + e < P.Cin) ? __ldg(xb + (size_t)(c0 + e) * cstride + (size_t)Y * P.W + X) : 0.0f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] *= sc[chunk * 8 + e];
-        *reinterpret_cast<uint4 *>(A + chunk * chunk_bytes + hp * 16) =
-            make_uint4(pack2<kBF16>(v[0], v[1]), pack2<kBF16>(v[2], v[3]), pack2<kBF16>(v[4], v[5]), pack2<kBF16>(v[6], v[7]));
+          for (int e = 0; e < 8; ++e) v[e] *= sc[chunk * 8 + e];
+          u = make_uint4(pack2<kBF16>(v[0], v[1]), pack2<kBF16>(v[2], v[3]), pack2<kBF16>(v[4], v[5]), pack2<kBF16>(v[6], v[7]));
+        }
+        *reinterpret_cast<uint4 *>(A + chunk * chunk_bytes + hp * 16) = u;
         hp += kStageThreads;
         while (hp >= halo_px) hp -= halo_px, ++chunk;
       }
@@ -262,17 +283,31 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
               : "r"(trow + ph * P.n_tile + c0));
           tmem_wait_ld();
           if (ok) {
+            float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int co = nt * P.n_tile + c0 + j;
+              float t = __uint_as_float(r[j]);
               if (co < P.Cout) {
-                float v = __uint_as_float(r[j]);
-                if (P.out_scale != nullptr) v *= __ldg(P.out_scale + (size_t)b * P.Cout + co);
-                v += nz;
-                if (P.bias != nullptr) v += __ldg(P.bias + co);
-                if (P.act) v = (v > 0.0f ? v : 0.2f * v) * 1.41421356237309515f;
-                ob[(size_t)co * plane] = v;
+                if (P.out_scale != nullptr) t *= __ldg(P.out_scale + (size_t)b * P.Cout + co);
+                t += nz;
+                if (P.bias != nullptr) t += __ldg(P.bias + co);
+                if (P.act) t = (t > 0.0f ? t : 0.2f * t) * 1.41421356237309515f;
               }
+              v[j] = t;
+            }
+            const int co0 = nt * P.n_tile + c0;
+            if (OUTCL) {
+              // channels-last fp16: 16 channels of this pixel = 32 contiguous bytes (Cout % 8 == 0 is checked on the host)
+              uint16_t *oc = reinterpret_cast<uint16_t *>(P.out) + (((size_t)b * P.Ho + oy) * P.Wo + ox) * P.Cout + co0;
+              if (co0 + 8 <= P.Cout)
+                *reinterpret_cast<uint4 *>(oc) = make_uint4(pack2<false>(v[0], v[1]), pack2<false>(v[2], v[3]), pack2<false>(v[4], v[5]), pack2<false>(v[6], v[7]));
+              if (co0 + 16 <= P.Cout)
+                *reinterpret_cast<uint4 *>(oc + 8) = make_uint4(pack2<false>(v[8], v[9]), pack2<false>(v[10], v[11]), pack2<false>(v[12], v[13]), pack2<false>(v[14], v[15]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (co0 + j < P.Cout) ob[(size_t)(co0 + j) * plane] = v[j];
             }
           }
         }
@@ -335,6 +370,10 @@ extern "C" int hav_conv2d_forward(const hav_conv_args *a, void *stream) {
   if ((a->ksize != 1 && a->ksize != 3) || (a->up != 1 && a->up != 2) || (a->down != 1 && a->down != 2)) return HAV_E_VALUE;
   if (a->up == 2 && (a->down == 2 || a->ksize != 3)) return HAV_E_VALUE;
   if (a->precision != HAV_PREC_FP16 && a->precision != HAV_PREC_BF16) return HAV_E_VALUE;
+  if ((a->in_layout | a->out_layout) & ~1) return HAV_E_VALUE;
+  if ((a->in_layout || a->out_layout) && a->precision != HAV_PREC_FP16) return HAV_E_VALUE;
+  if (a->in_layout && (a->cin % 8) != 0) return HAV_E_SHAPE;
+  if (a->out_layout && (a->cout % 8) != 0) return HAV_E_SHAPE;
   if (a->batch == 0) return HAV_OK;
   if (a->x == nullptr || a->wpack == nullptr || a->out == nullptr) return HAV_E_NULL;
   conv::ConvDev P;
@@ -360,8 +399,8 @@ extern "C" int hav_conv2d_forward(const hav_conv_args *a, void *stream) {
     while (P.tmem_cols < need) P.tmem_cols *= 2;
   }
   P.tiles_x = (vw + conv::kTileW - 1) / conv::kTileW, P.tiles_y = (vh + conv::kTileH - 1) / conv::kTileH;
-  P.x = a->x, P.in_scale = a->in_scale, P.out_scale = a->out_scale, P.noise = a->noise, P.bias = a->bias;
-  P.wpack = (const uint8_t *)a->wpack, P.out = a->out, P.noise_weight = a->noise_weight;
+  P.x = (const float *)a->x, P.in_scale = a->in_scale, P.out_scale = a->out_scale, P.noise = a->noise, P.bias = a->bias;
+  P.wpack = (const uint8_t *)a->wpack, P.out = (float *)a->out, P.noise_weight = a->noise_weight;
   P.noise_bstride = a->noise_per_sample ? P.Ho * P.Wo : 0;
   const long sp_tiles = (long)a->batch * P.tiles_x * P.tiles_y;
   if (sp_tiles > 2147483647L || P.n_tiles > 65535) return HAV_E_SHAPE;
@@ -374,9 +413,24 @@ extern "C" int hav_conv2d_forward(const hav_conv_args *a, void *stream) {
     return cudaGetLastError();
   };
   const bool bf = a->precision == HAV_PREC_BF16;
-  if (a->up == 2) e = bf ? launch(conv::conv_tc_kernel<true, 3, true>) : launch(conv::conv_tc_kernel<false, 3, true>);
-  else if (a->ksize == 3) e = bf ? launch(conv::conv_tc_kernel<true, 3, false>) : launch(conv::conv_tc_kernel<false, 3, false>);
-  else e = bf ? launch(conv::conv_tc_kernel<true, 1, false>) : launch(conv::conv_tc_kernel<false, 1, false>);
+  const int lay = (a->in_layout ? 2 : 0) | (a->out_layout ? 1 : 0);
+  if (bf) {   // bf16 operands: NCHW fp32 tensors only
+    if (a->up == 2) e = launch(conv::conv_tc_kernel<true, 3, true, false, false>);
+    else if (a->ksize == 3) e = launch(conv::conv_tc_kernel<true, 3, false, false, false>);
+    else e = launch(conv::conv_tc_kernel<true, 1, false, false, false>);
+  } else {
+#define HAV_CONV_DISPATCH(KS_, UPP_)                                                        \
+  switch (lay) {                                                                            \
+    case 0: e = launch(conv::conv_tc_kernel<false, KS_, UPP_, false, false>); break;        \
+    case 1: e = launch(conv::conv_tc_kernel<false, KS_, UPP_, false, true>); break;         \
+    case 2: e = launch(conv::conv_tc_kernel<false, KS_, UPP_, true, false>); break;         \
+    default: e = launch(conv::conv_tc_kernel<false, KS_, UPP_, true, true>); break;         \
+  }
+    if (a->up == 2) { HAV_CONV_DISPATCH(3, true) }
+    else if (a->ksize == 3) { HAV_CONV_DISPATCH(3, false) }
+    else { HAV_CONV_DISPATCH(1, false) }
+#undef HAV_CONV_DISPATCH
+  }
   if (e != cudaSuccess) return (int)e;
   e = cudaGetLastError();
   return e == cudaSuccess ? HAV_OK : (int)e;

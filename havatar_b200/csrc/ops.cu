@@ -1,5 +1,6 @@
 // HBM-bound element-wise / FIR operators behind the reference's `model/op` extension boundary,
 // plus ray generation.  See include/havatar_b200.h for the contracts and reference citations.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -224,6 +225,69 @@ static cudaError_t launch_ufd_fast(float *out, const float *x, const float *kern
 }
 
 // ------------------------------------------------------------------------------------------------
+// upfirdn2d on channels-last fp16 tensors [B,H,W,C] (the StyleUNet's internal hand-over layout), square up / down
+// factors, fp32 accumulation, with the StyledConv tail fused in: out = act(fir(x) + noise_weight * noise + bias[c]).
+// One thread = one output pixel x 8 channels (one 16-byte load per tap, one 16-byte store).
+// ------------------------------------------------------------------------------------------------
+struct UfdClParams {
+  int B, in_h, in_w, C, out_h, out_w, kh, kw, up, down, pad_x0, pad_y0, act, noise_bstride;
+  float noise_weight;
+};
+
+__global__ void __launch_bounds__(256) upfirdn2d_cl_kernel(uint16_t *__restrict__ out, const uint16_t *__restrict__ x,
+                                                           const float *__restrict__ kernel, const float *__restrict__ noise,
+                                                           const float *__restrict__ bias, UfdClParams p) {
+  __shared__ float sk[kMaxTaps * kMaxTaps];
+  for (int i = threadIdx.x; i < p.kh * p.kw; i += blockDim.x) {
+    const int ky = i / p.kw, kx = i % p.kw;
+    sk[i] = __ldg(kernel + (p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx));   // correlate with the flipped kernel
+  }
+  __syncthreads();
+  const int c8n = p.C >> 3;
+  const long total = (long)p.B * p.out_h * p.out_w * c8n;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int c8 = (int)(r % c8n); r /= c8n;
+    const int ox = (int)(r % p.out_w); r /= p.out_w;
+    const int oy = (int)(r % p.out_h);
+    const int b = (int)(r / p.out_h);
+    const int Y0 = oy * p.down - p.pad_y0, X0 = ox * p.down - p.pad_x0;
+    const int ky0 = ((-Y0) % p.up + p.up) % p.up, kx0 = ((-X0) % p.up + p.up) % p.up;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int ky = ky0; ky < p.kh; ky += p.up) {
+      const int iy = (Y0 + ky) / p.up;
+      if (iy < 0 || iy >= p.in_h) continue;
+      for (int kx = kx0; kx < p.kw; kx += p.up) {
+        const int ix = (X0 + kx) / p.up;
+        if (ix < 0 || ix >= p.in_w) continue;
+        const uint4 u = __ldg(reinterpret_cast<const uint4 *>(x + (((size_t)b * p.in_h + iy) * p.in_w + ix) * p.C) + c8);
+        const float w = sk[ky * p.kw + kx];
+        const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          acc[2 * e] = fmaf(f.x, w, acc[2 * e]), acc[2 * e + 1] = fmaf(f.y, w, acc[2 * e + 1]);
+        }
+      }
+    }
+    const float nz = noise != nullptr ? p.noise_weight * __ldg(noise + (size_t)b * p.noise_bstride + (size_t)oy * p.out_w + ox) : 0.0f;
+    uint4 o;
+    __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v0 = acc[2 * e] + nz, v1 = acc[2 * e + 1] + nz;
+      if (bias != nullptr) v0 += __ldg(bias + c8 * 8 + 2 * e), v1 += __ldg(bias + c8 * 8 + 2 * e + 1);
+      if (p.act) {
+        v0 = (v0 > 0.0f ? v0 : 0.2f * v0) * 1.41421356237309515f;
+        v1 = (v1 > 0.0f ? v1 : 0.2f * v1) * 1.41421356237309515f;
+      }
+      oh[e] = __floats2half2_rn(v0, v1);
+    }
+    *(reinterpret_cast<uint4 *>(out + (((size_t)b * p.out_h + oy) * p.out_w + ox) * p.C) + c8) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // ray generation (dataloader/data_util.py:28-56)
 // ------------------------------------------------------------------------------------------------
 struct RayGen {
@@ -321,6 +385,28 @@ extern "C" int hav_upfirdn2d(float *out, const float *x, const float *kernel, in
                                                                  x + (size_t)i0 * in_h * in_w, kernel, p, tiles_x);
   }
   e = cudaGetLastError();
+  return e == cudaSuccess ? HAV_OK : (int)e;
+}
+
+extern "C" int hav_upfirdn2d_cl(void *out, const void *x, const float *kernel, int batch, int in_h, int in_w, int channels,
+                                int kh, int kw, int up, int down, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                                const float *noise, float noise_weight, int noise_per_sample, const float *bias, int act,
+                                void *stream) {
+  if (batch < 0 || in_h < 1 || in_w < 1 || channels < 8 || (channels & 7) || kh < 1 || kw < 1 || up < 1 || down < 1) return HAV_E_SHAPE;
+  if (kh > kMaxTaps || kw > kMaxTaps) return HAV_E_SHAPE;
+  const int out_h = (in_h * up + pad_y0 + pad_y1 - kh + down) / down, out_w = (in_w * up + pad_x0 + pad_x1 - kw + down) / down;
+  if (out_h < 1 || out_w < 1) return HAV_E_SHAPE;
+  if (batch == 0) return HAV_OK;
+  if (out == nullptr || x == nullptr || kernel == nullptr) return HAV_E_NULL;
+  UfdClParams p;
+  p.B = batch, p.in_h = in_h, p.in_w = in_w, p.C = channels, p.out_h = out_h, p.out_w = out_w, p.kh = kh, p.kw = kw;
+  p.up = up, p.down = down, p.pad_x0 = pad_x0, p.pad_y0 = pad_y0, p.act = act, p.noise_weight = noise_weight;
+  p.noise_bstride = noise_per_sample ? out_h * out_w : 0;
+  const long total = (long)batch * out_h * out_w * (channels / 8);
+  long want = (total + 255) / 256;
+  const int grid = (int)(want < (long)kSMs * 32 ? want : (long)kSMs * 32);
+  upfirdn2d_cl_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((uint16_t *)out, (const uint16_t *)x, kernel, noise, bias, p);
+  cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? HAV_OK : (int)e;
 }
 

@@ -39,7 +39,9 @@ class Blur(nn.Module):
         self.register_buffer("kernel", _fir(taps, float(upsample_factor ** 2)))
         self.pad = pad
 
-    def forward(self, x):
+    def forward(self, x, **tail):
+        if hconv.is_cl(x):          # channels-last fp16 hand-over: FIR + (noise, bias, lrelu) in one launch
+            return hconv.upfirdn2d_cl(x, self.kernel, pad=self.pad, **tail)
         return upfirdn2d(x, self.kernel, pad=self.pad)
 
 
@@ -131,9 +133,9 @@ class EqualConv2d(nn.Module):
         self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
         self._cache = _PackCache()
 
-    def run(self, x, bias=None, act=False):
+    def run(self, x, bias=None, act=False, out_cl=False):
         b = bias if bias is not None else self.bias
-        return hconv.conv2d(x, self._cache.get(self.weight, self.scale, False), bias=b, act=act, down=self.stride)
+        return hconv.conv2d(x, self._cache.get(self.weight, self.scale, False), bias=b, act=act, down=self.stride, out_cl=out_cl)
 
     def forward(self, x):
         return self.run(x)
@@ -167,13 +169,13 @@ class ConvLayer(nn.Sequential):
         super().__init__(*layers)
         self.activate = activate
 
-    def forward(self, x):
+    def forward(self, x, out_cl=False):
         mods = list(self)
         if isinstance(mods[0], Blur):
             x = mods[0](x)
             mods = mods[1:]
         act_bias = mods[1].bias if self.activate else None
-        return mods[0].run(x, bias=act_bias, act=self.activate)
+        return mods[0].run(x, bias=act_bias, act=self.activate, out_cl=out_cl)
 
 
 class EqualLinear(nn.Module):
@@ -226,18 +228,17 @@ class ModulatedConv2d(nn.Module):
         self.fused = fused
         self._cache = _PackCache()
 
-    def run(self, x, style, noise=None, noise_weight=0.0, bias=None, act=False):
+    def run(self, x, style, noise=None, noise_weight=0.0, bias=None, act=False, out_cl=False):
         s = self.modulation(style).contiguous()
         d = hconv.modconv_demod(self.weight.detach()[0], s, self.scale, self.eps) if self.demodulate else None
         packed = self._cache.get(self.weight, self.scale, self.upsample)
         if not self.upsample:
-            return hconv.conv2d(x, packed, in_scale=s, out_scale=d, noise=noise, noise_weight=noise_weight, bias=bias, act=act)
-        y = self.blur(hconv.conv2d(x, packed, in_scale=s, out_scale=d, up=2))      # convT stride 2 -> 4x4 blur (:264-277)
-        if noise is not None:
-            y = y + noise_weight * noise
-        if act:
-            return fused_leaky_relu(y, bias)
-        return y if bias is None else y + bias.view(1, -1, 1, 1)
+            return hconv.conv2d(x, packed, in_scale=s, out_scale=d, noise=noise, noise_weight=noise_weight, bias=bias, act=act,
+                                out_cl=out_cl)
+        # convT stride 2 (polyphase) -> 4x4 blur (:264-277); both in channels-last fp16, the StyledConv tail rides on the blur
+        y = hconv.conv2d(x, packed, in_scale=s, out_scale=d, up=2, out_cl=True)
+        y = self.blur(y, noise=noise, noise_weight=noise_weight, bias=bias, act=act)
+        return y if out_cl else hconv.to_nchw(y)
 
     def forward(self, x, style):
         return self.run(x, style)
@@ -283,12 +284,12 @@ class StyledConv(nn.Module):
         self.noise = NoiseInjection()
         self.activate = _ActBias(out_channel)
 
-    def forward(self, x, style, noise=None):
+    def forward(self, x, style, noise=None, out_cl=False):
         if noise is None:     # fresh N(0,1) per call, like NoiseInjection.forward (:306-309)
-            r = x.shape[-1] * 2 if self.conv.upsample else x.shape[-1]
-            rh = x.shape[-2] * 2 if self.conv.upsample else x.shape[-2]
-            noise = x.new_empty(x.shape[0], 1, rh, r).normal_()
-        return self.conv.run(x, style, noise=noise, noise_weight=self.noise.value(), bias=self.activate.bias, act=True)
+            h, w = (x.shape[1], x.shape[2]) if hconv.is_cl(x) else (x.shape[2], x.shape[3])
+            f = 2 if self.conv.upsample else 1
+            noise = torch.empty(x.shape[0], 1, h * f, w * f, dtype=torch.float32, device=x.device).normal_()
+        return self.conv.run(x, style, noise=noise, noise_weight=self.noise.value(), bias=self.activate.bias, act=True, out_cl=out_cl)
 
 
 class ToRGB(nn.Module):
@@ -320,8 +321,8 @@ class ConvBlock(nn.Module):
         self.conv1 = ConvLayer(in_channel, in_channel, 3)
         self.conv2 = ConvLayer(in_channel, out_channel, 3, downsample=downsample)
 
-    def forward(self, x):
-        return self.conv2(self.conv1(x))
+    def forward(self, x, out_cl=False):
+        return self.conv2(self.conv1(x, out_cl=True), out_cl=out_cl)
 
 
 class FromRGB(nn.Module):
@@ -339,10 +340,10 @@ class FromRGB(nn.Module):
         self.in_channel = in_channel * 4 if use_wt else in_channel
         self.conv = ConvLayer(self.in_channel, out_channel, 1)
 
-    def forward(self, x, skip=None):
+    def forward(self, x, skip=None, out_cl=False):
         if self.downsample:
             x = self.dwt(self.downsample(self.iwt(x))) if self.use_wt else self.downsample(x)
-        out = self.conv(x)
+        out = self.conv(x, out_cl=out_cl or (skip is not None and hconv.is_cl(skip)))
         if skip is not None:
             out = out + skip
         return x, out
@@ -373,11 +374,11 @@ class _CondEncoder:
 
     @staticmethod
     def run(net, cond_img):
-        cond_out = net.conv_in(cond_img)
+        cond_out = net.conv_in(cond_img, out_cl=True)          # feature maps travel channels-last fp16 between layers
         feats = [cond_out]
         for from_rgb, cond_conv in zip(net.from_rgbs, net.cond_convs):
-            cond_img, cond_out = from_rgb(cond_img, cond_out)
-            cond_out = cond_conv(cond_out)
+            cond_img, cond_out = from_rgb(cond_img, cond_out, out_cl=True)
+            cond_out = cond_conv(cond_out, out_cl=True)
             feats.append(cond_out)
         return feats
 
@@ -439,12 +440,12 @@ class SWGAN_unet(nn.Module):
         i, skip, out = 0, None, None
         for conv1, conv2, n1, n2, to_rgb in zip(self.convs[::2], self.convs[1::2], noise[::2], noise[1::2], self.to_rgbs):
             if i == 0:
-                out = self.comb_convs[-1](feats[-1])
+                out = self.comb_convs[-1](feats[-1], out_cl=True)
             elif i < 2 * len(self.comb_convs):
-                out = self.comb_convs[-1 - (i // 2)](torch.cat([out, feats[-1 - (i // 2)]], dim=1))
-            out = conv1(out, latent[:, i], noise=n1)
-            out = conv2(out, latent[:, i + 1], noise=n2)
-            skip = to_rgb(out, latent[:, i + 2], skip)
+                out = self.comb_convs[-1 - (i // 2)](torch.cat([out, feats[-1 - (i // 2)]], dim=-1), out_cl=True)
+            out = conv1(out, latent[:, i], noise=n1, out_cl=True)
+            out = conv2(out, latent[:, i + 1], noise=n2, out_cl=True)
+            skip = to_rgb(out, latent[:, i + 2], skip)          # 12-channel wavelet skip stays NCHW fp32
             i += 2
         return self.iwt(skip)
 
@@ -479,9 +480,10 @@ class Discriminator(nn.Module):
         x = self.dwt(x)
         out = None
         for from_rgb, block in zip(self.from_rgbs, self.convs):
-            x, out = from_rgb(x, out)
-            out = block(out)
-        _, out = self.from_rgbs[-1](x, out)
+            x, out = from_rgb(x, out, out_cl=True)
+            out = block(out, out_cl=True)
+        _, out = self.from_rgbs[-1](x, out, out_cl=True)
+        out = hconv.to_nchw(out)                                  # 4x4 map: the minibatch statistics run in torch
         b, c, h, w = out.shape
         group = min(b, self.stddev_group)                                  # minibatch standard deviation (:539-545)
         sd = out.view(group, -1, self.stddev_feat, c // self.stddev_feat, h, w)
@@ -569,13 +571,13 @@ class StyleGAN_zxc(nn.Module):
                 self.zero_noise = [n.to(dev) for n in self.zero_noise]
             noise = self.zero_noise
         feats = _CondEncoder.run(self, cond_feats)
-        out = self.conv1(self.input(latent), latent[:, 0], noise=noise[0])
+        out = self.conv1(self.input(latent), latent[:, 0], noise=noise[0], out_cl=True)
         i = 1
         for conv1, conv2, n1, n2 in zip(self.convs[::2], self.convs[1::2], noise[1::2], noise[2::2]):
             if 1 < i <= 2 * len(feats) + 1:
-                out = self.comb_convs[-(i // 2)](torch.cat([out, feats[-(i // 2)]], dim=1))
-            out = conv1(out, latent[:, i], noise=n1)
-            out = conv2(out, latent[:, i + 1], noise=n2)
+                out = self.comb_convs[-(i // 2)](torch.cat([out, feats[-(i // 2)]], dim=-1), out_cl=True)
+            out = conv1(out, latent[:, i], noise=n1, out_cl=True)
+            out = conv2(out, latent[:, i + 1], noise=n2, out_cl=True)
             i += 2
-        image = self.conv_out(out)
+        image = self.conv_out(out)                               # back to the reference layout (NCHW fp32)
         return (image, latent) if return_latents else (image, None)

@@ -78,6 +78,13 @@ int hav_upfirdn2d(float *out, const float *x, const float *kernel, int major, in
                   int minor, int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0,
                   int pad_x1, int pad_y0, int pad_y1, void *stream);
 
+/* upfirdn2d on channels-last fp16 tensors (HAV_LAYOUT_NHWC_F16: x [B,H,W,C] -> out [B,Ho,Wo,C], C % 8 == 0), square up / down
+ * factors, with the tail of StyledConv fused in (model/styleUnet.py:593-599 after the blur of :264-277):
+ *   out = act( fir(x) + noise_weight * noise + bias[c] ),  act 0: none, 1: leaky-relu(0.2) * sqrt(2); noise / bias may be NULL. */
+int hav_upfirdn2d_cl(void *out, const void *x, const float *kernel, int batch, int in_h, int in_w, int channels, int kh, int kw,
+                     int up, int down, int pad_x0, int pad_x1, int pad_y0, int pad_y1, const float *noise, float noise_weight,
+                     int noise_per_sample, const float *bias, int act, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused volumetric render: per-ray depth sampling -> 2-bone skinning warp -> bi-plane bilinear fetch
  * -> positional encoding -> 5-linear MLP -> alpha composite (-> sample_pdf -> second pass).
@@ -150,6 +157,9 @@ int hav_get_rays(float *ray_batch, int height, int width, const float intr[4], c
  * Weights are packed once per weight update with hav_conv_pack_weights for the SAME `up` they will be used with
  * (w is [Cout,Cin,k,k], or [Cin,Cout,k,k] -- conv_transpose2d's own layout -- when transpose_io != 0).
  */
+#define HAV_LAYOUT_NCHW_F32 0 /* [B,C,H,W] float32 */
+#define HAV_LAYOUT_NHWC_F16 1 /* [B,H,W,C] IEEE half, C % 8 == 0 (fp16 precision only) */
+
 typedef struct hav_conv_args {
   uint32_t struct_bytes; /* = sizeof(hav_conv_args) */
   int32_t precision;     /* HAV_PREC_FP16 or HAV_PREC_BF16: must match the packed weights */
@@ -158,13 +168,15 @@ typedef struct hav_conv_args {
   int32_t act;              /* 0: none, 1: leaky-relu(0.2) * sqrt(2) (model/op/fused_act.py:103-122) */
   int32_t noise_per_sample; /* 0: noise is [1,1,Ho,Wo] broadcast over the batch, 1: [B,1,Ho,Wo] */
   float noise_weight;       /* NoiseInjection.weight (model/styleUnet.py:300-310) */
-  const float *x;
+  int32_t in_layout;        /* HAV_LAYOUT_NCHW_F32 (reference layout) or HAV_LAYOUT_NHWC_F16 (internal hand-over between layers) */
+  int32_t out_layout;
+  const void *x;
   const void *wpack;        /* hav_conv_wpack_bytes(cout, cin, ksize, up) bytes written by hav_conv_pack_weights */
   const float *in_scale;    /* [B,Cin] modulation s, or NULL */
   const float *out_scale;   /* [B,Cout] demodulation, or NULL */
   const float *noise;       /* or NULL */
   const float *bias;        /* [Cout] or NULL */
-  float *out;
+  void *out;
 } hav_conv_args;
 
 uint64_t hav_conv_wpack_bytes(int cout, int cin, int ksize, int up);

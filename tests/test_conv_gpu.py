@@ -91,3 +91,44 @@ def test_full_size_layer_linearity():
     y12 = conv.conv2d(x1, pw) + conv.conv2d(x2, pw)
     assert rel_err(y, y12) < 5e-3
     assert torch.isfinite(y).all()
+
+
+@pytest.mark.parametrize("up,down", [(1, 1), (2, 1), (1, 2)])
+def test_channels_last_fp16_hand_over(up, down):
+    """NHWC fp16 in / out (the StyleUNet's internal layout) gives the same convolution as the NCHW fp32 path."""
+    torch.manual_seed(4)
+    B, Cin, Cout, H = 2, 128, 64, 24
+    x = torch.randn(B, Cin, H, H, device="cuda")
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda")
+    s = torch.rand(B, Cin, device="cuda") + 0.5
+    d = torch.rand(B, Cout, device="cuda") + 0.5
+    bias = torch.randn(Cout, device="cuda")
+    pw = conv.pack_weights(w, 1 / math.sqrt(Cin * 9), up=up)
+    ref = conv.conv2d(x, pw, in_scale=s, out_scale=d, bias=bias, act=True, up=up, down=down)
+    xcl = x.permute(0, 2, 3, 1).contiguous().half()
+    got_cl = conv.conv2d(xcl, pw, in_scale=s, out_scale=d, bias=bias, act=True, up=up, down=down, out_cl=True)
+    assert got_cl.dtype == torch.float16 and got_cl.shape == (B, ref.shape[2], ref.shape[3], Cout)
+    assert rel_err(conv.to_nchw(got_cl), ref) < 5e-3
+    got_mixed = conv.conv2d(xcl, pw, in_scale=s, out_scale=d, bias=bias, act=True, up=up, down=down, out_cl=False)
+    assert rel_err(got_mixed, ref) < 5e-3
+
+
+@pytest.mark.parametrize("up,down,pad", [(1, 1, (1, 1)), (1, 1, (2, 2)), (2, 1, (2, 1)), (1, 2, (1, 1))])
+def test_upfirdn2d_channels_last_with_fused_tail(up, down, pad):
+    from havatar_b200 import op
+
+    torch.manual_seed(5)
+    B, C, H, W = 2, 16, 13, 18
+    x = torch.randn(B, C, H, W, device="cuda")
+    k = torch.tensor([1.0, 3.0, 3.0, 1.0], device="cuda")
+    k = k[None, :] * k[:, None]
+    k = k / k.sum() * (up * up)
+    ref = op.upfirdn2d(x.half().float(), k, up=up, down=down, pad=pad)
+    noise = torch.randn(1, 1, ref.shape[2], ref.shape[3], device="cuda")
+    bias = torch.randn(C, device="cuda")
+    ref_tail = F.leaky_relu(ref + 0.3 * noise + bias.view(1, -1, 1, 1), 0.2) * math.sqrt(2)
+    xcl = x.permute(0, 2, 3, 1).contiguous().half()
+    got = conv.upfirdn2d_cl(xcl, k, up=up, down=down, pad=pad)
+    assert rel_err(conv.to_nchw(got), ref) < 2e-3
+    got = conv.upfirdn2d_cl(xcl, k, up=up, down=down, pad=pad, noise=noise, noise_weight=0.3, bias=bias, act=True)
+    assert rel_err(conv.to_nchw(got), ref_tail) < 2e-3
