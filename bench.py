@@ -195,6 +195,15 @@ def run_ours(args):
     kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     clocks = sampler.stop(t0, time.time()) if sampler is not None else None
     acc_mean = float(out.acc_coarse.mean())
+    # "matched PSNR": the 16-bit tensor-core render against the fp32 CUDA-core (reference-exact) mode on the same frame
+    psnr = None
+    if args.precision != "fp32" and rank == 0:
+        ref32 = render.render_rays(d["ray_batch"], d["background_prior"], d["inv_head_T"], d["planes"], wvol, wts, S, 0, precision="fp32")
+        mse = float(((out.rgb_coarse[..., :3] - ref32.rgb_coarse[..., :3]) ** 2).mean())
+        psnr = {"rgb_psnr_db_vs_fp32_mode": (10.0 * (-1.0) * __import__("math").log10(max(mse, 1e-20))),
+                "max_abs_err_67ch": float((out.rgb_coarse - ref32.rgb_coarse).abs().max()),
+                "max_abs_err_acc": float((out.acc_coarse - ref32.acc_coarse).abs().max())}
+        del ref32
 
     # ---- timed region 2: end to end through the host-buffer API: every step uploads its inputs from pinned host
     #      memory and downloads all rendered maps to pinned host memory; copies of neighbouring frames overlap the
@@ -283,7 +292,7 @@ def run_ours(args):
                    "frames_per_gpu_per_step": 1, "rays_per_step": world * R, "samples_per_ray": S,
                    "mlp_arithmetic": "%s operands, fp32 accumulate (tcgen05/TMEM)" % args.precision if args.precision != "fp32" else "fp32 CUDA cores",
                    "l2": "256 MiB buffer written between timed steps (L2 flush); per-step CUDA events on the launch stream",
-                   "acc_mean": acc_mean},
+                   "acc_mean": acc_mean, "fidelity": psnr},
         "e2e": {"value": world * R / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "serial_ms_per_step": e2e_serial_ms,

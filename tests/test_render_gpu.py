@@ -14,8 +14,9 @@ pytestmark = pytest.mark.gpu
 
 # fp32 CUDA-core mode: same arithmetic as the reference, only summation order / libm differ.
 TOL_FP32 = dict(rgb=1e-4, depth=2e-4, acc=1e-4, wmax=1e-4)
-# 16-bit tensor-core operands, fp32 accumulate (the tolerance SURVEY.md section 8d states: 2e-2 abs)
-TOL_TC = dict(rgb=2e-2, depth=4e-2, acc=2e-2, wmax=2e-2)
+# 16-bit tensor-core operands, fp32 accumulate.  SURVEY.md section 8d allows 2e-2 abs; fp16 measures ~1e-4 on these scenes
+# (bench.py reports 83 dB PSNR against the fp32 mode on the full frame), so the gate is 10x tighter than the allowance
+TOL_TC = dict(rgb=2e-3, depth=4e-3, acc=2e-3, wmax=2e-3)
 CASES = ["render_c32_s32", "render_hier_det", "render_hier_rand", "render_oddshape"]
 
 
@@ -57,7 +58,7 @@ def test_render_matches_reference_golden(golden_dir, name, precision):
     got = run_cuda(sc, case["num_coarse"], case["num_fine"], rnd, precision)
     tol = TOL_FP32 if precision == "fp32" else TOL_TC
     if precision == "bf16":
-        tol = {k: 3 * v for k, v in tol.items()}   # 8-bit mantissa operands
+        tol = {k: 20 * v for k, v in tol.items()}   # 8-bit mantissa operands: 4e-2
     for k in z.files:
         if k == "case":
             continue
@@ -145,7 +146,7 @@ def test_full_frame_ray_bookkeeping_is_bit_exact(precision):
     sub2 = dict(sc, ray_batch=sc["ray_batch"][:, idx2], background_prior=sc["background_prior"][:, idx2])
     ref = ro.render_rays(sub2["ray_batch"], sub2["background_prior"], sc["inv_head_T"], sc["planes"], sc["wvol"],
                          sc["weights"], ro.default_boxes(), 64, 0)
-    tol = 1e-4 if precision == "fp32" else 2e-2
+    tol = 1e-4 if precision == "fp32" else 2e-3
     assert np.abs(full["rgb_coarse"][:, idx2] - ref["rgb_coarse"]).max() < tol
     assert np.abs(full["acc_coarse"][:, idx2, 0] - ref["acc_coarse"]).max() < tol
 
