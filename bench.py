@@ -288,6 +288,31 @@ def run_ours(args):
         cpu_rate, cpu_s, cpu_sample = cpu_reference_rate(4, threads)
     except Exception as exc:
         cpu_rate, cpu_s, cpu_sample = None, None, "failed: %s" % exc
+    # the reference's own GPU path, as far as it can be had on this box: the same ATen call sequence the reference executes
+    # (oracle/render_oracle_torch.py: grid_sample, Linear, cumprod, ..., 4096-ray chunks, fp32, TF32 off), on this GPU
+    ref_gpu = None
+    try:
+        from oracle import render_oracle as ro
+        from oracle import render_oracle_torch as rt
+
+        torch.backends.cuda.matmul.allow_tf32 = False
+        gargs = (d["ray_batch"], d["background_prior"], d["inv_head_T"], d["planes"], wvol, wts, ro.default_boxes(), S, 0)
+        for _ in range(2):
+            rt.render_rays(*gargs, chunk=CPU_CHUNK_RAYS, device=dev, to_numpy=False)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(3):
+            gout = rt.render_rays(*gargs, chunk=CPU_CHUNK_RAYS, device=dev, to_numpy=False)
+        g1.record()
+        torch.cuda.synchronize()
+        gms = g0.elapsed_time(g1) / 3
+        ref_gpu = {"value": R / (gms * 1e-3), "unit": "rays/s", "ms_per_frame": gms, "kind": "port",
+                   "what": "torch-CUDA port of the reference render path (same ATen ops, 4096-ray chunks, fp32, TF32 off), full 512x512x64 frame",
+                   "max_abs_diff_vs_ours": float((gout["rgb_coarse"] - out.rgb_coarse).abs().max())}
+        del gout
+    except Exception as exc:
+        ref_gpu = {"error": "%s: %s" % (type(exc).__name__, exc)}
     line = {
         "metric": METRIC, "value": world * R / (step_ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
@@ -311,6 +336,7 @@ def run_ours(args):
                      "hbm_gbs_algorithmic": R * BYTES_PER_RAY / (kern_ms * 1e-3) / 1e9},
         "cpu_baseline": {"value": cpu_rate, "unit": "rays/s", "cores": threads, "kind": "port", "sample": cpu_sample,
                          "seconds": cpu_s},
+        "reference_gpu_port": ref_gpu,
         "clocks": clocks,
         "hd": dict(hd, note="HD frames/s = XY/YZ plane generators (StyleGAN_zxc) + 512x512x64 or 128x128x64 render + SWGAN_unet, "
                             "one frame per GPU, CUDA-graph replay, random-init weights, per-rank values (not max-reduced)"),

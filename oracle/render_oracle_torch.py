@@ -38,7 +38,7 @@ def _pass(ro, rd, z, inv_T, planes, wvol, w, boxes, bg, noise):
     f0 = _grid2(planes[0:1], q[:, [0, 1]])                                               # util.py:378
     f1 = _grid2(planes[1:2], q[:, [2, 1]])                                               # util.py:381
     feat = torch.stack([f0, f1], dim=-1).reshape(pc.shape[0], -1)                        # util.py:388
-    freqs = 2.0 ** torch.linspace(0.0, 7.0, 8)                                           # embedder.py:32-61
+    freqs = 2.0 ** torch.linspace(0.0, 7.0, 8, device=pc.device)                         # embedder.py:32-61
     ang = pc[:, None, :] * freqs[None, :, None]
     pe = torch.sin(torch.stack([ang, ang + math.pi / 2], dim=-2)).reshape(pc.shape[0], -1)
     x = torch.cat([feat, pe], dim=-1)                                                    # nerf_model.py:101-117
@@ -70,10 +70,10 @@ def _sample_pdf(bins, weights, n, u_rand):
     cdf = torch.cumsum(weights / weights.sum(dim=-1, keepdim=True), dim=-1)
     cdf = torch.cat([torch.zeros_like(cdf[:, :1]), cdf], dim=-1)
     if u_rand is None:
-        u = torch.linspace(0.0, 1.0, n).expand(cdf.shape[0], n)
+        u = torch.linspace(0.0, 1.0, n, device=cdf.device).expand(cdf.shape[0], n)
     else:
         s = 1 / n
-        u = (torch.arange(n) * s)[None] + u_rand * (s - 1e-6)
+        u = (torch.arange(n, device=cdf.device) * s)[None] + u_rand * (s - 1e-6)
     u = u.contiguous()
     inds = torch.searchsorted(cdf.contiguous(), u, right=True)
     below, above = (inds - 1).clamp(min=0), inds.clamp(max=cdf.shape[-1] - 1)
@@ -86,10 +86,12 @@ def _sample_pdf(bins, weights, n, u_rand):
 
 @torch.no_grad()
 def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, boxes, num_coarse, num_fine=0,
-                t_rand=None, noise_coarse=None, u_rand=None, noise_fine=None, chunk=4096):
-    """Same contract as oracle.render_oracle.render_rays, torch CPU tensors in/out, rays processed in
-    chunks of `chunk` like the reference (model/nerf_trainer.py:65-71; nerf.validation.chunksize)."""
-    T = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32)
+                t_rand=None, noise_coarse=None, u_rand=None, noise_fine=None, chunk=4096, device="cpu", to_numpy=True):
+    """Same contract as oracle.render_oracle.render_rays, rays processed in chunks of `chunk` like the reference
+    (model/nerf_trainer.py:65-71; nerf.validation.chunksize).  device="cuda" runs the very same ATen call sequence on the
+    GPU in fp32 -- bench.py times that as the stand-in for the reference's own GPU path (the reference tree is Python and
+    does not exist on the GPU box)."""
+    T = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32).to(device)
     ray_batch, background_prior, inv_head_T, planes, wvol = map(T, (ray_batch, background_prior, inv_head_T, planes, wvol))
     t_rand, noise_coarse, u_rand, noise_fine = map(T, (t_rand, noise_coarse, u_rand, noise_fine))
     w = {k: T(v) for k, v in weights.items()}
@@ -97,7 +99,7 @@ def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, 
     B, R = ray_batch.shape[:2]
     keys = ("rgb_coarse", "depth_coarse", "acc_coarse", "weights_max", "rgb_fine", "depth_fine", "acc_fine")
     out = {k: [] for k in keys}
-    tvals = torch.linspace(0.0, 1.0, num_coarse)
+    tvals = torch.linspace(0.0, 1.0, num_coarse, device=device)
     for b in range(B):
         per = {k: [] for k in keys}
         for r0 in range(0, R, chunk):
@@ -124,4 +126,6 @@ def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, 
         for k in keys:
             if per[k]:
                 out[k].append(torch.cat(per[k], dim=0))
-    return {k: (torch.stack(v).numpy() if v else None) for k, v in out.items()}
+    if not to_numpy:
+        return {k: (torch.stack(v) if v else None) for k, v in out.items()}
+    return {k: (torch.stack(v).cpu().numpy() if v else None) for k, v in out.items()}
