@@ -35,6 +35,19 @@ class RenderArgs(C.Structure):
     ]
 
 
+class RenderBwdArgs(C.Structure):
+    """hav_render_bwd_args (include/havatar_b200.h)."""
+    _fields_ = [
+        ("struct_bytes", C.c_uint32), ("grad_scale", C.c_float), ("fwd", C.POINTER(RenderArgs)),
+        ("g_rgb_coarse", _fp), ("g_depth_coarse", _fp), ("g_acc_coarse", _fp),
+        ("g_rgb_fine", _fp), ("g_depth_fine", _fp), ("g_acc_fine", _fp),
+        ("g_planes", _fp), ("g_wvol", _fp),
+        ("g_w0", _fp), ("g_b0", _fp), ("g_w1", _fp), ("g_b1", _fp), ("g_w_alpha", _fp), ("g_b_alpha", _fp),
+        ("g_w_feat", _fp), ("g_b_feat", _fp), ("g_w_rgb", _fp), ("g_b_rgb", _fp),
+        ("workspace", _fp), ("workspace_bytes", C.c_uint64),
+    ]
+
+
 class ConvArgs(C.Structure):
     """hav_conv_args (include/havatar_b200.h)."""
     _fields_ = [
@@ -56,6 +69,8 @@ SIGNATURES = {
     "hav_upfirdn2d": (C.c_int, [_fp, _fp, _fp] + [C.c_int] * 14 + [_fp]),
     "hav_render_workspace_bytes": (C.c_uint64, [C.POINTER(RenderArgs)]),
     "hav_render_forward": (C.c_int, [C.POINTER(RenderArgs), _fp]),
+    "hav_render_backward_workspace_bytes": (C.c_uint64, [C.POINTER(RenderBwdArgs)]),
+    "hav_render_backward": (C.c_int, [C.POINTER(RenderBwdArgs), _fp]),
     "hav_conv_wpack_bytes": (C.c_uint64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "hav_conv_pack_weights": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, _fp]),
     "hav_modconv_demod": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _fp]),

@@ -14,7 +14,7 @@ struct WsLayout {
   int num_blocks, scratch_blocks;
 };
 
-static int check_args(const hav_render_args *a) {
+int render_check_args(const hav_render_args *a) {
   if (a == nullptr) return HAV_E_NULL;
   if (a->struct_bytes != sizeof(hav_render_args)) return HAV_E_VALUE;
   if (a->precision != HAV_PREC_FP32 && a->precision != HAV_PREC_BF16 && a->precision != HAV_PREC_FP16) return HAV_E_VALUE;
@@ -62,27 +62,8 @@ static WsLayout layout(const hav_render_args *a) {
   return L;
 }
 
-}  // namespace hav
-
-using namespace hav;
-
-extern "C" uint64_t hav_render_workspace_bytes(const hav_render_args *a) {
-  if (check_args(a) != HAV_OK) return 0;
-  return layout(a).total;
-}
-
-extern "C" int hav_render_forward(const hav_render_args *a, void *stream) {
-  int rc = check_args(a);
-  if (rc != HAV_OK) return rc;
+void render_fill_dev(const hav_render_args *a, RenderDev &P) {
   const int64_t total = (int64_t)a->batch * a->rays;
-  if (total == 0) return HAV_OK;  // empty ray batch: nothing to write
-  WsLayout L = layout(a);
-  if (a->workspace == nullptr) return HAV_E_NULL;
-  if (a->workspace_bytes < L.total || ((uintptr_t)a->workspace & 255) != 0) return HAV_E_WORKSPACE;
-  cudaStream_t st = (cudaStream_t)stream;
-  uint8_t *ws = (uint8_t *)a->workspace;
-
-  RenderDev P;
   memset(&P, 0, sizeof(P));
   P.B = a->batch, P.R = a->rays, P.total_rays = (int)total;
   P.Sc = a->num_coarse, P.nfine = a->num_fine;
@@ -96,6 +77,30 @@ extern "C" int hav_render_forward(const hav_render_args *a, void *stream) {
   P.t_rand = a->t_rand, P.noise_c = a->noise_coarse, P.u_rand = a->u_rand, P.noise_f = a->noise_fine;
   P.rgb_c = a->rgb_coarse, P.depth_c = a->depth_coarse, P.acc_c = a->acc_coarse, P.wmax = a->weights_max;
   P.rgb_f = a->rgb_fine, P.depth_f = a->depth_fine, P.acc_f = a->acc_fine, P.z_fine = a->z_fine;
+}
+
+}  // namespace hav
+
+using namespace hav;
+
+extern "C" uint64_t hav_render_workspace_bytes(const hav_render_args *a) {
+  if (render_check_args(a) != HAV_OK) return 0;
+  return layout(a).total;
+}
+
+extern "C" int hav_render_forward(const hav_render_args *a, void *stream) {
+  int rc = render_check_args(a);
+  if (rc != HAV_OK) return rc;
+  const int64_t total = (int64_t)a->batch * a->rays;
+  if (total == 0) return HAV_OK;  // empty ray batch: nothing to write
+  WsLayout L = layout(a);
+  if (a->workspace == nullptr) return HAV_E_NULL;
+  if (a->workspace_bytes < L.total || ((uintptr_t)a->workspace & 255) != 0) return HAV_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t *ws = (uint8_t *)a->workspace;
+
+  RenderDev P;
+  render_fill_dev(a, P);
   float *pk = (float *)(ws + L.pack_f32);
   P.W0t = pk + kOffW0t, P.W1t = pk + kOffW1t, P.Wht = pk + kOffWht;
   P.b0 = pk + kOffB0, P.b1 = pk + kOffB1, P.bh = pk + kOffBh, P.Wr = pk + kOffWr, P.br = pk + kOffBr;

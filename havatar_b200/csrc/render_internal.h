@@ -9,6 +9,9 @@ namespace hav {
 
 struct RenderDev;
 
+int render_check_args(const hav_render_args *a);              // render_api.cu
+void render_fill_dev(const hav_render_args *a, RenderDev &P);  // everything except the packed-weight pointers
+
 // ---- fp32 packed-weight blob (float offsets), built by pack_mlp_fp32_kernel ----
 constexpr int kOffW0t = 0;                       // [176][128]
 constexpr int kOffW1t = kOffW0t + 176 * 128;     // [128][128]

@@ -72,7 +72,7 @@ def _workspace(device, nbytes):
 
 def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, num_coarse, num_fine=0,
                 boxes=None, t_rand=None, noise_coarse=None, u_rand=None, noise_fine=None, precision="fp16",
-                want_z_fine=False, reuse_packed=False, out=None):
+                want_z_fine=False, reuse_packed=False, out=None, return_ctx=False):
     """ray_batch [B,R,8] (o3 d3 near far; extra trailing columns such as the reference's viewdirs are
     ignored), background_prior [B,R,3] or None, inv_head_T [B,4,3], planes [2,B,64,H,W], wvol [1,2,D,H,W],
     weights: mapping with the reference's model_coarse keys (MLP_KEYS).  Random draws are explicit inputs
@@ -80,7 +80,8 @@ def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, 
     u_rand [B,R,num_fine]; None switches that randomness off (u_rand None == sample_pdf det=True).
     reuse_packed=True skips re-packing weights/planes (HAV_RENDER_REUSE_PACKED: same weights, planes, precision
     and batch as the previous call on this stream).  out = a previous RenderOut to write into (no allocation).
-    Returns RenderOut of [B,R,*] tensors (fine slots None when num_fine == 0)."""
+    return_ctx=True additionally returns the call's argument block (a RenderCtx that keeps every tensor alive) for
+    render_backward.  Returns RenderOut of [B,R,*] tensors (fine slots None when num_fine == 0)."""
     L = _lib.lib()
     if ray_batch.dim() != 3 or ray_batch.shape[-1] < 8:
         raise _lib.HavError("ray_batch must be [B,R,>=8]")
@@ -147,8 +148,116 @@ def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, 
         a.workspace, a.workspace_bytes = C.c_void_p(ws.data_ptr()), ws.numel()
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(L.hav_render_forward(C.byref(a), C.c_void_p(stream)), "hav_render_forward")
+    res = RenderOut(**out)
+    if return_ctx:
+        return res, RenderCtx(a, keep, res, dev)
     del keep
-    return RenderOut(**out)
+    return res
+
+
+class RenderCtx:
+    """Argument block of one hav_render_forward call + the input tensors its pointers refer to (kept alive) + its outputs
+    (`out`; the autograd node drops this reference and keeps the outputs through save_for_backward instead)."""
+
+    def __init__(self, args, keep, out, dev):
+        self.args, self.keep, self.out, self.dev = args, keep, out, dev
+
+
+_bwd_workspaces = {}
+
+
+def render_backward(ctx, g_rgb_coarse=None, g_depth_coarse=None, g_acc_coarse=None, g_rgb_fine=None, g_depth_fine=None,
+                    g_acc_fine=None, grad_scale=0.0):
+    """Gradients of the render_rays call described by `ctx` (render_rays(..., want_z_fine=True, return_ctx=True)) given the
+    upstream gradients of its outputs -- what loss.backward() computes through predict_and_render_radiance in the reference
+    (model/nerf_trainer.py:120-201, train_avatar.py:149).  One hav_render_backward call.  Returns a dict: 'planes'
+    [2,B,64,H,W], 'wvol' [1,2,D,H,W] and the ten MLP_KEYS tensors."""
+    L = _lib.lib()
+    a, dev = ctx.args, ctx.dev
+    B, R = int(a.batch), int(a.rays)
+    if a.precision == _lib.PREC_FP32:
+        raise _lib.HavError("render_backward needs a 16-bit tensor-core forward (precision 'fp16' or 'bf16')")
+    if a.num_fine > 0 and not a.z_fine:
+        raise _lib.HavError("render_backward needs the forward's z_fine (render_rays(..., want_z_fine=True))")
+    b = _lib.RenderBwdArgs()
+    b.struct_bytes = C.sizeof(_lib.RenderBwdArgs)
+    b.grad_scale = float(grad_scale)
+    b.fwd = C.pointer(a)
+    keep = []
+    for name, g, shape in (("g_rgb_coarse", g_rgb_coarse, (B, R, 67)), ("g_depth_coarse", g_depth_coarse, (B, R, 1)),
+                           ("g_acc_coarse", g_acc_coarse, (B, R, 1)), ("g_rgb_fine", g_rgb_fine, (B, R, 67)),
+                           ("g_depth_fine", g_depth_fine, (B, R, 1)), ("g_acc_fine", g_acc_fine, (B, R, 1))):
+        if g is not None:
+            g = _f32c(g.reshape(shape) if g.numel() == B * R * shape[-1] else g, name, shape)
+            keep.append(g)
+        setattr(b, name, _ptr(g))
+    new = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    grads = {"planes": new(2, B, int(a.plane_c), int(a.plane_h), int(a.plane_w)),
+             "wvol": new(1, 2, int(a.vol_d), int(a.vol_h), int(a.vol_w))}
+    b.g_planes, b.g_wvol = _ptr(grads["planes"]), _ptr(grads["wvol"])
+    for key, field, shape in zip(MLP_KEYS, _MLP_FIELDS, _MLP_SHAPES):
+        grads[key] = new(*shape)
+        setattr(b, "g_" + field, _ptr(grads[key]))
+    with torch.cuda.device(dev):
+        need = int(L.hav_render_backward_workspace_bytes(C.byref(b)))
+        if need == 0 and B * R > 0:
+            _lib.check(L.hav_render_backward(C.byref(b), None) or -2, "hav_render_backward")
+        key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+        ws = _bwd_workspaces.get(key)
+        if ws is None or ws.numel() < need:
+            ws = None
+            _bwd_workspaces.pop(key, None)
+            ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)
+            _bwd_workspaces[key] = ws
+        b.workspace, b.workspace_bytes = C.c_void_p(ws.data_ptr()), ws.numel()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(L.hav_render_backward(C.byref(b), C.c_void_p(stream)), "hav_render_backward")
+    del keep
+    return grads
+
+
+class _RenderFunction(torch.autograd.Function):
+    """autograd node: forward = hav_render_forward, backward = hav_render_backward."""
+
+    @staticmethod
+    def forward(ctx, opts, ray_batch, background_prior, inv_head_T, planes, wvol, *mlp):
+        weights = dict(zip(MLP_KEYS, mlp))
+        out, rctx = render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, want_z_fine=True,
+                                return_ctx=True, **opts)
+        ctx.rctx = rctx
+        rctx.keep.append(out.z_fine)
+        rctx.out = None
+        ctx.save_for_backward(*[t for t in out[:7] if t is not None])   # keeps the storages hav_render_backward reads alive
+        ctx.mark_non_differentiable(out.weights_max)
+        res = [out.rgb_coarse, out.depth_coarse, out.acc_coarse, out.weights_max]
+        if out.rgb_fine is not None:
+            res += [out.rgb_fine, out.depth_fine, out.acc_fine]
+        return tuple(res)
+
+    @staticmethod
+    def backward(ctx, *g):
+        cont = lambda t: None if t is None else t.contiguous()
+        kw = dict(g_rgb_coarse=cont(g[0]), g_depth_coarse=cont(g[1]), g_acc_coarse=cont(g[2]))
+        if len(g) > 4:
+            kw.update(g_rgb_fine=cont(g[4]), g_depth_fine=cont(g[5]), g_acc_fine=cont(g[6]))
+        saved = ctx.saved_tensors   # noqa: F841  (same storages as the pointers inside ctx.rctx.args)
+        grads = render_backward(ctx.rctx, **kw)
+        del saved
+        return (None, None, None, None, grads["planes"], grads["wvol"]) + tuple(grads[k] for k in MLP_KEYS)
+
+
+def render_rays_autograd(ray_batch, background_prior, inv_head_T, planes, wvol, weights, num_coarse, num_fine=0, boxes=None,
+                         t_rand=None, noise_coarse=None, u_rand=None, noise_fine=None, precision="fp16"):
+    """render_rays as a differentiable torch op: gradients flow to `planes`, `wvol` and the MLP tensors in `weights`
+    (the learnable inputs of predict_and_render_radiance); rays, poses and random draws are constants.
+    Returns RenderOut (z_fine slot None)."""
+    if precision == "fp32":
+        raise _lib.HavError("the differentiable render runs on the tensor-core path: precision 'fp16' or 'bf16'")
+    opts = dict(num_coarse=num_coarse, num_fine=num_fine, boxes=boxes, t_rand=t_rand, noise_coarse=noise_coarse,
+                u_rand=u_rand, noise_fine=noise_fine, precision=precision)
+    res = _RenderFunction.apply(opts, ray_batch, background_prior, inv_head_T, planes, wvol, *[weights[k] for k in MLP_KEYS])
+    res = tuple(res) + (None,) * (7 - len(res))
+    return RenderOut(*res, None)
 
 
 def get_rays(height, width, intr, c2w, near, far, device="cuda"):

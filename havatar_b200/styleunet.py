@@ -4,7 +4,8 @@
     StyleGAN_zxc   <- model/styleUnet.py:631-878    (plane generators XY_gen / YZ_gen, model/nerf_model.py:39-42, :58-86)
 
 Same constructor arguments, same `forward` signatures and the same state_dict keys / shapes, so `load_state_dict` of a
-reference checkpoint works unchanged.  Forward (inference) only: every convolution runs on the tcgen05 implicit-GEMM kernel
+reference checkpoint works unchanged.  With gradients enabled the forward is the differentiable formulation of
+styleunet_train.py (training steps); under torch.no_grad() (inference) every convolution runs on the tcgen05 implicit-GEMM kernel
 (havatar_b200/conv.py) in the shared-weight formulation of ModulatedConv2d's own non-fused branch (styleUnet.py:225-251),
 with modulation, demodulation, noise, bias and leaky-relu fused into that launch where the layer has no blur in between;
 blur / up / down / Haar go through the upfirdn2d kernel, the style MLP's activation through fused_bias_act.
@@ -17,6 +18,7 @@ import torch
 from torch import nn
 
 from . import conv as hconv
+from . import styleunet_train as T
 from .op import fused_leaky_relu, upfirdn2d
 
 
@@ -426,16 +428,25 @@ class SWGAN_unet(nn.Module):
     def get_latent(self, x):
         return self.style(x)
 
-    @torch.no_grad()
-    def forward(self, styles, condition_img, cond=None, return_latents=False, inject_index=None, truncation=1,
-                truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True):
+    def forward(self, *args, **kwargs):
+        """Gradients enabled -> the differentiable formulation (styleunet_train.py); otherwise the fused inference kernels."""
+        if torch.is_grad_enabled():
+            return self._forward(True, *args, **kwargs)
+        with torch.no_grad():
+            return self._forward(False, *args, **kwargs)
+
+    def _forward(self, ag, styles, condition_img, cond=None, return_latents=False, inject_index=None, truncation=1,
+                 truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True):
         if not input_is_latent:
-            styles = [self.style(s if cond is None else torch.cat([s, cond], dim=-1)) for s in styles]
+            mlp = (lambda v: T.style_mlp(self.style, v)) if ag else self.style
+            styles = [mlp(s if cond is None else torch.cat([s, cond], dim=-1)) for s in styles]
         if noise is None:
             noise = [None] * self.num_layers if randomize_noise else [getattr(self.noises, f"noise_{i}") for i in range(self.num_layers)]
         if truncation < 1:
             styles = [truncation_latent + truncation * (s - truncation_latent) for s in styles]
         latent = _latents(styles, self.n_latent, inject_index)
+        if ag:
+            return T.swgan_unet_forward(self, latent, condition_img, noise)
         feats = _CondEncoder.run(self, condition_img)
         i, skip, out = 0, None, None
         for conv1, conv2, n1, n2, to_rgb in zip(self.convs[::2], self.convs[1::2], noise[::2], noise[1::2], self.to_rgbs):
@@ -475,8 +486,13 @@ class Discriminator(nn.Module):
                                           EqualLinear(channels[4], 1))
         self.c_dim = c_dim
 
-    @torch.no_grad()
     def forward(self, x, flat_pose=None):
+        if torch.is_grad_enabled():     # GAN losses / R1: first- and second-order autograd (utils/styleUnet_util.py:65-79)
+            return T.discriminator_forward(self, x)
+        with torch.no_grad():
+            return self._forward_inference(x)
+
+    def _forward_inference(self, x):
         x = self.dwt(x)
         out = None
         for from_rgb, block in zip(self.from_rgbs, self.convs):
@@ -550,14 +566,19 @@ class StyleGAN_zxc(nn.Module):
             noises += [f(1, 1, 2 ** i, 2 ** i), f(1, 1, 2 ** i, 2 ** i)]
         return noises
 
-    @torch.no_grad()
-    def forward(self, styles, cond_feats, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
-                input_is_latent=False, noise=None, randomize_noise=True, **kwargs):
+    def forward(self, *args, **kwargs):
+        if torch.is_grad_enabled():
+            return self._forward(True, *args, **kwargs)
+        with torch.no_grad():
+            return self._forward(False, *args, **kwargs)
+
+    def _forward(self, ag, styles, cond_feats, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
+                 input_is_latent=False, noise=None, randomize_noise=True, **kwargs):
         dev = cond_feats.device
         batch = cond_feats.shape[0]
         if self.zero_latents is None:
             if not input_is_latent:
-                styles = [self.style(s) for s in styles]
+                styles = [T.style_mlp(self.style, s) if ag else self.style(s) for s in styles]
             if truncation < 1:
                 styles = [truncation_latent + truncation * (s - truncation_latent) for s in styles]
             latent = _latents(styles, self.n_latent, inject_index)
@@ -570,6 +591,9 @@ class StyleGAN_zxc(nn.Module):
             if any(n.device != dev for n in self.zero_noise):
                 self.zero_noise = [n.to(dev) for n in self.zero_noise]
             noise = self.zero_noise
+        if ag:
+            image = T.stylegan_zxc_forward(self, latent, cond_feats, noise)
+            return (image, latent) if return_latents else (image, None)
         feats = _CondEncoder.run(self, cond_feats)
         out = self.conv1(self.input(latent), latent[:, 0], noise=noise[0], out_cl=True)
         i = 1

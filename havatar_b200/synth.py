@@ -134,6 +134,18 @@ def randoms(batch, rays, num_coarse, num_fine, seed=7, noise_std=0.1):
 _FIXED = (".kernel", ".ll", ".lh", ".hl", ".hh")
 
 
+def cotangents(batch, rays, fine, seed=11, scale=1e-3):
+    """Upstream gradients for the backward parity cases: d(loss)/d(rgb [B,R,67]), /d(depth), /d(acc) of each pass.  `scale`
+    mimics a mean-reduced loss (small values exercise the loss scaling of the 16-bit gradient operands)."""
+    rs = np.random.RandomState(seed)
+    out = {}
+    for p in (("coarse", "fine") if fine else ("coarse",)):
+        out["rgb_" + p] = (rs.standard_normal((batch, rays, 67)) * scale).astype(F32)
+        out["depth_" + p] = (rs.standard_normal((batch, rays)) * scale).astype(F32)
+        out["acc_" + p] = (rs.standard_normal((batch, rays)) * scale).astype(F32)
+    return out
+
+
 def named_normal(name, shape, seed=0):
     import zlib
 

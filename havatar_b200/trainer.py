@@ -9,9 +9,13 @@ keys / shapes, so `load_state_dict(ckpt['nerf_render'])` works.  What differs is
   nerf_forward's chunk loop + predict_and_render_radiance (:38-92, :120-201) -> ONE hav_render_forward over all rays
   the reference's torch.rand / torch.randn draws -> generated here in the reference's order and handed to the kernel
 
-Forward only (inference / validation renders): outputs are detached; training needs the fused backward.
+Under torch.no_grad() (inference / validation renders) everything runs on the fused inference kernels and outputs carry no
+graph.  With gradients enabled (the training step, train_avatar.py:112-149) the render is the differentiable fused op
+(hav_render_forward + hav_render_backward through render.render_rays_autograd): gradients reach the MLP, the bi-plane
+features -> the plane generators and latent codes (styleunet_train.py), and the skinning-weight volume -> the VolumeDecoder.
 The skinning-weight VolumeDecoder (model/network/voxel_encoder.py:150-179) is input independent; it is evaluated with
-torch once per weight version and cached."""
+torch ONCE per forward (the reference re-evaluates it in every chunk and pass, Skinning_Field.py:79) and cached per weight
+version when no gradient is needed."""
 import math
 
 import numpy as np
@@ -105,6 +109,8 @@ class SkinningField(nn.Module):
         """[1,2,D,H,W] skinning-weight volume for the kernel (Skinning_Field.py:79), cached per weight version."""
         if self.fix_canoW:
             return self.canonical_W
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.canonical_Wvolume.parameters()):
+            return self.canonical_Wvolume()         # training: part of the graph (Skinning_Field.py:79)
         key = tuple((p.data_ptr(), p._version) for p in self.canonical_Wvolume.parameters())
         if key != self._key:
             with torch.no_grad():
@@ -130,7 +136,6 @@ class PlaneNeRF(nn.Module):
         self.fc_rgb = nn.Linear(64, 3)
         self.triPlane_embeddings = None
 
-    @torch.no_grad()
     def set_conditional_embedding(self, front_render_cond, left_render_cond, right_render_cond, latents, cond_c):
         """model/nerf_model.py:58-86."""
         lat = [torch.cat([latents, cond_c.reshape(latents.shape[0], -1)], -1)]
@@ -174,7 +179,6 @@ class Trainer(nn.Module):
             self._box_val, self._box_key = (f(g.scale_factor), f(g.trans_factor), f(h.scale_factor), f(h.trans_factor)), key
         return self._box_val
 
-    @torch.no_grad()
     def nerf_forward(self, **inputs):
         """model/nerf_trainer.py:38-92 without the chunk loop; returns the 7-tuple of predict_and_render_radiance."""
         opt = getattr(self.cfg.nerf, inputs["mode"])
@@ -187,30 +191,33 @@ class Trainer(nn.Module):
         dev = ray_batch.device
         nc, nf = int(opt.num_coarse), int(opt.num_fine)
         rnd = {}
-        if opt.perturb:                                                           # :132-139, utils/nerf_util.py:93-96
+        given = inputs.get("randoms")       # tests: the reference's draws as explicit tensors (SURVEY.md section 8a quirk v)
+        if given is not None:
+            rnd = {k: v for k, v in given.items() if k in ("t_rand", "u_rand", "noise_coarse", "noise_fine") and v is not None}
+        elif opt.perturb:                                                           # :132-139, utils/nerf_util.py:93-96
             rnd["t_rand"] = torch.rand(B, R, nc, dtype=torch.float32, device=dev)
             if nf > 0:
                 rnd["u_rand"] = torch.rand([B * R, nf], dtype=torch.float32).to(dev).view(B, R, nf)   # CPU generator, like the reference
         std = float(opt.radiance_field_noise_std)
-        if std > 0.0:                                                             # utils/nerf_util.py:47-57
+        if given is None and std > 0.0:                                                             # utils/nerf_util.py:47-57
             rnd["noise_coarse"] = torch.randn(B, R, nc, device=dev) * std
             if nf > 0:
                 rnd["noise_fine"] = torch.randn(B, R, (nc + 1) // 2 + nf, device=dev) * std
-        o = hrender.render_rays(ray_batch, bg, inv_head_T, self.model_coarse.triPlane_embeddings, self.headpose_skin_net.volume(),
-                                self.model_coarse.mlp_weights(), nc, nf, boxes=self._boxes(), precision=self.precision, **rnd)
+        render = hrender.render_rays_autograd if torch.is_grad_enabled() else hrender.render_rays
+        o = render(ray_batch, bg, inv_head_T, self.model_coarse.triPlane_embeddings, self.headpose_skin_net.volume(),
+                   self.model_coarse.mlp_weights(), nc, nf, boxes=self._boxes(), precision=self.precision, **rnd)
         return o.rgb_coarse, o.depth_coarse, o.acc_coarse, o.weights_max, o.rgb_fine, o.depth_fine, o.acc_fine
 
-    @torch.no_grad()
     def forward(self, **data):
         """model/nerf_trainer.py:94-118 (including its quirk ii: slots 1 and 5 of the long tuple are both depth_fine)."""
         ray_batch = data["ray_batch"]
         B = ray_batch.shape[0]
         latent_code = self.latent_codes[data["fidx"]] if data["mode"] == "train" else self.latent_codes[0:1]
-        latent_code_loss = torch.square(latent_code - self.latent_codes.mean(dim=0, keepdims=True)).mean()
+        latent_code_loss = torch.square(latent_code - self.latent_codes.mean(dim=0, keepdims=True).detach()).mean()
         rgb_c, _, acc_c, weights, rgb_f, depth_f, acc_f = self.nerf_forward(
             ray_batch=ray_batch, background_prior=data["background_prior"], latent_code=latent_code, inv_head_T=data["inv_head_T"],
             front_render_cond=data["front_render_cond"], left_render_cond=data["left_render_cond"],
-            right_render_cond=data["right_render_cond"], mode=data["mode"])
+            right_render_cond=data["right_render_cond"], mode=data["mode"], randoms=data.get("randoms"))
         if data["render_full_img"]:
             render = rgb_f if rgb_f is not None else rgb_c
             mask = acc_f if acc_f is not None else acc_c

@@ -14,6 +14,7 @@
  *   hav_upfirdn2d        <- model/op/upfirdn2d.cpp:17-31        (pybind module `upfirdn2d`)
  *   hav_render_forward   <- model/nerf_trainer.py:120-201       (Trainer.predict_and_render_radiance; the
  *                            reference has no native boundary here -- it is ~140 ATen launches per chunk)
+ *   hav_render_backward  <- loss.backward() through model/nerf_trainer.py:120-201 (train_avatar.py:149; ATen autograd)
  *   hav_get_rays         <- dataloader/data_util.py:28-56 + dataloader/dataloader.py:174-180
  *   hav_conv2d_forward   <- model/styleUnet.py:222-297 (ModulatedConv2d.forward) and :108-118 (EqualConv2d.forward): the
  *                            reference calls cuDNN grouped conv2d / conv_transpose2d through model/op/conv2d_gradfix.py:22-75
@@ -138,6 +139,35 @@ typedef struct hav_render_args {
 
 uint64_t hav_render_workspace_bytes(const hav_render_args *args);
 int hav_render_forward(const hav_render_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward of hav_render_forward: what autograd produces for Trainer.predict_and_render_radiance in the reference
+ * (model/nerf_trainer.py:120-201 under loss.backward(), train_avatar.py:149) -- gradients with respect to the bi-plane
+ * features, the skinning-weight volume and the ten MLP tensors.  `fwd` is the argument block of the forward call being
+ * differentiated: same inputs and random draws, its OUTPUT buffers still holding that call's results (rgb / depth / acc of
+ * each pass are read; z_fine is required when num_fine > 0: the resampled depths are constants of the backward because the
+ * reference detaches them, nerf_trainer.py:167), precision HAV_PREC_FP16 or HAV_PREC_BF16.  fwd->workspace is not used.
+ * weights_max has no gradient path (the reference never differentiates it, train_avatar.py:131-146).
+ * Upstream gradients may be NULL (= zero).  All outputs are OVERWRITTEN (not accumulated), float32, reference layouts.
+ * grad_scale: power-of-two loss scale for the 16-bit gradient operands; <= 0 = chosen on the device from max|upstream|.
+ */
+typedef struct hav_render_bwd_args {
+  uint32_t struct_bytes; /* = sizeof(hav_render_bwd_args) */
+  float grad_scale;
+  const hav_render_args *fwd;
+  const float *g_rgb_coarse;   /* [B,R,67] */
+  const float *g_depth_coarse; /* [B,R] */
+  const float *g_acc_coarse;   /* [B,R] */
+  const float *g_rgb_fine, *g_depth_fine, *g_acc_fine;
+  float *g_planes;             /* [2,B,C,H,W] */
+  float *g_wvol;               /* [1,2,D,H,W] */
+  float *g_w0, *g_b0, *g_w1, *g_b1, *g_w_alpha, *g_b_alpha, *g_w_feat, *g_b_feat, *g_w_rgb, *g_b_rgb;
+  void *workspace;             /* >= hav_render_backward_workspace_bytes(args) bytes, 256-byte aligned */
+  uint64_t workspace_bytes;
+} hav_render_bwd_args;
+
+uint64_t hav_render_backward_workspace_bytes(const hav_render_bwd_args *args);
+int hav_render_backward(const hav_render_bwd_args *args, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Ray generation (dataloader/data_util.py:28-56 get_rays + near/far of dataloader/dataloader.py:174-180).

@@ -32,17 +32,27 @@ RENDER_CASES = {
 }
 
 
-def _reference_render(trainer, torch, case):
+# backward cases: gradients of  sum_k <cotangent_k, out_k>  from the reference's own autograd (small planes / volume keep the
+# fixtures small; every learnable input of predict_and_render_radiance gets a gradient)
+RENDER_BWD_CASES = {
+    "render_bwd_coarse": dict(batch=1, crop=(248, 240, 7, 15), num_coarse=24, num_fine=0, rand=False, seed=40,
+                              plane_hw=(32, 32), vol_dhw=(16, 16, 16)),
+    "render_bwd_hier_rand": dict(batch=2, crop=(230, 250, 8, 16), num_coarse=64, num_fine=16, rand=True, seed=50,
+                                 plane_hw=(32, 48), vol_dhw=(12, 16, 20)),
+}
+
+
+def _reference_render(trainer, torch, case, grad=False):
     sc = synth.scene(batch=case["batch"], crop=case["crop"], seed=case["seed"],
                      plane_hw=case.get("plane_hw", (128, 128)), vol_dhw=case.get("vol_dhw", (64, 64, 64)))
     B, R = sc["ray_batch"].shape[:2]
     mc = trainer.model_coarse
     sd = {k: torch.from_numpy(v) for k, v in sc["weights"].items()}
     mc.load_state_dict(sd, strict=False)
-    mc.triPlane_embeddings = torch.from_numpy(sc["planes"])
+    mc.triPlane_embeddings = torch.from_numpy(sc["planes"]).requires_grad_(grad)
     hs = trainer.headpose_skin_net
     hs.fix_canoW = True
-    hs.canonical_W = torch.from_numpy(sc["wvol"])
+    hs.canonical_W = torch.from_numpy(sc["wvol"]).requires_grad_(grad)
     opt = trainer.cfg.nerf.train
     opt.num_coarse, opt.num_fine = case["num_coarse"], case["num_fine"]
     opt.perturb = bool(case["rand"])
@@ -70,13 +80,36 @@ def _reference_render(trainer, torch, case):
 
         torch.rand, torch.randn = fake_rand, fake_randn
     try:
-        with torch.no_grad():
+        with torch.set_grad_enabled(grad):
             out = trainer.predict_and_render_radiance("train", rays11, torch.from_numpy(sc["background_prior"]),
                                                       inv_head_T=torch.from_numpy(sc["inv_head_T"]))
     finally:
         torch.rand, torch.randn = orig_rand, orig_randn
     names = ["rgb_coarse", "depth_coarse", "acc_coarse", "weights_max", "rgb_fine", "depth_fine", "acc_fine"]
-    return {n: o.numpy() for n, o in zip(names, out) if o is not None}
+    res = {n: o.detach().numpy() for n, o in zip(names, out) if o is not None}
+    if not grad:
+        return res
+    outs = dict(zip(names, out))
+    cot = synth.cotangents(B, R, case["num_fine"] > 0, seed=case["seed"] + 11)
+    loss = 0.0
+    for k, c in cot.items():
+        loss = loss + (outs[k] * torch.from_numpy(c).reshape(outs[k].shape)).sum()
+    trainer.zero_grad()
+    loss.backward()
+    res = {"out_" + k: v for k, v in res.items()}
+    res["g_planes"] = mc.triPlane_embeddings.grad.numpy()
+    res["g_wvol"] = hs.canonical_W.grad.numpy()
+    params = dict(mc.named_parameters())
+    for k in sc["weights"]:
+        res["g_" + k] = params[k].grad.numpy().copy()
+    return res
+
+
+def gen_render_bwd(trainer, torch):
+    for name, case in RENDER_BWD_CASES.items():
+        out = _reference_render(trainer, torch, case, grad=True)
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), case=json.dumps(case), **out)
+        print(name, {k: (v.shape, "%.3g" % np.abs(v).max()) for k, v in out.items() if k.startswith("g_")})
 
 
 def gen_render(trainer, torch):
@@ -277,6 +310,89 @@ def gen_trainer(torch):
                         latent_code_loss=np.float32(lat), state_dict_shapes=json.dumps({k: list(v) for k, v in shapes.items()}))
 
 
+TRAIN_GRAD_KEYS = ["latent_codes", "model_coarse.fc_alpha.weight", "model_coarse.fc_rgb.bias", "model_coarse.layers_xyz.0.bias",
+                   "model_coarse.layers_xyz.1.weight", "model_coarse.XY_gen.conv_out.0.weight", "model_coarse.XY_gen.style.1.weight",
+                   "model_coarse.YZ_gen.conv1.conv.modulation.bias", "model_coarse.YZ_gen.convs.5.activate.bias",
+                   "model_coarse.YZ_gen.conv_in.1.weight", "headpose_skin_net.canonical_Wvolume.final_conv.weight",
+                   "headpose_skin_net.canonical_Wvolume.filters.0.up.1.bias"]
+
+
+def train_step_inputs(seed=5, batch=2, patch=16):
+    """Deterministic inputs of the stage-one training-step golden (shared with tests/test_trainer.py): B patches of
+    patch x patch rays (train_avatar.py:61-62 uses 64 x 64), targets, masks, the reference's random draws."""
+    sc = synth.scene(batch=batch, crop=(248, 240, patch, patch), seed=seed)
+    R = patch * patch
+    conds = {k: np.abs(synth.named_normal("input." + k, (batch, 7, 256, 256), seed)).astype(np.float32) % np.float32(1.0)
+             for k in ("front_render_cond", "left_render_cond", "right_render_cond")}
+    noise0 = {g: synth.named_normal("input.%s.noise0" % g, (1, 1, 16, 16), seed) for g in ("XY_gen", "YZ_gen")}
+    rnd = synth.randoms(batch, R, 64, 16, seed=seed + 7)
+    rs = np.random.RandomState(seed + 1)
+    target = rs.uniform(0, 1, size=(batch, R, 3)).astype(np.float32)
+    mask = (rs.uniform(0, 1, size=(batch, R, 1)) > 0.4).astype(np.float32)
+    return sc, conds, noise0, rnd, target, mask
+
+
+def train_step_loss(torch, out, target, mask, mask_weight=0.01):
+    """The differentiable part of the stage-one loss that needs no external weights (train_avatar.py:131-146 minus LPIPS and
+    the volume-smoothness term): mse + mask BCE on the coarse and the fine pass + the latent-code regulariser."""
+    import torch.nn.functional as F
+
+    rgb_c, _, acc_c, _, rgb_f, _, acc_f, lat = out
+    loss = F.mse_loss(rgb_c[..., :3], target) + mask_weight * F.binary_cross_entropy(acc_c.clip(1e-3, 1.0 - 1e-3), mask)
+    loss = loss + F.mse_loss(rgb_f[..., :3], target) + mask_weight * F.binary_cross_entropy(acc_f.clip(1e-3, 1.0 - 1e-3), mask)
+    return loss + lat
+
+
+def gen_trainer_train(torch):
+    """Whole training-step golden: the unmodified reference Trainer.forward(mode='train') + loss.backward() on CPU; stores the
+    loss and the gradients of a dozen parameters spread over every sub-network."""
+    from oracle import ref_shim
+    from model.nerf_trainer import Trainer
+
+    cfg = ref_shim.load_cfg()
+    cfg.nerf.train.perturb, cfg.nerf.train.radiance_field_noise_std = True, 0.1
+    cfg.nerf.train.num_coarse, cfg.nerf.train.num_fine = 64, 16
+    net = Trainer(cfg, 4)
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    sd = synth.trainer_state(shapes, seed=3)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    with torch.no_grad():
+        net.latent_codes.copy_(torch.from_numpy(synth.named_normal("latent_codes", (4, 32), 5) * np.float32(0.1)))
+    sc, conds, noise0, rnd, target, mask = train_step_inputs()
+    net.model_coarse.XY_gen.zero_noise[0] = torch.from_numpy(noise0["XY_gen"])
+    net.model_coarse.YZ_gen.zero_noise[0] = torch.from_numpy(noise0["YZ_gen"])
+    B, R = sc["ray_batch"].shape[:2]
+    q_rand = [rnd["t_rand"], rnd["u_rand"].reshape(B * R, -1)]
+    q_randn = [rnd["unit_coarse"].reshape(B * R, -1), rnd["unit_fine"].reshape(B * R, -1)]
+    orig_rand, orig_randn = torch.rand, torch.randn
+
+    def fake_rand(shape, *a, **k):
+        v = q_rand.pop(0)
+        assert tuple(shape) == v.shape, (tuple(shape), v.shape)
+        return torch.from_numpy(v.copy())
+
+    def fake_randn(shape, *a, **k):
+        v = q_randn.pop(0)
+        assert tuple(shape) == v.shape, (tuple(shape), v.shape)
+        return torch.from_numpy(v.copy())
+
+    torch.rand, torch.randn = fake_rand, fake_randn
+    try:
+        out = net(mode="train", fidx=torch.tensor([1, 3]), render_full_img=False, ray_batch=torch.from_numpy(sc["ray_batch"]),
+                  background_prior=torch.from_numpy(sc["background_prior"]), inv_head_T=torch.from_numpy(sc["inv_head_T"]),
+                  **{k: torch.from_numpy(v) for k, v in conds.items()})
+    finally:
+        torch.rand, torch.randn = orig_rand, orig_randn
+    assert not q_rand and not q_randn
+    loss = train_step_loss(torch, out, torch.from_numpy(target), torch.from_numpy(mask))
+    loss.backward()
+    params = dict(net.named_parameters())
+    res = {"g_" + k: params[k].grad.numpy() for k in TRAIN_GRAD_KEYS}
+    print("trainer_train loss %.6f" % float(loss), {k: "%.3g" % np.abs(v).max() for k, v in res.items()})
+    np.savez_compressed(os.path.join(GOLD, "trainer_train_step.npz"), loss=np.float32(loss.item()), rgb_fine=out[4].detach().numpy(),
+                        acc_fine=out[6].detach().numpy(), **res)
+
+
 def main():
     from oracle import ref_shim
 
@@ -286,14 +402,20 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(GOLD, exist_ok=True)
-    gen_stages(torch)
-    gen_ops(torch)
-    gen_styleunet(torch)
-    gen_trainer(torch)
+    if "--train-only" in sys.argv:
+        return gen_trainer_train(torch)
+    if "--bwd-only" not in sys.argv:
+        gen_stages(torch)
+        gen_ops(torch)
+        gen_styleunet(torch)
+        gen_trainer(torch)
     from model.nerf_trainer import Trainer
 
     trainer = Trainer(cfg, 4)
-    gen_render(trainer, torch)
+    if "--bwd-only" not in sys.argv:
+        gen_render(trainer, torch)
+    gen_render_bwd(trainer, torch)
+    gen_trainer_train(torch)
 
 
 if __name__ == "__main__":

@@ -84,6 +84,27 @@ def _sample_pdf(bins, weights, n, u_rand):
     return b0 + (u - c0) / denom * (b1 - b0)
 
 
+def render_rays_grad(ray_batch, background_prior, inv_head_T, planes, wvol, weights, boxes, num_coarse, num_fine=0,
+                     cotangents=None, device="cpu", **rand):
+    """Gradients of  sum_k <cotangents[k], out[k]>  with respect to planes, wvol and the MLP tensors, by torch autograd over
+    the ATen call sequence above -- what loss.backward() does in the reference (train_avatar.py:149).  z_samples is detached
+    like the reference does (model/nerf_trainer.py:167).  -> (outputs dict, grads dict), numpy."""
+    T = lambda a: torch.as_tensor(a, dtype=torch.float32).to(device)
+    leaves = {"planes": T(planes).requires_grad_(True), "wvol": T(wvol).requires_grad_(True)}
+    w = {k: T(v).requires_grad_(True) for k, v in weights.items()}
+    with torch.enable_grad():
+        out = render_rays.__wrapped__(ray_batch, background_prior, inv_head_T, leaves["planes"], leaves["wvol"], w, boxes,
+                                      num_coarse, num_fine, device=device, to_numpy=False, **rand)
+        loss = 0.0
+        for k, c in cotangents.items():
+            if c is not None and out.get(k) is not None:
+                loss = loss + (out[k] * T(c).reshape(out[k].shape)).sum()
+        loss.backward()
+    grads = {k: v.grad.cpu().numpy() for k, v in leaves.items()}
+    grads.update({k: v.grad.cpu().numpy() for k, v in w.items()})
+    return {k: (None if v is None else v.detach().cpu().numpy()) for k, v in out.items()}, grads
+
+
 @torch.no_grad()
 def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, boxes, num_coarse, num_fine=0,
                 t_rand=None, noise_coarse=None, u_rand=None, noise_fine=None, chunk=4096, device="cpu", to_numpy=True):
@@ -91,7 +112,7 @@ def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, 
     (model/nerf_trainer.py:65-71; nerf.validation.chunksize).  device="cuda" runs the very same ATen call sequence on the
     GPU in fp32 -- bench.py times that as the stand-in for the reference's own GPU path (the reference tree is Python and
     does not exist on the GPU box)."""
-    T = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32).to(device)
+    T = lambda a: None if a is None else (a if isinstance(a, torch.Tensor) and a.requires_grad else torch.as_tensor(a, dtype=torch.float32).to(device))
     ray_batch, background_prior, inv_head_T, planes, wvol = map(T, (ray_batch, background_prior, inv_head_T, planes, wvol))
     t_rand, noise_coarse, u_rand, noise_fine = map(T, (t_rand, noise_coarse, u_rand, noise_fine))
     w = {k: T(v) for k, v in weights.items()}
@@ -117,7 +138,7 @@ def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, 
             per["rgb_coarse"].append(rgb), per["depth_coarse"].append(depth), per["acc_coarse"].append(acc)
             if num_fine > 0:
                 zs = _sample_pdf(0.5 * (z[:, 1:] + z[:, :-1]), wts[:, 1:-1], num_fine, sel(u_rand))       # :166-167
-                zf, _ = torch.sort(torch.cat([z[:, ::2], zs], dim=-1), dim=-1)                            # :170
+                zf, _ = torch.sort(torch.cat([z[:, ::2], zs.detach()], dim=-1), dim=-1)                            # :170
                 rgbf, accf, wf, depthf = _pass(ro, rd, zf, inv_head_T[b], planes[:, b], wvol, w, boxes, bg, sel(noise_fine))
                 per["rgb_fine"].append(rgbf), per["depth_fine"].append(depthf), per["acc_fine"].append(accf)
                 per["weights_max"].append(wf.max(dim=-1)[0])

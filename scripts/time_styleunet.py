@@ -7,6 +7,7 @@ inp = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 out = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 torch.manual_seed(0)
+torch.set_grad_enabled(False)   # inference kernels (grad mode selects the differentiable formulation)
 net = styleunet.SWGAN_unet(inp_size=inp, inp_ch=64, out_ch=3, out_size=out, style_dim=64, n_mlp=4, middle_size=8).cuda()
 x = torch.randn(B, 64, inp, inp, device="cuda"); s = torch.randn(B, 64, device="cuda")
 noise = net.make_noise("cuda")

@@ -34,8 +34,11 @@ def test_full_size_constructors_match_reference_parameter_counts():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["kernels", "autograd"])
 @pytest.mark.parametrize("name", list(STYLEUNET_CASES))
-def test_forward_matches_reference_golden(golden_dir, name):
+def test_forward_matches_reference_golden(golden_dir, name, mode):
+    """mode 'kernels': torch.no_grad() -> the fused tcgen05 inference path; 'autograd': gradients enabled -> the differentiable
+    formulation of styleunet_train.py (what the training steps run).  Both against the reference's output."""
     case = STYLEUNET_CASES[name]
     g = np.load(os.path.join(golden_dir, "styleunet_%s.npz" % name))
     net = _build(case)
@@ -44,15 +47,17 @@ def test_forward_matches_reference_golden(golden_dir, name):
     assert not missing.unexpected_keys
     net = net.cuda()
     t = lambda a: torch.from_numpy(a).cuda()
-    if case["net"] == "SWGAN_unet":
-        out = net([t(style)], t(cond), noise=[t(n) for n in noise])
-    elif case["net"] == "Discriminator":
-        out = net(t(cond))
-    else:
-        net.zero_noise[0] = t(noise[0])
-        out, _ = net([t(style)], t(cond))
+    with torch.set_grad_enabled(mode == "autograd"):
+        if case["net"] == "SWGAN_unet":
+            out = net([t(style)], t(cond), noise=[t(n) for n in noise])
+        elif case["net"] == "Discriminator":
+            out = net(t(cond))
+        else:
+            net.zero_noise[0] = t(noise[0])
+            out, _ = net([t(style)], t(cond))
     torch.cuda.synchronize()
-    out, ref = out.cpu().numpy(), g["out"]
+    assert out.requires_grad == (mode == "autograd")
+    out, ref = out.detach().cpu().numpy(), g["out"]
     assert out.shape == ref.shape
     # fp16 operands, fp32 accumulation, ~20 convolutions deep: 2e-2 of the output range (stated tolerance)
     err = np.abs(out - ref).max() / np.abs(ref).max()
