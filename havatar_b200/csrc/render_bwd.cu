@@ -29,8 +29,13 @@ using namespace tc;
 constexpr int kThr = 128;
 constexpr int kSmA = kWImgBytes;
 constexpr int kSmStage = kSmA + kABytes;
-constexpr int kSmBarB = kSmStage + kStageBytes;
-constexpr int kSmBytesB = kSmBarB + 64;
+constexpr int kSmD = kSmStage + kStageBytes;      // d(feature)/d(ix), d(feature)/d(iy) of every row: 32 chunks like the A operand
+constexpr int kDChunks = 32;
+constexpr int kSmBarB = kSmD + kDChunks * kChunkA;
+constexpr int kSmWin = kSmBarB + 64;              // per-warp min / max of the tap coordinates: [4 warps][8] ints
+constexpr int kSmBytesB = kSmWin + 4 * 8 * 4;
+static_assert(kSmBytesB <= 232448, "shared memory budget");
+constexpr int kWinTexels = 128;                   // texel window of the tensor-core scatter (one TMEM lane per texel)
 constexpr int kC0 = 0, kC1 = 128, kC2 = 256, kC3 = 384;   // TMEM column blocks
 
 // per-tile operand images in HBM
@@ -68,6 +73,13 @@ __device__ __forceinline__ void unpack2(uint32_t v, float &lo, float &hi) {
     lo = f.x, hi = f.y;
   }
 }
+template <bool kBF16>
+__device__ __forceinline__ uint32_t sub2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  if (kBF16) asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  else asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
 #define HAV_TMEM_LD16(r, taddr)                                                                                        \
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),        \
@@ -83,14 +95,16 @@ constexpr uint32_t kBMajorMN = 1u << 16, kAMajorMN = 1u << 15;
 
 // F.grid_sample(4-D, zeros, align_corners) tap base on the zero-bordered packed plane + whether the coordinate is inside the
 // range where the interpolant depends on it (outside every corner is padding: zero gradient, as in ATen's backward)
-__device__ __forceinline__ void plane_taps_b(float gx, float gy, int H, int W, int img, int &off, float &wx, float &wy, bool &in) {
+__device__ __forceinline__ void plane_taps_b(float gx, float gy, int H, int W, int img, int &off, float &wx, float &wy, bool &in,
+                                             int &px, int &py) {
   const float ux = unnorm(gx, W), uy = unnorm(gy, H);
   in = ux > -1.0f && ux < (float)W && uy > -1.0f && uy < (float)H;
   float ix = fminf(fmaxf(ux, -1.0f), (float)W), iy = fminf(fmaxf(uy, -1.0f), (float)H);
   float x0f = floorf(ix), y0f = floorf(iy);
   wx = ix - x0f, wy = iy - y0f;
   const int Hp = H + kPadLo + kPadHi, Wp = W + kPadLo + kPadHi;
-  off = (img * Hp + ((int)y0f + kPadLo)) * Wp + ((int)x0f + kPadLo);
+  px = (int)x0f + kPadLo, py = img * Hp + ((int)y0f + kPadLo);   // column / row of tap (y0,x0) in the stacked padded images
+  off = py * Wp + px;
 }
 
 // backward of trilinear_border (render_common.cuh) with respect to the volume: the same corners and weights, scattered
@@ -161,6 +175,8 @@ __global__ void __launch_bounds__(kThr, 1) render_bwd_kernel(const RenderDev P, 
   uint8_t *Abuf = smem + kSmA;
   const uint32_t A_addr = smem_base + kSmA;
   Stage *stage = reinterpret_cast<Stage *>(smem + kSmStage);
+  uint8_t *Dbuf = smem + kSmD;
+  int *win_s = reinterpret_cast<int *>(smem + kSmWin);
   const uint32_t bar = smem_base + kSmBarB;
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kSmBarB + 32);
 
@@ -191,6 +207,7 @@ __global__ void __launch_bounds__(kThr, 1) render_bwd_kernel(const RenderDev P, 
 
   constexpr uint32_t kIdesc128 = instr_desc(128, kBF16), kIdescH = instr_desc(kNH, kBF16);
   constexpr uint32_t kIdescD128 = instr_desc(128, kBF16) | kBMajorMN, kIdescDX = instr_desc(kIn, kBF16) | kBMajorMN;
+  constexpr uint32_t kIdescSc = instr_desc(kPlaneC, kBF16) | kAMajorMN | kBMajorMN;
   const uint32_t W0_addr = smem_base + kW0Off, W1_addr = smem_base + kW1Off, WH_addr = smem_base + kWHOff;
   const int Wp = P.PW + kPadLo + kPadHi;
   const uint4 *planes = reinterpret_cast<const uint4 *>(P.planes_cl);
@@ -280,10 +297,19 @@ __global__ void __launch_bounds__(kThr, 1) render_bwd_kernel(const RenderDev P, 
         }
         Stage st;
         bool in0, in1;
+        int tpx[2], tpy[2];
         {
           float qx = pc[0] * P.ps[0] + P.pt[0], qy = pc[1] * P.ps[1] + P.pt[1], qz = pc[2] * P.ps[2] + P.pt[2];
-          plane_taps_b(qx, qy, P.PH, P.PW, ray.b, st.off0, st.wx0, st.wy0, in0);
-          plane_taps_b(qz, qy, P.PH, P.PW, P.B + ray.b, st.off1, st.wx1, st.wy1, in1);
+          plane_taps_b(qx, qy, P.PH, P.PW, ray.b, st.off0, st.wx0, st.wy0, in0, tpx[0], tpy[0]);
+          plane_taps_b(qz, qy, P.PH, P.PW, P.B + ray.b, st.off1, st.wx1, st.wy1, in1, tpx[1], tpy[1]);
+          // bounding box of this tile's taps per plane (warp reduction now, combined after the next barrier)
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl) {
+            const int big = 0x3fffffff;
+            const int xmn = __reduce_min_sync(0xffffffffu, ray.valid ? tpx[pl] : big), xmx = __reduce_max_sync(0xffffffffu, ray.valid ? tpx[pl] : -big);
+            const int ymn = __reduce_min_sync(0xffffffffu, ray.valid ? tpy[pl] : big), ymx = __reduce_max_sync(0xffffffffu, ray.valid ? tpy[pl] : -big);
+            if (lane == 0) *reinterpret_cast<int4 *>(win_s + warp * 8 + pl * 4) = make_int4(xmn, xmx, ymn, ymx);
+          }
           reinterpret_cast<uint4 *>(stage + t)[0] = make_uint4(st.off0, st.off1, __float_as_uint(st.wx0), __float_as_uint(st.wy0));
           reinterpret_cast<uint2 *>(stage + t)[2] = make_uint2(__float_as_uint(st.wx1), __float_as_uint(st.wy1));
         }
@@ -309,6 +335,18 @@ __global__ void __launch_bounds__(kThr, 1) render_bwd_kernel(const RenderDev P, 
             *reinterpret_cast<uint4 *>(Abuf + (16 + c) * kChunkA + t * 16) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
         }
         bar_wg(0);
+        int wxmin[2], wymin[2], wW[2];   // texel window of this tile per plane: origin and row pitch (see the scatter below)
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          int4 b = *reinterpret_cast<const int4 *>(win_s + pl * 4);
+#pragma unroll
+          for (int wq = 1; wq < 4; ++wq) {
+            const int4 o = *reinterpret_cast<const int4 *>(win_s + wq * 8 + pl * 4);
+            b.x = min(b.x, o.x), b.y = max(b.y, o.y), b.z = min(b.z, o.z), b.w = max(b.w, o.w);
+          }
+          wxmin[pl] = b.x, wymin[pl] = b.z;
+          wW[pl] = b.y >= b.x ? min(b.y - b.x + 2, kWinTexels) : 1;
+        }
         {   // cooperative bi-plane gather: 16 lanes per row (2 planes x 8 channel octets), 2 rows per step
           const int sub = lane >> 4, plane = (lane >> 3) & 1, oct = lane & 7;
 #pragma unroll 2
@@ -328,6 +366,19 @@ __global__ void __launch_bounds__(kThr, 1) render_bwd_kernel(const RenderDev P, 
             r.z = fma2<kBF16>(t11.z, w11, fma2<kBF16>(t10.z, w10, fma2<kBF16>(t01.z, w01, mul2<kBF16>(t00.z, w00))));
             r.w = fma2<kBF16>(t11.w, w11, fma2<kBF16>(t10.w, w10, fma2<kBF16>(t01.w, w01, mul2<kBF16>(t00.w, w00))));
             *reinterpret_cast<uint4 *>(Abuf + (plane * 8 + oct) * kChunkA + row * 16) = r;
+            // coordinate derivatives of the interpolant, kept for the backward of this tile (util.py:395-406):
+            //   d/d(ix) = (t01 - t00) uy + (t11 - t10) wy ,  d/d(iy) = (t10 - t00) ux + (t11 - t01) wx
+            const uint32_t a4[4] = {t00.x, t00.y, t00.z, t00.w}, b4[4] = {t01.x, t01.y, t01.z, t01.w};
+            const uint32_t c4[4] = {t10.x, t10.y, t10.z, t10.w}, d4[4] = {t11.x, t11.y, t11.z, t11.w};
+            const uint32_t ux2 = pack2<kBF16>(ux, ux), uy2 = pack2<kBF16>(uy, uy), wx2 = pack2<kBF16>(wx, wx), wy2 = pack2<kBF16>(wy, wy);
+            uint32_t dx4[4], dy4[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              dx4[h] = fma2<kBF16>(sub2<kBF16>(b4[h], a4[h]), uy2, mul2<kBF16>(sub2<kBF16>(d4[h], c4[h]), wy2));
+              dy4[h] = fma2<kBF16>(sub2<kBF16>(c4[h], a4[h]), ux2, mul2<kBF16>(sub2<kBF16>(d4[h], b4[h]), wx2));
+            }
+            *reinterpret_cast<uint4 *>(Dbuf + ((plane * 8 + oct) * 2) * kChunkA + row * 16) = make_uint4(dx4[0], dx4[1], dx4[2], dx4[3]);
+            *reinterpret_cast<uint4 *>(Dbuf + ((plane * 8 + oct) * 2 + 1) * kChunkA + row * 16) = make_uint4(dy4[0], dy4[1], dy4[2], dy4[3]);
           }
         }
         fence_async_smem();
@@ -451,7 +502,19 @@ __global__ void __launch_bounds__(kThr, 1) render_bwd_kernel(const RenderDev P, 
 #pragma unroll
             for (int j = 0; j < 3; ++j) dpc[j] *= ginv;
           }
-          // bi-plane features: texel gradients (scatter) and coordinate gradients (util.py:359-406)
+          // bi-plane features (util.py:359-406).  Coordinate gradients: <d_feat, d(feature)/d(ix, iy)> with the derivatives
+          // saved by the gather.  Texel gradients: rows of a tile share most of their texels (neighbouring pixels are a
+          // fraction of a texel apart), so instead of 4 taps x 64 channels of global reductions per row and plane the tile is
+          // reduced on the tensor core first:  G[texel][ch] = S[texel][row] . d_feat[row][ch], S = bilinear weights of the rows
+          // over a window of <= 128 texels around the tile's taps (one TMEM lane per window texel); only window texels are
+          // then added to the global image.  Rows whose taps fall outside the window take the direct path.
+          int m00[2];
+          bool inwin[2];
+#pragma unroll
+          for (int plane = 0; plane < 2; ++plane) {
+            m00[plane] = (tpy[plane] - wymin[plane]) * wW[plane] + (tpx[plane] - wxmin[plane]);
+            inwin[plane] = ray.valid && tpx[plane] - wxmin[plane] + 1 < wW[plane] && m00[plane] + wW[plane] + 1 < kWinTexels;
+          }
 #pragma unroll 1
           for (int plane = 0; plane < 2; ++plane) {
             const int off = plane ? st.off1 : st.off0;
@@ -459,46 +522,50 @@ __global__ void __launch_bounds__(kThr, 1) render_bwd_kernel(const RenderDev P, 
             const float ux = 1.0f - wx, uy = 1.0f - wy;
             const float tw[4] = {ux * uy, wx * uy, ux * wy, wx * wy};
             const int toff[4] = {0, 1, Wp, Wp + 1};
-            float dots[4] = {0.f, 0.f, 0.f, 0.f};
+            float dfx = 0.0f, dfy = 0.0f;
 #pragma unroll 1
             for (int q = 0; q < 2; ++q) {
               uint32_t r[32];
               HAV_TMEM_LD32(r, tmC0 + tm_lane + plane * 64 + q * 32);
               tmem_wait_ld();
 #pragma unroll
-              for (int tap = 0; tap < 4; ++tap) {
-                const size_t texel = (size_t)(off + toff[tap]);
-                const uint4 *tp = planes + texel * 8 + q * 4;
-                float *gp = Q.gplanes_cl + texel * kPlaneC + q * 32;
-                const float wv = tw[tap] * ginv;
-                float d = 0.0f;
+              for (int i = 0; i < 4; ++i) {
+                const uint8_t *dp = Dbuf + ((plane * 8 + q * 4 + i) * 2) * kChunkA + t * 16;
+                const uint4 vx = *reinterpret_cast<const uint4 *>(dp), vy = *reinterpret_cast<const uint4 *>(dp + kChunkA);
+                const uint32_t x4[4] = {vx.x, vx.y, vx.z, vx.w}, y4[4] = {vy.x, vy.y, vy.z, vy.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const uint4 tv = __ldg(tp + i);
-                  const uint32_t tw4[4] = {tv.x, tv.y, tv.z, tv.w};
-#pragma unroll
-                  for (int h2 = 0; h2 < 4; ++h2) {
-                    float lo, hi;
-                    unpack2<kBF16>(tw4[h2], lo, hi);
-                    d = fmaf(__uint_as_float(r[i * 8 + h2 * 2]), lo, d);
-                    d = fmaf(__uint_as_float(r[i * 8 + h2 * 2 + 1]), hi, d);
-                  }
+                for (int h2 = 0; h2 < 4; ++h2) {
+                  float lo, hi;
+                  unpack2<kBF16>(x4[h2], lo, hi);
+                  dfx = fmaf(__uint_as_float(r[i * 8 + h2 * 2]), lo, dfx);
+                  dfx = fmaf(__uint_as_float(r[i * 8 + h2 * 2 + 1]), hi, dfx);
+                  unpack2<kBF16>(y4[h2], lo, hi);
+                  dfy = fmaf(__uint_as_float(r[i * 8 + h2 * 2]), lo, dfy);
+                  dfy = fmaf(__uint_as_float(r[i * 8 + h2 * 2 + 1]), hi, dfy);
                 }
-                dots[tap] += d;
-                if (ray.valid && wv != 0.0f) {
+                // d_feat (still loss-scaled) as the 16-bit B operand of the scatter GEMM, in the dead X buffer
+                *reinterpret_cast<uint4 *>(Abuf + (plane * 8 + q * 4 + i) * kChunkA + t * 16) =
+                    make_uint4(pack2<kBF16>(__uint_as_float(r[i * 8]), __uint_as_float(r[i * 8 + 1])),
+                               pack2<kBF16>(__uint_as_float(r[i * 8 + 2]), __uint_as_float(r[i * 8 + 3])),
+                               pack2<kBF16>(__uint_as_float(r[i * 8 + 4]), __uint_as_float(r[i * 8 + 5])),
+                               pack2<kBF16>(__uint_as_float(r[i * 8 + 6]), __uint_as_float(r[i * 8 + 7])));
+              }
+              if (ray.valid && !inwin[plane]) {   // direct path: w_tap * d_feat straight into the channels-last image
+#pragma unroll 1
+                for (int tap = 0; tap < 4; ++tap) {
+                  const float wv = tw[tap] * ginv;
+                  if (wv != 0.0f) {
+                    float *gp = Q.gplanes_cl + (size_t)(off + toff[tap]) * kPlaneC + q * 32;
 #pragma unroll
-                  for (int i = 0; i < 8; ++i)
-                    red_add_v4(gp + i * 4, __uint_as_float(r[i * 4]) * wv, __uint_as_float(r[i * 4 + 1]) * wv,
-                               __uint_as_float(r[i * 4 + 2]) * wv, __uint_as_float(r[i * 4 + 3]) * wv);
+                    for (int i = 0; i < 8; ++i)
+                      red_add_v4(gp + i * 4, __uint_as_float(r[i * 4]) * wv, __uint_as_float(r[i * 4 + 1]) * wv,
+                                 __uint_as_float(r[i * 4 + 2]) * wv, __uint_as_float(r[i * 4 + 3]) * wv);
+                  }
                 }
               }
             }
-            const bool in = plane ? in1 : in0;
-            if (in) {
-              // d/d(ix) = (t01 - t00) uy + (t11 - t10) wy ;  d/d(iy) = (t10 - t00) ux + (t11 - t01) wx
-              const float dix = ((dots[1] - dots[0]) * uy + (dots[3] - dots[2]) * wy) * ginv;
-              const float diy = ((dots[2] - dots[0]) * ux + (dots[3] - dots[1]) * wx) * ginv;
-              const float gx = dix * 0.5f * (float)(P.PW - 1), gy = diy * 0.5f * (float)(P.PH - 1);
+            if (plane ? in1 : in0) {
+              const float gx = dfx * ginv * 0.5f * (float)(P.PW - 1), gy = dfy * ginv * 0.5f * (float)(P.PH - 1);
               // plane 0 is sampled at (qx, qy), plane 1 at (qz, qy)  (util.py:378-381)
               if (plane == 0) dpc[0] = fmaf(gx, P.ps[0], dpc[0]);
               else dpc[2] = fmaf(gx, P.ps[2], dpc[2]);
@@ -516,6 +583,56 @@ __global__ void __launch_bounds__(kThr, 1) render_bwd_kernel(const RenderDev P, 
                                      p[2] * P.ss[2] + P.st[2], dw0);
             trilinear_border_scatter(Q.gwvol + vs, P.VD, P.VH, P.VW, p1[0] * P.ss[0] + P.st[0], p1[1] * P.ss[1] + P.st[1],
                                      p1[2] * P.ss[2] + P.st[2], dw1);
+          }
+          // ---- scatter GEMM.  S lives where the coordinate derivatives were (every thread is done reading them after the
+          //      barrier), MN-major: element (texel m, row r) at [m / 8][r][m % 8], so row thread r owns and rewrites its whole
+          //      column (16 x 16 bytes per plane) every tile -- no clearing pass.
+          bar_wg(0);
+#pragma unroll 1
+          for (int plane = 0; plane < 2; ++plane) {
+            const float wx = plane ? st.wx1 : st.wx0, wy = plane ? st.wy1 : st.wy0;
+            const float ux = 1.0f - wx, uy = 1.0f - wy;
+            const int mt[4] = {m00[plane], m00[plane] + 1, m00[plane] + wW[plane], m00[plane] + wW[plane] + 1};
+            const uint32_t p01 = pack2<kBF16>(ux * uy, wx * uy), p23 = pack2<kBF16>(ux * wy, wx * wy);
+            const uint16_t hw[4] = {(uint16_t)(p01 & 0xFFFFu), (uint16_t)(p01 >> 16), (uint16_t)(p23 & 0xFFFFu), (uint16_t)(p23 >> 16)};
+            uint8_t *Sp = Dbuf + plane * (16 * kChunk) + t * 16;
+#pragma unroll
+            for (int gq = 0; gq < 16; ++gq) *reinterpret_cast<uint4 *>(Sp + gq * kChunk) = make_uint4(0u, 0u, 0u, 0u);
+            if (inwin[plane]) {   // same-thread stores: the four weights land after the zero fill of this column
+#pragma unroll
+              for (int tap = 0; tap < 4; ++tap)
+                *reinterpret_cast<volatile uint16_t *>(Sp + (mt[tap] >> 3) * kChunk + (mt[tap] & 7) * 2) = hw[tap];
+            }
+          }
+          fence_async_smem();
+          tc_fence_before();
+          bar_wg(0);
+          HAV_MMA_ROUND({
+            for (int plane = 0; plane < 2; ++plane)
+              for (int k = 0; k < 8; ++k)
+                umma_ss(tmC2 + plane * 64, smem_desc_mn(smem_base + kSmD + plane * (16 * kChunk) + k * 256, 128, kChunk, Q.swap_mn),
+                        smem_desc_mn(A_addr + plane * 8 * kChunkA + k * 256, 128, kChunkA, Q.swap_mn), kIdescSc, k > 0);
+          });
+          // window texel m = this thread's TMEM lane: add its 64 channels to the global image unless the row is empty
+#pragma unroll 1
+          for (int plane = 0; plane < 2; ++plane) {
+            const size_t texel = (size_t)(wymin[plane] + t / wW[plane]) * Wp + (wxmin[plane] + t % wW[plane]);
+#pragma unroll 1
+            for (int q = 0; q < 2; ++q) {
+              uint32_t r[32];
+              HAV_TMEM_LD32(r, tmC2 + tm_lane + plane * 64 + q * 32);
+              tmem_wait_ld();
+              uint32_t any = 0u;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) any |= r[i];
+              if ((any & 0x7FFFFFFFu) != 0u) {
+                float *gp = Q.gplanes_cl + texel * kPlaneC + q * 32;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  red_add_v4(gp + i * 4, __uint_as_float(r[i * 4]) * ginv, __uint_as_float(r[i * 4 + 1]) * ginv,
+                             __uint_as_float(r[i * 4 + 2]) * ginv, __uint_as_float(r[i * 4 + 3]) * ginv);
+              }
+            }
           }
         }
         tc_fence_before();   // the next tile's L0 overwrites C0

@@ -30,6 +30,7 @@ class AvatarHD(torch.nn.Module):
         self.render_size, self.num_coarse, self.num_fine, self.precision, self.boxes = render_size, num_coarse, num_fine, precision, boxes
         self._noise = None
 
+    @torch.no_grad()
     def planes(self, latent_code, inv_head_T, front, left, right):
         """set_conditional_embedding (model/nerf_model.py:58-86): left view flipped along W, its mask channel dropped."""
         lat = [torch.cat([latent_code, inv_head_T.reshape(inv_head_T.shape[0], -1)], dim=-1)]
