@@ -267,6 +267,44 @@ def run_ours(args):
       except Exception as exc:  # the secondary metric must never take the headline line down with it
         hd["error"] = "%s: %s" % (type(exc).__name__, exc)
 
+    # ---- the two training steps (BASELINE.json configs[2] and configs[4]): per-rank frames, gradients all-reduced over NCCL
+    #      in buckets from inside backward (havatar_b200/parallel.py); device-timed, max over ranks
+    train = {}
+    if not args.no_train:
+      try:
+        from havatar_b200 import train_step
+
+        torch.cuda.empty_cache()
+        for name, mk, mkb, frames in (
+                ("stage_one_b4_patch64", lambda: train_step.StageOneStep(n_frames=4 * world, device=dev),
+                 lambda: train_step.synthetic_batch(1, 4, dev, seed=rank, patch=64, frame_offset=4 * rank), 4),
+                ("stage_two_b1_128_to_512", lambda: train_step.StageTwoStep(n_frames=world, device=dev),
+                 lambda: train_step.synthetic_batch(2, 1, dev, seed=rank, render_size=128, gen_size=512, frame_offset=rank), 1)):
+            st, batch = mk(), mkb()
+            for _ in range(3):
+                st(batch)
+            barrier()
+            n_t = max(3, min(args.steps, 10))
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for _ in range(n_t):
+                res_t = st(batch)
+            b_.record()
+            barrier()
+            ms = torch.tensor([a_.elapsed_time(b_) / n_t], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            ok = all(bool(torch.isfinite(v)) for v in res_t.values() if v is not None)
+            syncs = [g_.sync for g_ in (getattr(st, "g", None), getattr(st, "d", None), getattr(st, "nerf", None)) if g_ is not None and g_.sync is not None]
+            train[name] = {"ms_per_step": float(ms), "frames_per_sec": world * frames * 1e3 / float(ms), "steps": n_t, "finite": ok,
+                           "frames_per_gpu": frames,
+                           "allreduce_bytes_per_step": sum(s_.bytes_per_step for s_ in syncs),
+                           "allreduce_buckets": sum(len(s_.buckets) for s_ in syncs)}
+            del st, batch
+            torch.cuda.empty_cache()
+      except Exception as exc:
+        train["error"] = "%s: %s" % (type(exc).__name__, exc)
+
     t = torch.tensor([step_ms, kern_ms, e2e_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -338,6 +376,9 @@ def run_ours(args):
                          "seconds": cpu_s},
         "reference_gpu_port": ref_gpu,
         "clocks": clocks,
+        "train": dict(train, note="one optimiser iteration per step, synthetic data, LPIPS omitted (weights unavailable offline): stage one = "
+                                  "train_avatar.py:112-158 on 4 frames x 64x64-ray patches per GPU (64+16 samples, fused render fwd+bwd, patch "
+                                  "discriminator); stage two = train_avatarHD.py:201-303 on 1 frame per GPU (D step + G step, 128^2 render -> 512^2)"),
         "hd": dict(hd, note="HD frames/s = XY/YZ plane generators (StyleGAN_zxc) + 512x512x64 or 128x128x64 render + SWGAN_unet, "
                             "one frame per GPU, CUDA-graph replay, random-init weights, per-rank values (not max-reduced)"),
     }
@@ -353,6 +394,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--no-train", dest="no_train", action="store_true", help="skip the training-step measurement")
     ap.add_argument("--no-hd", dest="no_hd", action="store_true", help="skip the secondary HD frames/s measurement")
     args = ap.parse_args()
     if args.impl == "reference":

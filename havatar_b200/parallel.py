@@ -1,0 +1,152 @@
+"""Data-parallel gradient exchange for the two training steps: one process per GPU, frames sharded
+across ranks, and ONE exchange step per optimiser step -- all-reduce(SUM)/world on the gradients only.  The reference has no
+multi-GPU render path of its own (train_avatarHD.py wraps its modules in torch DistributedDataParallel, :125-134); this is the
+B200-side equivalent, written for NVLink 5 / NVSwitch:
+
+  * gradients live in a few large flat fp32 buckets (parameters' .grad are views into them), so one collective moves
+    64 MiB instead of hundreds of small tensors -- on NVSwitch the cost is launch latency + bytes / bus bandwidth, not
+    per-link hops, so buckets are sized for overlap granularity only;
+  * buckets are filled in reverse parameter order (the order backward produces gradients); a post-accumulate hook counts a
+    bucket's parameters down and issues its all-reduce asynchronously the moment the last one lands, so the exchange of the
+    early buckets overlaps the rest of backward (NCCL runs it on its own stream);
+  * collectives are issued strictly in bucket order on every rank (a ready bucket waits for its predecessors), so ranks can
+    never disagree on the order of NCCL calls;
+  * `finish()` issues what is left (parameters that received no gradient this step), waits, and divides by the world size
+    (ReduceOp.AVG inside NCCL; an explicit scale on backends without it, e.g. gloo in the CPU tests).
+
+Nothing here touches the render data path: rays / frames shard with no collective (havatar_b200/shard.py)."""
+import torch
+import torch.distributed as dist
+
+
+def broadcast_parameters(modules, src=0, group=None):
+    """Same initial weights (and buffers) on every rank: broadcast rank `src`'s copies, flattened per dtype."""
+    if not isinstance(modules, (list, tuple)):
+        modules = [modules]
+    tensors = []
+    for m in modules:
+        tensors += [p.data for p in m.parameters()] + [b.data for b in m.buffers()]
+    by_type = {}
+    for t in tensors:
+        by_type.setdefault((t.dtype, t.device), []).append(t)
+    for ts in by_type.values():
+        flat = torch.cat([t.reshape(-1) for t in ts])
+        dist.broadcast(flat, src=src, group=group)
+        off = 0
+        for t in ts:
+            t.copy_(flat[off:off + t.numel()].view_as(t))
+            off += t.numel()
+
+
+class _Bucket:
+    __slots__ = ("flat", "params", "pending", "ready", "work")
+
+    def __init__(self, flat, params):
+        self.flat, self.params = flat, params
+        self.pending, self.ready, self.work = len(params), False, None
+
+
+class GradSync:
+    """Bucketed, backward-overlapped gradient all-reduce over `params` (an iterable of nn.Parameter).
+
+        sync = GradSync(model.parameters())
+        loss.backward()          # hooks issue the bucket all-reduces while backward is still running
+        sync.finish()            # every .grad now holds the mean over ranks
+        optimizer.step(); sync.zero_grad()
+
+    `.grad` of every parameter is a view into its bucket and must stay one: use `sync.zero_grad()` (one memset per bucket)
+    instead of `optimizer.zero_grad()` (whose default set_to_none=True would drop the views)."""
+
+    def __init__(self, params, group=None, bucket_bytes=64 << 20, average=True):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.average = average
+        params = [p for p in params if p.requires_grad]
+        seen, uniq = set(), []
+        for p in params:
+            if id(p) not in seen:
+                seen.add(id(p))
+                uniq.append(p)
+        self.params = uniq
+        backend = dist.get_backend(group) if self.world > 1 else None
+        self._avg_in_collective = bool(average and backend == "nccl")
+        self.buckets, self._bucket_of, self._hooks = [], {}, []
+        cur, cur_bytes, key = [], 0, None
+        for p in reversed(self.params):
+            k = (p.dtype, p.device)
+            nbytes = p.numel() * p.element_size()
+            if cur and (k != key or cur_bytes + nbytes > bucket_bytes):
+                self._close(cur)
+                cur, cur_bytes = [], 0
+            key = k
+            cur.append(p)
+            cur_bytes += nbytes
+        if cur:
+            self._close(cur)
+        self._next = 0
+        self.collectives = 0          # all-reduces issued since construction (bench / tests read it)
+        self.bytes_per_step = sum(b.flat.numel() * b.flat.element_size() for b in self.buckets)
+
+    def _close(self, params):
+        total = sum(-(-p.numel() // 32) * 32 for p in params)        # 128-byte aligned slots
+        flat = torch.zeros(total, dtype=params[0].dtype, device=params[0].device)
+        b = _Bucket(flat, params)
+        off = 0
+        for p in params:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += -(-p.numel() // 32) * 32
+            self._bucket_of[id(p)] = len(self.buckets)
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        self.buckets.append(b)
+
+    # ---- backward-time path
+    def _on_grad(self, p):
+        b = self.buckets[self._bucket_of[id(p)]]
+        b.pending -= 1
+        if b.pending == 0:
+            b.ready = True
+            self._issue_ready()
+
+    def _issue(self, b):
+        if self.world > 1:
+            op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
+            b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
+            self.collectives += 1
+        b.ready = True
+
+    def _issue_ready(self):
+        while self._next < len(self.buckets) and self.buckets[self._next].ready:
+            b = self.buckets[self._next]
+            if b.work is None:
+                self._issue(b)
+            self._next += 1
+
+    def finish(self):
+        """Issue the buckets backward did not complete, wait for all of them, apply the 1/world scale where the collective
+        did not, and re-arm for the next step."""
+        for b in self.buckets[self._next:]:
+            if b.work is None:
+                self._issue(b)
+        self._next = len(self.buckets)
+        for b in self.buckets:
+            if b.work is not None:
+                b.work.wait()
+                b.work = None
+            if self.world > 1 and self.average and not self._avg_in_collective:
+                b.flat.mul_(1.0 / self.world)
+        for b in self.buckets:
+            b.pending, b.ready = len(b.params), False
+            for p in b.params:       # an optimiser's zero_grad(set_to_none=True) or a grad replaced by autograd breaks the views
+                if p.grad is None or p.grad.data_ptr() < b.flat.data_ptr() or \
+                        p.grad.data_ptr() >= b.flat.data_ptr() + b.flat.numel() * b.flat.element_size():
+                    raise RuntimeError("GradSync: a parameter's .grad no longer aliases its bucket; use GradSync.zero_grad()")
+        self._next = 0
+
+    def zero_grad(self):
+        for b in self.buckets:
+            b.flat.zero_()
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

@@ -1,0 +1,244 @@
+"""The two training steps of the reference as callable objects on the B200 kernels, with the data-parallel gradient exchange of
+SURVEY.md section 8e (BASELINE.json configs[2] and configs[4]).
+
+  StageOneStep  = one iteration of train_avatar.py:112-158 (Trainer.forward(mode='train') on B patches of 64x64 rays, 64 + 16
+                  hierarchical samples, perturb + density noise; mse + mask BCE on both passes + latent regulariser + the
+                  skinning-volume smoothness term :124-129; Adam).  LPIPS is not available offline, so the
+                  patch term is the non-saturating GAN loss through a 64x64 `Discriminator` on the rendered patch (the
+                  "GAN discriminator" BASELINE.json names for this config) and the discriminator takes its own logistic step.
+  StageTwoStep  = one iteration of train_avatarHD.py:201-303: D step (render + generator without grad, logistic loss, Adam),
+                  R1 every d_reg_every (double backward through our upfirdn2d / fused_leaky_relu autograd), G step (render with
+                  grad -> low-res losses; generator -> non-saturating + L1; one backward; generator and render Adam steps),
+                  EMA accumulate (utils/styleUnet_util.py:51-56).  LPIPS omitted for the same reason.
+
+What runs underneath: the fused tcgen05 render forward + backward (hav_render_forward / hav_render_backward), our upfirdn2d /
+fused_bias_act kernels with their 1st / 2nd order autograd, and -- for the convolutions' gradients -- see styleunet_train.py.
+With torch.distributed initialised each rank steps on its own frames and `parallel.GradSync` all-reduces the gradients
+(bucketed, overlapped with backward); weights are broadcast from rank 0 at construction; optimiser steps and the EMA are
+replicated."""
+from types import SimpleNamespace as NS
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import parallel, styleunet, trainer
+
+
+def default_cfg(num_coarse=64, num_fine=16, perturb=True, noise_std=0.1, inp_size=128, out_size=512):
+    """The fields of config/singleview_512_base.yml the orchestrator and the steps read."""
+    mode = lambda p, s: NS(num_coarse=num_coarse, num_fine=num_fine, perturb=p, radiance_field_noise_std=s, chunksize=4096)
+    return NS(experiment=NS(latent_code_dim=32, cond_pose=True, cond_expr=False, model_mode=None, mask_weight=0.01),
+              models=NS(coarse=NS(XYZ_bounding=[[-1.5, 1.5], [-1.6, 1.4], [-1.6, 1.2]]),
+                        StyleUnet=NS(inp_size=inp_size, out_size=out_size)),
+              nerf=NS(train=mode(perturb, noise_std), validation=mode(False, 0.0)))
+
+
+def d_logistic_loss(real_pred, fake_pred):                      # utils/styleUnet_util.py:65-69
+    return F.softplus(-real_pred).mean() + F.softplus(fake_pred).mean()
+
+
+def g_nonsaturating_loss(fake_pred):                            # utils/styleUnet_util.py:82-85
+    return F.softplus(-fake_pred).mean()
+
+
+def d_r1_loss(real_pred, real_img):                             # utils/styleUnet_util.py:72-79
+    grad_real, = torch.autograd.grad(outputs=real_pred.sum(), inputs=real_img, create_graph=True)
+    return grad_real.pow(2).reshape(grad_real.shape[0], -1).sum(1).mean()
+
+
+def volume_smoothness(w):                                       # train_avatar.py:124-129
+    core = w[1:-1, 1:-1, 1:-1]
+    nb = [w[:-2, 1:-1, 1:-1], w[2:, 1:-1, 1:-1], w[1:-1, 2:, 1:-1], w[1:-1, :-2, 1:-1], w[1:-1, 1:-1, 2:], w[1:-1, 1:-1, :-2]]
+    return torch.mean(sum(torch.abs(core - v) for v in nb) / 6.0)
+
+
+def _distributed():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class _Group:
+    """Parameters + Adam + (when distributed) the bucketed gradient all-reduce of one optimiser."""
+
+    def __init__(self, modules, lr, betas=(0.9, 0.999)):
+        self.params = [p for m in modules for p in m.parameters()]
+        self.sync = parallel.GradSync(self.params) if _distributed() else None
+        self.opt = torch.optim.Adam(self.params, lr=lr, betas=betas)
+
+    def step(self):
+        if self.sync is not None:
+            self.sync.finish()
+        self.opt.step()
+
+    def zero_grad(self):
+        if self.sync is not None:
+            self.sync.zero_grad()
+        else:
+            self.opt.zero_grad(set_to_none=True)
+
+    def requires_grad(self, flag):
+        for p in self.params:
+            p.requires_grad_(flag)
+
+
+class StageOneStep:
+    def __init__(self, n_frames=4, device="cuda", cfg=None, precision="fp16", patch=64, lr=5e-4, with_discriminator=True, seed=0):
+        torch.manual_seed(seed)
+        self.cfg = cfg or default_cfg()
+        self.device = torch.device(device)
+        self.net = trainer.Trainer(self.cfg, n_frames, precision=precision).to(self.device)
+        self.disc = styleunet.Discriminator(patch, img_channel=3).to(self.device) if with_discriminator else None
+        mods = [self.net] + ([self.disc] if self.disc is not None else [])
+        if _distributed():
+            parallel.broadcast_parameters(mods)
+        self.g = _Group([self.net], lr)                                             # train_avatar.py:68-71
+        self.d = _Group([self.disc], 2e-3 * 16 / 17, betas=(0.0, 0.99 ** (16 / 17))) if self.disc is not None else None
+        self.patch, self.it = patch, 0
+
+    def __call__(self, batch):
+        """batch: dict with ray_batch [B,R,8], background_prior [B,R,3], target [B,R,3], mask [B,R,1], fidx [B], inv_head_T
+        [B,4,3], {front,left,right}_render_cond [B,7,256,256] (device tensors).  Returns {'loss', 'd_loss'} (detached)."""
+        cfg, P = self.cfg, self.patch
+        self.it += 1
+        if self.d is not None:
+            self.d.requires_grad(False)
+        out = self.net(mode="train", fidx=batch["fidx"], render_full_img=False, ray_batch=batch["ray_batch"],
+                       background_prior=batch["background_prior"], inv_head_T=batch["inv_head_T"],
+                       front_render_cond=batch["front_render_cond"], left_render_cond=batch["left_render_cond"],
+                       right_render_cond=batch["right_render_cond"], randoms=batch.get("randoms"))
+        rgb_c, _, acc_c, _, rgb_f, _, acc_f, lat = out
+        target, mask, mw = batch["target"], batch["mask"], cfg.experiment.mask_weight
+        loss = F.mse_loss(rgb_c[..., :3], target) + mw * F.binary_cross_entropy(acc_c.clip(1e-3, 1.0 - 1e-3), mask)   # :131-132
+        if rgb_f is not None:                                                                                       # :134-136
+            loss = loss + F.mse_loss(rgb_f[..., :3], target) + mw * F.binary_cross_entropy(acc_f.clip(1e-3, 1.0 - 1e-3), mask)
+        # :124-129 re-evaluates the VolumeDecoder for this term; the forward's own evaluation is the same tensor, reuse it
+        skin = self.net.headpose_skin_net
+        vol = skin.last_volume if skin.last_volume is not None and not skin.fix_canoW else skin.canonical_Wvolume()
+        sw = volume_smoothness(vol[0, 1])
+        skin.last_volume = None
+        loss = loss + lat + 1e-4 * sw                                                                               # :146
+        fake = None
+        if self.disc is not None:
+            rgb = rgb_f if rgb_f is not None else rgb_c
+            B = rgb.shape[0]
+            fake = rgb[..., :3].reshape(B, P, P, 3).permute(0, 3, 1, 2).contiguous()
+            loss = loss + 0.05 * g_nonsaturating_loss(self.disc(fake))       # in the slot of the 0.05-weighted patch term (:144)
+        loss.backward()                                                                                             # :149
+        self.g.step()                                                                                               # :151
+        self.g.zero_grad()
+        lr_new = max(5e-4 * (0.1 ** (self.it / 250000.0)), 5e-5)                                                    # :154-158
+        for grp in self.g.opt.param_groups:
+            grp["lr"] = lr_new
+        d_loss = None
+        if self.disc is not None:
+            self.d.requires_grad(True)
+            real = batch["target"].reshape(-1, P, P, 3).permute(0, 3, 1, 2).contiguous()
+            d_loss = d_logistic_loss(self.disc(real), self.disc(fake.detach()))
+            d_loss.backward()
+            self.d.step()
+            self.d.zero_grad()
+        return {"loss": loss.detach(), "d_loss": None if d_loss is None else d_loss.detach()}
+
+
+class StageTwoStep:
+    def __init__(self, n_frames=8, device="cuda", cfg=None, precision="fp16", render_size=128, gen_size=512, d_reg_every=16,
+                 r1=10.0, latent=64, n_mlp=4, seed=0):
+        torch.manual_seed(seed)
+        self.cfg = cfg or default_cfg(inp_size=render_size, out_size=gen_size)
+        self.device = torch.device(device)
+        self.net = trainer.Trainer(self.cfg, n_frames, precision=precision).to(self.device)                 # train_avatarHD.py:109
+        mk = lambda: styleunet.SWGAN_unet(inp_size=render_size, inp_ch=64, out_ch=3, out_size=gen_size, style_dim=latent,
+                                          n_mlp=n_mlp).to(self.device)                                          # :110-111
+        self.generator, self.g_ema = mk(), mk()
+        self.g_ema.load_state_dict(self.generator.state_dict())
+        self.g_ema.requires_grad_(False)
+        self.disc = styleunet.Discriminator(gen_size, img_channel=3).to(self.device)                         # :112
+        if _distributed():
+            parallel.broadcast_parameters([self.net, self.generator, self.g_ema, self.disc])
+        g_ratio, d_ratio = 4 / 5, d_reg_every / (d_reg_every + 1)                                            # :117-122
+        self.nerf = _Group([self.net], 5e-4)
+        self.g = _Group([self.generator], 2e-3 * g_ratio, betas=(0.0, 0.99 ** g_ratio))
+        self.d = _Group([self.disc], 2e-3 * d_ratio, betas=(0.0, 0.99 ** d_ratio))
+        self.render_size, self.gen_size, self.latent = render_size, gen_size, latent
+        self.d_reg_every, self.r1, self.it = d_reg_every, r1, 0
+        self.accum = 0.5 ** (32 / (10 * 1000))                                                               # :162
+
+    def _noise(self, b):                                             # mixing_noise with mixing = 0 (:170-175)
+        return [torch.randn(b, self.latent, device=self.device)]
+
+    def __call__(self, batch):
+        """batch: the StageOneStep keys with full low-res frames (R = render_size^2) plus gt_hr_img [B,3,G,G] and gt_lr_mask
+        [B,1,render,render]."""
+        self.it += 1
+        i, rs, gs = self.it, self.render_size, self.gen_size
+        gt_hr = batch["gt_hr_img"]
+        inp = dict(mode="train", fidx=batch["fidx"], render_full_img=True, ray_batch=batch["ray_batch"],
+                   background_prior=batch["background_prior"], inv_head_T=batch["inv_head_T"],
+                   front_render_cond=batch["front_render_cond"], left_render_cond=batch["left_render_cond"],
+                   right_render_cond=batch["right_render_cond"])
+        B = gt_hr.shape[0]
+        gt_lr = F.interpolate(F.interpolate(gt_hr, size=(rs, rs), mode="bilinear", align_corners=True), size=(gs, gs),
+                              mode="bilinear", align_corners=True)                                              # :202-204
+        gan_w = min(1e-3 * 1.1 ** (i // 500), 0.1)                                                              # :205-206
+        # ---- D step (:211-231)
+        self.nerf.requires_grad(False), self.g.requires_grad(False), self.d.requires_grad(True)
+        with torch.no_grad():
+            render, _, _ = self.net(**inp)
+            fake = self.generator(self._noise(B), render[:, 3:].contiguous())
+        d_loss = d_logistic_loss(self.disc(gt_hr), self.disc(fake)) * gan_w
+        self.d.zero_grad()
+        d_loss.backward()
+        self.d.step()
+        r1_loss = None
+        if i % self.d_reg_every == 0:                                                                           # :233-240
+            real = gt_hr.detach().requires_grad_(True)
+            pred = self.disc(real)
+            r1_loss = d_r1_loss(pred, real) * gan_w
+            self.d.zero_grad()
+            (self.r1 / 2 * r1_loss * self.d_reg_every + 0 * pred[0]).sum().backward()
+            self.d.step()
+        # ---- G step (:243-280)
+        self.nerf.requires_grad(True), self.g.requires_grad(True), self.d.requires_grad(False)
+        self.nerf.zero_grad(), self.g.zero_grad()
+        render, mask, lat = self.net(**inp)
+        lr_img = F.interpolate(render[:, :3], size=(gs, gs), mode="bilinear", align_corners=True)
+        g_loss = F.mse_loss(lr_img, gt_lr) + lat
+        g_loss = g_loss + self.cfg.experiment.mask_weight * F.binary_cross_entropy(mask.clip(1e-3, 1.0 - 1e-3), batch["gt_lr_mask"])
+        fake = self.generator(self._noise(B), render[:, 3:].contiguous())
+        g_loss = g_loss + g_nonsaturating_loss(self.disc(fake)) * gan_w + F.l1_loss(fake, gt_hr)
+        g_loss.backward()
+        self.g.step()
+        self.nerf.step()
+        with torch.no_grad():                                                                                   # :303
+            pe, pg = list(self.g_ema.parameters()), list(self.generator.parameters())
+            torch._foreach_mul_(pe, self.accum)
+            torch._foreach_add_(pe, pg, alpha=1 - self.accum)
+        return {"d_loss": d_loss.detach(), "g_loss": g_loss.detach(), "r1": None if r1_loss is None else r1_loss.detach()}
+
+
+def synthetic_batch(stage, batch, device, seed=0, patch=64, render_size=128, gen_size=512, frame_offset=0):
+    """Seeded synthetic inputs in the dataloader's layouts (dataloader/dataloader.py:146-229): stage 1 =
+    `batch` frames x one patch x patch window of rays of a 512x512 camera; stage 2 = `batch` full render_size^2 low-res frames +
+    a gen_size^2 ground-truth image.  `frame_offset` = first global frame index of this rank (data-parallel sharding)."""
+    import numpy as np
+
+    from . import synth
+
+    dev = torch.device(device)
+    g = torch.Generator().manual_seed(1000 + seed)
+    if stage == 1:
+        sc = synth.scene(batch=batch, height=512, width=512, crop=(256 - patch // 2, 256 - patch // 2, patch, patch), seed=seed)
+    else:
+        sc = synth.scene(batch=batch, height=render_size, width=render_size, seed=seed)
+    R = sc["ray_batch"].shape[1]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    cond = lambda: torch.rand(batch, 7, 256, 256, generator=g).to(dev)
+    out = {"ray_batch": t(sc["ray_batch"]), "background_prior": t(sc["background_prior"]), "inv_head_T": t(sc["inv_head_T"]),
+           "front_render_cond": cond(), "left_render_cond": cond(), "right_render_cond": cond(),
+           "fidx": (torch.arange(batch) + frame_offset).to(dev),
+           "target": torch.rand(batch, R, 3, generator=g).to(dev),
+           "mask": (torch.rand(batch, R, 1, generator=g) > 0.4).float().to(dev)}
+    if stage == 2:
+        out["gt_hr_img"] = (torch.rand(batch, 3, gen_size, gen_size, generator=g) * 2 - 1).to(dev)
+        out["gt_lr_mask"] = out["mask"].reshape(batch, render_size, render_size, 1).permute(0, 3, 1, 2).contiguous()
+    return out

@@ -94,7 +94,7 @@ class SkinningField(nn.Module):
         self.register_buffer("identity_trans", torch.eye(4, dtype=torch.float32)[:, :-1])
         self.fix_canoW = False
         self.canonical_W = None
-        self._key, self._vol = None, None
+        self._key, self._vol, self.last_volume = None, None, None
 
     def fix_canonical_W(self):
         """Skinning_Field.py:57-62: freeze the volume and pin the head region to the head bone."""
@@ -110,7 +110,8 @@ class SkinningField(nn.Module):
         if self.fix_canoW:
             return self.canonical_W
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.canonical_Wvolume.parameters()):
-            return self.canonical_Wvolume()         # training: part of the graph (Skinning_Field.py:79)
+            self.last_volume = self.canonical_Wvolume()         # training: part of the graph (Skinning_Field.py:79)
+            return self.last_volume
         key = tuple((p.data_ptr(), p._version) for p in self.canonical_Wvolume.parameters())
         if key != self._key:
             with torch.no_grad():
