@@ -59,6 +59,15 @@ class ConvArgs(C.Structure):
     ]
 
 
+class ConvWgradArgs(C.Structure):
+    """hav_conv_wgrad_args (include/havatar_b200.h)."""
+    _fields_ = [
+        ("struct_bytes", C.c_uint32), ("batch", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("in_h", C.c_int32),
+        ("in_w", C.c_int32), ("ksize", C.c_int32), ("up", C.c_int32), ("down", C.c_int32), ("accumulate", C.c_int32),
+        ("wscale", C.c_float), ("g", _fp), ("x", _fp), ("in_scale", _fp), ("out_scale", _fp), ("dw", _fp),
+    ]
+
+
 # symbol -> (restype, argtypes); tests check that every one of these is exported
 SIGNATURES = {
     "hav_abi_version": (C.c_int, []),
@@ -75,6 +84,8 @@ SIGNATURES = {
     "hav_conv_pack_weights": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, _fp]),
     "hav_modconv_demod": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _fp]),
     "hav_conv2d_forward": (C.c_int, [C.POINTER(ConvArgs), _fp]),
+    "hav_conv2d_wgrad": (C.c_int, [C.POINTER(ConvWgradArgs), _fp]),
+    "hav_rowscale_dot": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int64, _fp]),
     "hav_get_rays": (C.c_int, [_fp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
                                C.c_float, _fp]),
 }

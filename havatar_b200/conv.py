@@ -1,8 +1,12 @@
-"""Host side of the tensor-core convolution (C ABI: hav_conv2d_forward, hav_conv_pack_weights, hav_modconv_demod).
+"""Host side of the tensor-core convolution (C ABI: hav_conv2d_forward, hav_conv_pack_weights, hav_modconv_demod,
+hav_conv2d_wgrad, hav_rowscale_dot).
 
 conv2d() is ModulatedConv2d.forward / EqualConv2d.forward of the reference (model/styleUnet.py:222-297, :108-118)
-with the per-layer elementwise work of StyledConv / ToRGB / ConvLayer fused into the same launch.  Forward only (inference);
-torch is used for device memory and streams.  No CPU fallback."""
+with the per-layer elementwise work of StyledConv / ToRGB / ConvLayer fused into the same launch (the inference call).
+conv2d_autograd() is the differentiable primitive of the training steps: the same forward kernel, and a backward made of the
+forward kernel again (data gradient), the tcgen05 weight-gradient kernel and one row kernel for the modulation gradients --
+what the reference gets from cuDNN through model/op/conv2d_gradfix.py.  torch is used for device memory, streams and the
+autograd graph.  No CPU fallback."""
 import ctypes as C
 
 import torch
@@ -23,9 +27,10 @@ def _check(t, name):
     return t.detach().contiguous()
 
 
-def pack_weights(weight, scale=1.0, up=1, transpose_io=False, precision="fp16"):
+def pack_weights(weight, scale=1.0, up=1, transpose_io=False, precision="fp16", flip=False):
     """weight [Cout,Cin,k,k] (or [Cin,Cout,k,k] with transpose_io) -> PackedConvWeight holding scale * weight, laid out for
-    conv2d(..., up=up) (the transposed convolution uses 64-channel tiles and four phase accumulators)."""
+    conv2d(..., up=up) (the transposed convolution uses 64-channel tiles and four phase accumulators).  flip mirrors the taps
+    (with transpose_io: the weight of a stride-1 layer's data-gradient convolution)."""
     L = _lib.lib()
     w = _check(weight, "weight")
     if w.dim() != 4 or w.shape[2] != w.shape[3]:
@@ -39,7 +44,7 @@ def pack_weights(weight, scale=1.0, up=1, transpose_io=False, precision="fp16"):
     with torch.cuda.device(w.device):
         st = torch.cuda.current_stream(w.device).cuda_stream
         _lib.check(L.hav_conv_pack_weights(C.c_void_p(buf.data_ptr()), C.c_void_p(w.data_ptr()), cout, cin, k, float(scale),
-                                           int(up), int(bool(transpose_io)), _lib.PRECISIONS[precision], C.c_void_p(st)),
+                                           int(up), int(bool(transpose_io)) | (2 if flip else 0), _lib.PRECISIONS[precision], C.c_void_p(st)),
                    "hav_conv_pack_weights")
     return PackedConvWeight(buf, cout, cin, k, precision, int(up))
 
@@ -165,3 +170,116 @@ def upfirdn2d_cl(x, kernel, up=1, down=1, pad=(0, 0), noise=None, noise_weight=0
                                       C.c_void_p(bs.data_ptr()) if bs is not None else None, int(bool(act)), C.c_void_p(st)),
                    "hav_upfirdn2d_cl")
     return out
+
+
+def conv_wgrad(g, x, ksize, in_scale=None, out_scale=None, wscale=1.0, up=1, down=1, out=None):
+    """dW [Cout,Cin,k,k] of  y = out_scale * conv(in_scale * x, wscale * W)  given g = dL/dy (C ABI: hav_conv2d_wgrad).
+    `out` accumulates into an existing gradient tensor."""
+    L = _lib.lib()
+    g, x = _check(g, "g"), _check(x, "x")
+    B, cin, H, W = [int(v) for v in x.shape]
+    cout = int(g.shape[1])
+    if up == 2:
+        Ho, Wo = 2 * H + 1, 2 * W + 1
+    elif down == 2:
+        Ho, Wo = (H - ksize) // 2 + 1, (W - ksize) // 2 + 1
+    else:
+        Ho, Wo = H, W
+    if tuple(g.shape) != (B, cout, Ho, Wo):
+        raise _lib.HavError("g must be %s, got %s" % ((B, cout, Ho, Wo), tuple(g.shape)))
+    a = _lib.ConvWgradArgs()
+    a.struct_bytes = C.sizeof(_lib.ConvWgradArgs)
+    a.batch, a.cin, a.cout, a.in_h, a.in_w = B, cin, cout, H, W
+    a.ksize, a.up, a.down, a.accumulate, a.wscale = int(ksize), int(up), int(down), int(out is not None), float(wscale)
+    keep = [g, x]
+    a.g, a.x = C.c_void_p(g.data_ptr()), C.c_void_p(x.data_ptr())
+    for name, t, shape in (("in_scale", in_scale, (B, cin)), ("out_scale", out_scale, (B, cout))):
+        if t is not None:
+            t = _check(t, name)
+            if tuple(t.shape) != shape:
+                raise _lib.HavError("%s must be %s" % (name, shape))
+            keep.append(t)
+            setattr(a, name, C.c_void_p(t.data_ptr()))
+    if out is None:
+        out = torch.empty((cout, cin, ksize, ksize), dtype=torch.float32, device=x.device)
+    elif not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == cout * cin * ksize * ksize):
+        raise _lib.HavError("out must be a contiguous float32 CUDA tensor with Cout*Cin*k*k elements")
+    a.dw = C.c_void_p(out.data_ptr())
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(L.hav_conv2d_wgrad(C.byref(a), C.c_void_p(st)), "hav_conv2d_wgrad")
+    del keep
+    return out
+
+
+def rowscale_dot(a, x=None, scale=None, want_out=True, want_dot=True):
+    """a, x [B,C,H,W]; scale [B,C].  Returns (a * scale[:, :, None, None] or None, (a * x).sum((2, 3)) or None) in one pass
+    (C ABI: hav_rowscale_dot)."""
+    L = _lib.lib()
+    a = _check(a, "a")
+    B, Cc = int(a.shape[0]), int(a.shape[1])
+    n = a.numel() // max(B * Cc, 1)
+    x = None if x is None else _check(x, "x")
+    scale = None if scale is None else _check(scale, "scale")
+    if x is not None and x.shape != a.shape:
+        raise _lib.HavError("x must have the shape of a")
+    out = torch.empty_like(a) if want_out else None
+    dot = torch.empty((B, Cc), dtype=torch.float32, device=a.device) if want_dot else None
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    with torch.cuda.device(a.device):
+        st = torch.cuda.current_stream(a.device).cuda_stream
+        _lib.check(L.hav_rowscale_dot(p(out), p(dot), p(a), p(x), p(scale), B * Cc, n, C.c_void_p(st)), "hav_rowscale_dot")
+    return out, dot
+
+
+class _ConvFunction(torch.autograd.Function):
+    """y = out_scale[b,co] * conv(in_scale[b,ci] * x, wscale * weight): ModulatedConv2d in its shared-weight form
+    (model/styleUnet.py:225-251) and, with both scales None, EqualConv2d (:108-118).  Forward: fp16 operands; backward: bf16
+    operands (gradients have no fixed range), fp32 accumulation everywhere."""
+
+    @staticmethod
+    def forward(ctx, x, weight, in_scale, out_scale, wscale, up, down):
+        k = int(weight.shape[-1])
+        packed = pack_weights(weight, wscale, up=up, precision="fp16")
+        y = conv2d(x, packed, in_scale=in_scale, out_scale=out_scale, up=up, down=down)
+        ctx.save_for_backward(x, weight, in_scale, out_scale, y if out_scale is not None else None)
+        ctx.cfg = (float(wscale), int(up), int(down), k)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, weight, in_scale, out_scale, y = ctx.saved_tensors
+        wscale, up, down, k = ctx.cfg
+        g = g.contiguous()
+        dx = dw = ds = dd = None
+        if ctx.needs_input_grad[0] or (in_scale is not None and ctx.needs_input_grad[2]):
+            # data gradient = the forward kernel on g with the transposed weight image; stride 2 <-> transposed stride 2
+            if up == 2:
+                wp = pack_weights(weight, wscale, up=1, transpose_io=True, precision="bf16")
+                dxs = conv2d(g, wp, in_scale=out_scale, down=2)
+            elif down == 2:
+                wp = pack_weights(weight, wscale, up=2, transpose_io=True, precision="bf16")
+                dxs = conv2d(g, wp, in_scale=out_scale, up=2)
+                H, W = int(x.shape[2]), int(x.shape[3])
+                if dxs.shape[2] != H or dxs.shape[3] != W:       # even input: its last row / column never reached an output
+                    dxs = torch.nn.functional.pad(dxs, (0, W - dxs.shape[3], 0, H - dxs.shape[2]))
+            else:
+                wp = pack_weights(weight, wscale, up=1, transpose_io=True, flip=True, precision="bf16")
+                dxs = conv2d(g, wp, in_scale=out_scale)
+            if in_scale is not None:
+                dx, ds = rowscale_dot(dxs, x, in_scale, want_out=ctx.needs_input_grad[0], want_dot=ctx.needs_input_grad[2])
+            else:
+                dx = dxs
+        if ctx.needs_input_grad[1]:
+            dw = conv_wgrad(g, x, k, in_scale=in_scale, out_scale=out_scale, wscale=wscale, up=up, down=down)
+        if out_scale is not None and ctx.needs_input_grad[3]:
+            _, gy = rowscale_dot(g, y, None, want_out=False)
+            dd = gy / out_scale
+        return dx, dw, ds, dd, None, None, None
+
+
+def conv2d_autograd(x, weight, in_scale=None, out_scale=None, wscale=1.0, up=1, down=1):
+    """Differentiable  out_scale * conv(in_scale * x, wscale * weight)  on the tcgen05 kernels (first-order gradients w.r.t. x,
+    weight [Cout,Cin,k,k], in_scale [B,Cin] and out_scale [B,Cout])."""
+    return _ConvFunction.apply(x, weight, in_scale, out_scale, float(wscale), int(up), int(down))

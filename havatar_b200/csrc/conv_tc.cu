@@ -342,7 +342,8 @@ extern "C" int hav_conv_pack_weights(void *wpack, const float *w, int cout, int 
   if (wpack == nullptr || w == nullptr) return HAV_E_NULL;
   if (cout < 1 || cin < 1 || (ksize != 1 && ksize != 3) || (up != 1 && up != 2)) return HAV_E_SHAPE;
   if (precision != HAV_PREC_FP16 && precision != HAV_PREC_BF16) return HAV_E_VALUE;
-  const int flip = 0;
+  const int flip = (transpose_io >> 1) & 1;
+  transpose_io &= 1;
   const int n_tile = conv_n_tile(cout, up), n_tiles = (cout + n_tile - 1) / n_tile, kblocks = (cin + conv::kCinBlk - 1) / conv::kCinBlk;
   if (precision == HAV_PREC_BF16)
     conv::pack_conv_weights_kernel<true><<<296, 256, 0, (cudaStream_t)stream>>>(w, (uint16_t *)wpack, cout, cin, ksize, n_tile, n_tiles,

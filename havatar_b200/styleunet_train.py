@@ -7,14 +7,37 @@ below instead: the reference's layer formulas (model/styleUnet.py, cited per fun
 autograd.  What runs underneath:
   * upfirdn2d (Blur / Upsample / Downsample / Haar) and fused_leaky_relu: OUR sm_100a kernels with their first- and
     second-order autograd (havatar_b200/op, the `model/op` replacements),
-  * the convolutions: torch.nn.functional.conv2d / conv_transpose2d (cuDNN) in ModulatedConv2d's shared-weight formulation
-    (the reference's own non-fused branch, styleUnet.py:225-251) -- a library call: the tcgen05 convolution kernel has no
-    backward yet (open rows).
+  * the convolutions: conv.conv2d_autograd -- the tcgen05 forward kernel, and a backward made of the same kernel on the
+    transposed weight image (data gradient), the tcgen05 weight-gradient kernel (hav_conv2d_wgrad) and one row kernel for the
+    modulation / demodulation gradients, in ModulatedConv2d's shared-weight formulation (the reference's own non-fused branch,
+    styleUnet.py:225-251).
+    The one exception is a pass that needs SECOND-order gradients through the convolutions (the R1 penalty every 16th
+    discriminator step, utils/styleUnet_util.py:72-79): inside `library_convs()` the same formulas run on
+    torch.nn.functional.conv2d / conv_transpose2d (cuDNN), whose double backward autograd already has.
 """
+import contextlib
+
 import torch
 import torch.nn.functional as F
 
+from . import conv as hconv
 from .op import fused_leaky_relu
+
+_NATIVE = [True]
+
+
+@contextlib.contextmanager
+def library_convs():
+    """Run the convolutions of the enclosed forward on torch's own ops (needed only where the graph is differentiated twice)."""
+    prev, _NATIVE[0] = _NATIVE[0], False
+    try:
+        yield
+    finally:
+        _NATIVE[0] = prev
+
+
+def _native(x):
+    return _NATIVE[0] and x.is_cuda and x.dtype == torch.float32
 
 
 def equal_linear(m, x):
@@ -37,7 +60,13 @@ def conv_layer(m, x):
         x = mods[0](x)
         mods = mods[1:]
     conv = mods[0]
-    out = F.conv2d(x, conv.weight * conv.scale, bias=conv.bias, stride=conv.stride, padding=conv.padding)
+    k = conv.weight.shape[-1]
+    if _native(x) and k in (1, 3) and ((conv.stride == 1 and conv.padding == k // 2) or (conv.stride == 2 and conv.padding == 0 and k == 3)):
+        out = hconv.conv2d_autograd(x, conv.weight, None, None, conv.scale, down=conv.stride)
+        if conv.bias is not None:
+            out = out + conv.bias[None, :, None, None]
+    else:
+        out = F.conv2d(x, conv.weight * conv.scale, bias=conv.bias, stride=conv.stride, padding=conv.padding)
     if m.activate:
         out = fused_leaky_relu(out, mods[1].bias)
     return out
@@ -46,6 +75,14 @@ def conv_layer(m, x):
 def mod_conv(m, x, style):
     """ModulatedConv2d.forward (styleUnet.py:222-297), shared-weight form:  demod * conv(x * s, scale * W)."""
     s = equal_linear(m.modulation, style)                                  # [B,Cin]
+    k = m.weight.shape[-1]
+    if _native(x) and (k == 3 or (k == 1 and not m.upsample)) and m.padding == k // 2:
+        w0 = m.weight[0]
+        d = None
+        if m.demodulate:                                                   # :256-258
+            d = torch.rsqrt((s * s) @ (w0 * w0).sum(dim=(2, 3)).t() * (m.scale * m.scale) + m.eps)
+        out = hconv.conv2d_autograd(x, w0, s, d, m.scale, up=2 if m.upsample else 1)
+        return m.blur(out) if m.upsample else out                          # :271-277
     w = m.weight[0] * m.scale                                              # [Cout,Cin,k,k]
     x = x * s[:, :, None, None]
     if m.upsample:

@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
-from . import parallel, styleunet, trainer
+from . import parallel, styleunet, styleunet_train, trainer
 
 
 def default_cfg(num_coarse=64, num_fine=16, perturb=True, noise_std=0.1, inp_size=128, out_size=512):
@@ -192,7 +192,8 @@ class StageTwoStep:
         r1_loss = None
         if i % self.d_reg_every == 0:                                                                           # :233-240
             real = gt_hr.detach().requires_grad_(True)
-            pred = self.disc(real)
+            with styleunet_train.library_convs():       # second-order gradients through the convolutions
+                pred = self.disc(real)
             r1_loss = d_r1_loss(pred, real) * gan_w
             self.d.zero_grad()
             (self.r1 / 2 * r1_loss * self.d_reg_every + 0 * pred[0]).sum().backward()

@@ -19,6 +19,7 @@
  *   hav_conv2d_forward   <- model/styleUnet.py:222-297 (ModulatedConv2d.forward) and :108-118 (EqualConv2d.forward): the
  *                            reference calls cuDNN grouped conv2d / conv_transpose2d through model/op/conv2d_gradfix.py:22-75
  *   hav_pack_planes      <- model/nerf_model.py:85 (plane stacking; layout change for the bf16 path)
+ *   hav_conv2d_wgrad     <- autograd's convolution_backward under the same modules (model/op/conv2d_gradfix.py:94-227)
  * INTEGRATION.md shows the reference-side binding for each.
  */
 #ifndef HAVATAR_B200_H_
@@ -185,8 +186,12 @@ int hav_get_rays(float *ray_batch, int height, int width, const float intr[4], c
  *   down = 2: conv2d stride 2, padding 0 (:281-283);  otherwise stride 1, padding ksize/2 (:289-291).
  *   x [B,Cin,H,W], out [B,Cout,Ho,Wo] float32 NCHW; operands are rounded to 16 bit, accumulation is fp32 (TMEM).
  * Weights are packed once per weight update with hav_conv_pack_weights for the SAME `up` they will be used with
- * (w is [Cout,Cin,k,k], or [Cin,Cout,k,k] -- conv_transpose2d's own layout -- when transpose_io != 0).
+ * (w is [Cout,Cin,k,k], or [Cin,Cout,k,k] -- conv_transpose2d's own layout -- when bit 0 of transpose_io is set; bit 1
+ * (HAV_CONV_PACK_FLIP) mirrors the taps, w[.., k-1-kh, k-1-kw]: with both bits set the packed image is the weight of the
+ * DATA-GRADIENT convolution of a stride-1 layer, so hav_conv2d_forward also serves as that layer's backward-data kernel).
  */
+#define HAV_CONV_PACK_TRANSPOSE_IO 1
+#define HAV_CONV_PACK_FLIP 2
 #define HAV_LAYOUT_NCHW_F32 0 /* [B,C,H,W] float32 */
 #define HAV_LAYOUT_NHWC_F16 1 /* [B,H,W,C] IEEE half, C % 8 == 0 (fp16 precision only) */
 
@@ -216,6 +221,35 @@ int hav_conv_pack_weights(void *wpack, const float *w, int cout, int cin, int ks
 int hav_modconv_demod(float *demod, const float *w, const float *style, int batch, int cout, int cin, int ksize, float scale,
                       float eps, void *stream);
 int hav_conv2d_forward(const hav_conv_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward of hav_conv2d_forward (replaces cuDNN's convolution_backward under model/op/conv2d_gradfix.py:94-227 for the
+ * training steps train_avatar.py:149 / train_avatarHD.py:229,276).  For  y = out_scale * conv(in_scale * x, wscale * w):
+ *   data gradient    = hav_conv2d_forward on g with the transposed (and, for stride 1, flipped) weight image, in_scale :=
+ *                      out_scale, and the roles of up / down exchanged (the gradient of a stride-2 convolution is a
+ *                      transposed one and vice versa);
+ *   weight gradient  = hav_conv2d_wgrad:  dw[co,ci,kh,kw] (+)= wscale * sum_{b,p} (out_scale[b,co] g[b,co,p]) *
+ *                      (in_scale[b,ci] x[b,ci,p + (kh,kw) - pad]),  tcgen05 bf16 operands, fp32 accumulate, split over the
+ *                      positions with fp32 reductions into dw ([Cout,Cin,k,k] float32; zeroed first unless accumulate != 0);
+ *   scale gradients  = hav_rowscale_dot (rows = (sample, channel) images): out = a * scale[row], dot[row] = sum a * x.
+ * x [B,Cin,H,W] is the forward INPUT, g [B,Cout,Ho,Wo] the gradient of the forward output (sizes as in hav_conv2d_forward).
+ */
+typedef struct hav_conv_wgrad_args {
+  uint32_t struct_bytes; /* = sizeof(hav_conv_wgrad_args) */
+  int32_t batch, cin, cout, in_h, in_w;
+  int32_t ksize, up, down;
+  int32_t accumulate;
+  float wscale;
+  const float *g;
+  const float *x;
+  const float *in_scale;  /* [B,Cin] or NULL */
+  const float *out_scale; /* [B,Cout] or NULL */
+  float *dw;
+} hav_conv_wgrad_args;
+
+int hav_conv2d_wgrad(const hav_conv_wgrad_args *args, void *stream);
+int hav_rowscale_dot(float *out, float *dot, const float *a, const float *x, const float *scale, int64_t rows, int64_t n,
+                     void *stream);
 
 #ifdef __cplusplus
 }
