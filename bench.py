@@ -275,33 +275,39 @@ def run_ours(args):
         from havatar_b200 import train_step
 
         torch.cuda.empty_cache()
+        modes = ("eager", "graph") if args.train_mode == "both" else (args.train_mode,)
         for name, mk, mkb, frames in (
-                ("stage_one_b4_patch64", lambda: train_step.StageOneStep(n_frames=4 * world, device=dev),
+                ("stage_one_b4_patch64", lambda c: train_step.StageOneStep(n_frames=4 * world, device=dev, capturable=c),
                  lambda: train_step.synthetic_batch(1, 4, dev, seed=rank, patch=64, frame_offset=4 * rank), 4),
-                ("stage_two_b1_128_to_512", lambda: train_step.StageTwoStep(n_frames=world, device=dev),
+                ("stage_two_b1_128_to_512", lambda c: train_step.StageTwoStep(n_frames=world, device=dev, capturable=c),
                  lambda: train_step.synthetic_batch(2, 1, dev, seed=rank, render_size=128, gen_size=512, frame_offset=rank), 1)):
-            st, batch = mk(), mkb()
-            for _ in range(3):
-                st(batch)
-            barrier()
-            n_t = max(3, min(args.steps, 10))
-            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a_.record()
-            for _ in range(n_t):
-                res_t = st(batch)
-            b_.record()
-            barrier()
-            ms = torch.tensor([a_.elapsed_time(b_) / n_t], dtype=torch.float64, device=dev)
-            if dist is not None:
-                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            ok = all(bool(torch.isfinite(v)) for v in res_t.values() if v is not None)
-            syncs = [g_.sync for g_ in (getattr(st, "g", None), getattr(st, "d", None), getattr(st, "nerf", None)) if g_ is not None and g_.sync is not None]
-            train[name] = {"ms_per_step": float(ms), "frames_per_sec": world * frames * 1e3 / float(ms), "steps": n_t, "finite": ok,
-                           "frames_per_gpu": frames,
-                           "allreduce_bytes_per_step": sum(s_.bytes_per_step for s_ in syncs),
-                           "allreduce_buckets": sum(len(s_.buckets) for s_ in syncs)}
-            del st, batch
-            torch.cuda.empty_cache()
+            entry = {"frames_per_gpu": frames}
+            for mode in modes:
+                st, batch = mk(mode == "graph"), mkb()
+                run = train_step.Graphed(st, batch) if mode == "graph" else st
+                for _ in range(3):
+                    run(batch)
+                barrier()
+                n_t = max(3, min(args.steps, 10))
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record()
+                for _ in range(n_t):
+                    res_t = run(batch)
+                b_.record()
+                barrier()
+                ms = torch.tensor([a_.elapsed_time(b_) / n_t], dtype=torch.float64, device=dev)
+                if dist is not None:
+                    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                ok = all(bool(torch.isfinite(v)) for v in res_t.values() if v is not None)
+                syncs = [g_.sync for g_ in st.groups() if g_.sync is not None]
+                entry[mode] = {"ms_per_step": float(ms), "frames_per_sec": world * frames * 1e3 / float(ms), "steps": n_t, "finite": ok}
+                entry["allreduce_bytes_per_step"] = sum(s_.bytes_per_step for s_ in syncs)
+                entry["allreduce_buckets"] = sum(len(s_.buckets) for s_ in syncs)
+                del st, batch, run
+                torch.cuda.empty_cache()
+            best = min((entry[m] for m in modes), key=lambda e: e["ms_per_step"])
+            entry.update(ms_per_step=best["ms_per_step"], frames_per_sec=best["frames_per_sec"])
+            train[name] = entry
       except Exception as exc:
         train["error"] = "%s: %s" % (type(exc).__name__, exc)
 
@@ -376,13 +382,13 @@ def run_ours(args):
                          "seconds": cpu_s},
         "reference_gpu_port": ref_gpu,
         "clocks": clocks,
-        "train": dict(train, note="one optimiser iteration per step, synthetic data, LPIPS omitted (weights unavailable offline): stage one = "
+        "train": dict(train, note="one optimiser iteration per step (eager = ~1500 host launches; graph = the iteration replayed as CUDA graphs), synthetic data, LPIPS omitted (weights unavailable offline): stage one = "
                                   "train_avatar.py:112-158 on 4 frames x 64x64-ray patches per GPU (64+16 samples, fused render fwd+bwd, patch "
                                   "discriminator); stage two = train_avatarHD.py:201-303 on 1 frame per GPU (D step + G step, 128^2 render -> 512^2)"),
         "hd": dict(hd, note="HD frames/s = XY/YZ plane generators (StyleGAN_zxc) + 512x512x64 or 128x128x64 render + SWGAN_unet, "
                             "one frame per GPU, CUDA-graph replay, random-init weights, per-rank values (not max-reduced)"),
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -394,6 +400,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--train-mode", default="both", choices=["both", "eager", "graph"],
+                    help="training-step leg: eager launches, whole-iteration CUDA graphs (train_step.Graphed), or both")
     ap.add_argument("--no-train", dest="no_train", action="store_true", help="skip the training-step measurement")
     ap.add_argument("--no-hd", dest="no_hd", action="store_true", help="skip the secondary HD frames/s measurement")
     args = ap.parse_args()

@@ -63,25 +63,35 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 
 // weights [Cout,Cin,k,k] fp32 -> per (n tile, channel block, tap): [8 chunks][n_tile rows][8] fp16, value scale * w
 // (flipped in kh,kw when flip != 0: the transposed convolution).  Channels / rows beyond Cin / Cout are zero.
+// One thread per (output row n, 8-channel K chunk): it reads the 8 x k*k source values (a contiguous 8*k*k run when the weight
+// is [Cout,Cin,k,k]; k*k-float runs that neighbouring threads continue when it is [Cin,Cout,k,k]) and writes one 16-byte unit
+// per tap, consecutive threads -> consecutive units.
 template <bool kBF16>
 __global__ void pack_conv_weights_kernel(const float *__restrict__ w, uint16_t *__restrict__ out, int Cout, int Cin, int k,
                                          int n_tile, int n_tiles, int kblocks, float scale, int flip, int transpose_io) {
   const int taps = k * k;
-  const long total = (long)n_tiles * kblocks * taps * (kCinBlk / 8) * n_tile * 8;
+  const long total = (long)n_tiles * kblocks * (kCinBlk / 8) * n_tile;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long r = i;
-    const int e = r % 8; r /= 8;
     const int n = r % n_tile; r /= n_tile;
     const int chunk = r % (kCinBlk / 8); r /= (kCinBlk / 8);
-    const int tap = r % taps; r /= taps;
     const int kb = r % kblocks; r /= kblocks;
     const int nt = (int)r;
-    const int co = nt * n_tile + n, ci = kb * kCinBlk + chunk * 8 + e;
-    int kh = tap / k, kw = tap % k;
-    if (flip) kh = k - 1 - kh, kw = k - 1 - kw;
-    float v = 0.0f;
-    if (co < Cout && ci < Cin) v = scale * (transpose_io ? w[(((long)ci * Cout + co) * k + kh) * k + kw] : w[(((long)co * Cin + ci) * k + kh) * k + kw]);
-    out[i] = kBF16 ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
+    const int co = nt * n_tile + n, ci0 = kb * kCinBlk + chunk * 8;
+    uint4 *dst = reinterpret_cast<uint4 *>(out) + (((long)nt * kblocks + kb) * taps * (kCinBlk / 8) + chunk) * n_tile + n;
+    for (int tap = 0; tap < taps; ++tap) {
+      const int src_tap = flip ? taps - 1 - tap : tap;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int ci = ci0 + e;
+        v[e] = 0.0f;
+        if (co < Cout && ci < Cin)
+          v[e] = scale * __ldg(transpose_io ? w + ((long)ci * Cout + co) * taps + src_tap : w + ((long)co * Cin + ci) * taps + src_tap);
+      }
+      dst[(long)tap * (kCinBlk / 8) * n_tile] = make_uint4(pack2<kBF16>(v[0], v[1]), pack2<kBF16>(v[2], v[3]), pack2<kBF16>(v[4], v[5]),
+                                                           pack2<kBF16>(v[6], v[7]));
+    }
   }
 }
 

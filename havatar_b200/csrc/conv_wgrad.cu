@@ -15,10 +15,11 @@
 // TMEM (432 of 512 columns), no im2col, no transposed copies.  A CTA owns a (128 co) x (48 ci) x 9 block of dW and a strided
 // share of the position tiles (split-K); partial sums leave TMEM as vectorised fp32 reductions (red.global.add.v4.f32).
 //
-// The strided convolutions reuse the kernel through zero insertion while staging:
-//   down = 2 (stride 2, pad 0):  dW = sum_P G2[P] x[P + (kh,kw)],   G2 = g with zeros inserted between its pixels (a_step = 2)
-//   up   = 2 (conv_transpose2d): dW = sum_P g[P] X2[P - (kh,kw)],   X2 = x with zeros inserted (x_step = 2), taps mirrored
-// (4x the necessary MMA work on those few layers, none on the stride-1 layers that dominate).
+// The strided convolutions are polyphase: with q the tensor that is read with stride 2,
+//   down = 2 (stride 2, pad 0):  dW[kh,kw] = sum_p g[p] x[2p + (kh,kw)]     A = g, B = x
+//   up   = 2 (conv_transpose2d): dW[kh,kw] = sum_p x[p] g[2p + (kh,kw)]     A = x, B = g  (accumulators hold dW transposed)
+// the B side is staged as its four parity planes q[2i+a, 2j+b] ((8+1) x (16+1) pixels each) and tap (kh,kw) reads plane
+// (kh&1, kw&1) shifted by (kh>>1, kw>>1) -- the same 72 MMAs per tile as a stride-1 layer, no multiplications by zeros.
 #include "tc_common.cuh"
 
 namespace hav {
@@ -27,29 +28,37 @@ namespace wg {
 using namespace tc;
 
 constexpr int kTH = 8, kTW = 16;                   // position tile: 8 rows x 16 px = 8 K-steps of 16
-constexpr int kHW = kTW + 2, kHH = kTH + 2, kHaloPx = kHH * kHW;   // 180
-constexpr int kNci = 48, kMco = 128;
-constexpr int kABytes = (kTH * kTW / 8) * kMco * 16;   // 32768
-constexpr int kBChunk = kHaloPx * 16;                  // 2880
-constexpr int kBBytes = (kNci / 8) * kBChunk;          // 17280
-constexpr int kStages = 3;
-constexpr int kSmA = 0;
-constexpr int kSmB = kSmA + kStages * kABytes;
-constexpr int kSmScale = kSmB + kStages * kBBytes;     // [kStages][48] float
-constexpr int kSmBar = kSmScale + kStages * kNci * 4;
-constexpr int kSmemBytes = kSmBar + 128;
+constexpr int kNb = 48, kMa = 128;                 // B-side channels (TMEM columns per tap) and A-side channels (TMEM lanes) per CTA
+constexpr int kABytes = (kTH * kTW / 8) * kMa * 16;   // 32768
 constexpr int kStageThreads = 256, kThreads = kStageThreads + 32;
 constexpr int kTmemCols = 512;
 constexpr uint32_t kBMajorMN = 1u << 16;
+constexpr int kSmScale = 128, kSmA = 1024;         // [0,128): mbarriers + TMEM slot; [128,1024): B-side scale tables
+
+// B-side staging geometry.  STRIDE 1: one halo of (8+2) x (16+2) pixels, tap (kh,kw) = shift (kh,kw).
+// STRIDE 2: four parity planes q[2i+a, 2j+b] of (8+1) x (16+1) pixels, tap (kh,kw) = plane (kh&1, kw&1) shifted by (kh>>1, kw>>1).
+template <int STRIDE>
+struct Geo {
+  static constexpr int kW = STRIDE == 1 ? kTW + 2 : kTW + 1, kH = STRIDE == 1 ? kTH + 2 : kTH + 1;
+  static constexpr int kPx = kW * kH;                          // 180 / 153
+  static constexpr int kPlanes = STRIDE == 1 ? 1 : 4;
+  static constexpr int kChunk = kPx * 16;                      // bytes of one 8-channel chunk of one plane
+  static constexpr int kPlaneBytes = (kNb / 8) * kChunk;
+  static constexpr int kBBytes = kPlanes * kPlaneBytes;        // 17280 / 58752
+  static constexpr int kUnits = kPlanes * (kNb / 8) * kPx;     // 1080 / 3672
+  static constexpr int kStages = STRIDE == 1 ? 3 : 2;
+  static constexpr int kSmB = kSmA + kStages * kABytes;
+  static constexpr int kSmemBytes = kSmB + kStages * kBBytes;  // 151168 / 184064
+};
 
 struct WgDev {
-  int B, Cin, Cout, k, taps;
-  int GH, GW, g_h, g_w, a_step;       // virtual position grid, real size of g, zero-insertion step of g
-  int x_h, x_w, x_step, x_off;        // real size of x, zero-insertion step of x, halo origin = tile origin + x_off
-  int a_vec, dw_vec;                  // 16-byte vector loads of g / vector reductions into dw are aligned
-  int mirror;                         // tap (kh,kw) reads the halo at (2-kh, 2-kw) instead of (kh,kw)
-  int tiles_x, tiles_y, ntiles, nsplit, co_tiles, ci_tiles;
-  const float *g, *x, *in_scale, *out_scale;
+  int B, Ca, Cb;                      // channels of the A tensor (TMEM lanes) and of the B tensor (TMEM columns)
+  int a_h, a_w, b_h, b_w;             // spatial sizes; position tiles run over the A tensor
+  int pad;                            // stride 1: B coordinate = position + tap - pad;  stride 2: 2 * position + tap
+  int out_t;                          // 0: dw[(a_ch * Cb + b_ch) * taps + tap]   1: dw[(b_ch * Ca + a_ch) * taps + tap]
+  int a_vec, dw_vec;                  // 16-byte vector loads of the A tensor / vector reductions into dw are aligned
+  int tiles_x, tiles_y, ntiles, nsplit, a_tiles, b_tiles;
+  const float *pa, *pb, *sa, *sb;     // tensors [B,C,h,w] and their per-(sample, channel) scales [B,C] (NULL = 1)
   float *dw;
   float wscale;
 };
@@ -60,32 +69,36 @@ __device__ __forceinline__ void mbar_arrive_wg(uint32_t bar) {
 __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+__device__ __forceinline__ void red_add(float *p, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
 
 #define HAV_TMEM_LD8(r, taddr)                                                                          \
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                 \
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) \
                : "r"(taddr))
 
-template <int KS>
+template <int KS, int STRIDE>
 __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const WgDev P) {
+  using G = Geo<STRIDE>;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t bar_full = smem_base + kSmBar, bar_free = bar_full + kStages * 8, bar_acc = bar_free + kStages * 8;
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kSmBar + 120);
+  const uint32_t bar_full = smem_base, bar_free = bar_full + G::kStages * 8, bar_acc = bar_free + G::kStages * 8;
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 120);
   constexpr int taps = KS * KS;
 
-  const int cot = blockIdx.x % P.co_tiles, cit = blockIdx.x / P.co_tiles;
+  const int at = blockIdx.x % P.a_tiles, bt = blockIdx.x / P.a_tiles;
   const int split = blockIdx.y;
-  const int co0 = cot * kMco, ci0 = cit * kNci;
+  const int ca0 = at * kMa, cb0 = bt * kNb;
 
   if (warp_u == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + kSmBar + 120), "r"(kTmemCols));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + 120), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 32) {
-    for (int i = 0; i < kStages; ++i) mbar_init(bar_full + i * 8, kStageThreads), mbar_init(bar_free + i * 8, 1);
+    for (int i = 0; i < G::kStages; ++i) mbar_init(bar_full + i * 8, kStageThreads), mbar_init(bar_free + i * 8, 1);
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -97,23 +110,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const WgDev P) 
   if (warp_u == kStageThreads / 32) {
     // ================= control warp: 8 rows x taps MMAs per position tile =================
     if (elect_one()) {
-      constexpr uint32_t idesc = instr_desc(kNci, true) | kBMajorMN;
+      constexpr uint32_t idesc = instr_desc(kNb, true) | kBMajorMN;
       int it = 0;
       for (int t = split; t < P.ntiles; t += P.nsplit, ++it) {
-        const int st = it % kStages;
-        mbar_wait_spin(bar_full + st * 8, (it / kStages) & 1);
+        const int st = it % G::kStages;
+        mbar_wait_spin(bar_full + st * 8, (it / G::kStages) & 1);
         tc_fence_after();
-        const uint32_t A0 = smem_base + kSmA + st * kABytes, B0 = smem_base + kSmB + st * kBBytes;
+        const uint32_t A0 = smem_base + kSmA + st * kABytes, B0 = smem_base + G::kSmB + st * G::kBBytes;
 #pragma unroll 1
         for (int r = 0; r < kTH; ++r) {
-          const uint64_t adesc = smem_desc(A0 + 2 * r * (kMco * 16), kMco * 16, 128);
+          const uint64_t adesc = smem_desc(A0 + 2 * r * (kMa * 16), kMa * 16, 128);
 #pragma unroll
           for (int tap = 0; tap < taps; ++tap) {
-            int kh = tap / KS, kw = tap - kh * KS;
-            if (P.mirror) kh = KS - 1 - kh, kw = KS - 1 - kw;
+            const int kh = tap / KS, kw = tap - kh * KS;
+            uint32_t b_addr;
+            if (STRIDE == 1) b_addr = B0 + ((r + kh) * G::kW + kw) * 16;
+            else b_addr = B0 + (((kh & 1) << 1) | (kw & 1)) * G::kPlaneBytes + ((r + (kh >> 1)) * G::kW + (kw >> 1)) * 16;
             // MN-major: LBO = distance between 8-pixel K groups (128 B), SBO = distance between 8-channel groups (one chunk)
-            const uint64_t bdesc = smem_desc(B0 + ((r + kh) * kHW + kw) * 16, 128, kBChunk);
-            umma_ss(tmem_acc + tap * kNci, adesc, bdesc, idesc, (it > 0 || r > 0) ? 1u : 0u);
+            umma_ss(tmem_acc + tap * kNb, adesc, smem_desc(b_addr, 128, G::kChunk), idesc, (it > 0 || r > 0) ? 1u : 0u);
           }
         }
         umma_commit(bar_free + st * 8);
@@ -123,102 +137,114 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const WgDev P) 
     __syncwarp();
   } else {
     // ================= staging warps =================
-    const size_t g_plane = (size_t)P.g_h * P.g_w, x_plane = (size_t)P.x_h * P.x_w;
-    const int co_l = tid & (kMco - 1), co = co0 + co_l;
+    const size_t a_plane = (size_t)P.a_h * P.a_w, b_plane = (size_t)P.b_h * P.b_w;
+    const int ca_l = tid & (kMa - 1), ca = ca0 + ca_l, a_half = tid >> 7;
+    const bool ca_ok = ca < P.Ca;
     const bool a_vec = P.a_vec != 0;
     int it = 0;
     for (int t = split; t < P.ntiles; t += P.nsplit, ++it) {
-      const int st = it % kStages;
+      const int st = it % G::kStages;
       int sp = t;
       const int tx = sp % P.tiles_x; sp /= P.tiles_x;
       const int ty = sp % P.tiles_y;
       const int b = sp / P.tiles_y;
       const int Y0 = ty * kTH, X0 = tx * kTW;
-      if (it >= kStages) mbar_wait_spin(bar_free + st * 8, ((it / kStages) - 1) & 1);
-      float *sc = reinterpret_cast<float *>(smem + kSmScale) + st * kNci;
-      if (tid < kNci) {
-        const int ci = ci0 + tid;
-        sc[tid] = ci < P.Cin ? (P.in_scale != nullptr ? __ldg(P.in_scale + (size_t)b * P.Cin + ci) : 1.0f) : 0.0f;
-      }
-      // ---- A: d*g, K-major.  unit = (8-px chunk c = 2*row + half, channel); this thread's channel is fixed
+      // ---- A loads first (they do not depend on the ring slot): this thread's channel, the 8 rows of the tile, one 8-px half
+      float va[kTH][8];
       {
-        uint8_t *A = smem + kSmA + st * kABytes;
-        const bool co_ok = co < P.Cout;
-        const float as = co_ok ? (P.out_scale != nullptr ? __ldg(P.out_scale + (size_t)b * P.Cout + co) : 1.0f) : 0.0f;
-        const float *gb = P.g + ((size_t)b * P.Cout + (co_ok ? co : 0)) * g_plane;
-#pragma unroll 2
-        for (int c = tid >> 7; c < 16; c += 2) {
-          const int Y = Y0 + (c >> 1), X = X0 + (c & 1) * 8;
-          float v[8];
+        const float *ab = P.pa + ((size_t)b * P.Ca + (ca_ok ? ca : 0)) * a_plane;
+        const int X = X0 + a_half * 8;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = 0.0f;
-          if (co_ok && Y < P.GH) {
-            if (a_vec && X + 8 <= P.GW) {
-              const float4 p = __ldg(reinterpret_cast<const float4 *>(gb + (size_t)Y * P.g_w + X));
-              const float4 q = __ldg(reinterpret_cast<const float4 *>(gb + (size_t)Y * P.g_w + X + 4));
-              v[0] = p.x, v[1] = p.y, v[2] = p.z, v[3] = p.w, v[4] = q.x, v[5] = q.y, v[6] = q.z, v[7] = q.w;
-            } else if (P.a_step == 1) {
+        for (int r = 0; r < kTH; ++r) {
+          const int Y = Y0 + r;
+          const bool row_ok = ca_ok && Y < P.a_h;
+          if (a_vec && row_ok && X + 8 <= P.a_w) {
+            const float4 p = __ldg(reinterpret_cast<const float4 *>(ab + (size_t)Y * P.a_w + X));
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(ab + (size_t)Y * P.a_w + X + 4));
+            va[r][0] = p.x, va[r][1] = p.y, va[r][2] = p.z, va[r][3] = p.w, va[r][4] = q.x, va[r][5] = q.y, va[r][6] = q.z, va[r][7] = q.w;
+          } else {
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if (X + e < P.GW) v[e] = __ldg(gb + (size_t)Y * P.g_w + X + e);
-            } else if (!(Y & 1)) {      // zero-inserted g: virtual (Y, X) holds g[Y/2, X/2] when both are even (X0 is even)
-#pragma unroll
-              for (int e = 0; e < 8; e += 2)
-                if (X + e < P.GW) v[e] = __ldg(gb + (size_t)(Y >> 1) * P.g_w + ((X + e) >> 1));
-            }
+            for (int e = 0; e < 8; ++e) va[r][e] = (row_ok && X + e < P.a_w) ? __ldg(ab + (size_t)Y * P.a_w + X + e) : 0.0f;
           }
-          *reinterpret_cast<uint4 *>(A + c * (kMco * 16) + co_l * 16) =
-              make_uint4(pack2<true>(v[0] * as, v[1] * as), pack2<true>(v[2] * as, v[3] * as), pack2<true>(v[4] * as, v[5] * as),
-                         pack2<true>(v[6] * as, v[7] * as));
         }
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(kStageThreads) : "memory");   // the scale table of this stage is complete
-      // ---- B: s*x halo, MN-major.  unit = (8-channel chunk, halo pixel); consecutive threads take consecutive pixels
+      const float as = ca_ok ? (P.sa != nullptr ? __ldg(P.sa + (size_t)b * P.Ca + ca) : 1.0f) : 0.0f;
+      if (it >= G::kStages) mbar_wait_spin(bar_free + st * 8, ((it / G::kStages) - 1) & 1);
+      float *sc = reinterpret_cast<float *>(smem + kSmScale) + st * kNb;
+      if (tid < kNb) {
+        const int cb = cb0 + tid;
+        sc[tid] = cb < P.Cb ? (P.sb != nullptr ? __ldg(P.sb + (size_t)b * P.Cb + cb) : 1.0f) : 0.0f;
+      }
       {
-        uint8_t *Bm = smem + kSmB + st * kBBytes;
-        const float *xb = P.x + (size_t)b * P.Cin * x_plane;
-        int hp = tid, chunk = 0;
-        while (hp >= kHaloPx) hp -= kHaloPx, ++chunk;
+        uint8_t *A = smem + kSmA + st * kABytes;
+#pragma unroll
+        for (int r = 0; r < kTH; ++r)
+          *reinterpret_cast<uint4 *>(A + (2 * r + a_half) * (kMa * 16) + ca_l * 16) =
+              make_uint4(pack2<true>(va[r][0] * as, va[r][1] * as), pack2<true>(va[r][2] * as, va[r][3] * as),
+                         pack2<true>(va[r][4] * as, va[r][5] * as), pack2<true>(va[r][6] * as, va[r][7] * as));
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kStageThreads) : "memory");   // the scale table of this stage is complete
+      // ---- B: MN-major planes.  unit = (plane, 8-channel chunk, pixel); consecutive threads take consecutive pixels.
+      //      Batches of 5 units: 40 independent loads in flight per thread before the first conversion.
+      {
+        uint8_t *Bm = smem + G::kSmB + st * G::kBBytes;
+        const float *bb = P.pb + (size_t)b * P.Cb * b_plane;
+        constexpr int kBatch = 5, kIters = (G::kUnits + kStageThreads * kBatch - 1) / (kStageThreads * kBatch);
 #pragma unroll 1
-        for (; chunk < kNci / 8;) {
-          const int py = hp / kHW, px = hp - py * kHW;
-          int Y = Y0 + py + P.x_off, X = X0 + px + P.x_off;
-          bool ok = Y >= 0 && X >= 0;
-          if (P.x_step == 2) ok = ok && !(Y & 1) && !(X & 1), Y >>= 1, X >>= 1;
-          ok = ok && Y < P.x_h && X < P.x_w;
-          const int c0 = ci0 + chunk * 8;
-          float v[8];
+        for (int bi = 0; bi < kIters; ++bi) {
+          float vb[kBatch][8];
+          int dst[kBatch], chs[kBatch];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = (ok && c0 + e < P.Cin) ? __ldg(xb + (size_t)(c0 + e) * x_plane + (size_t)Y * P.x_w + X) : 0.0f;
+          for (int j = 0; j < kBatch; ++j) {
+            const int u = tid + (bi * kBatch + j) * kStageThreads;
+            const bool in = u < G::kUnits;
+            const int plane = STRIDE == 1 ? 0 : u / ((kNb / 8) * G::kPx);
+            const int rem = STRIDE == 1 ? u : u - plane * ((kNb / 8) * G::kPx);
+            const int chunk = rem / G::kPx, hp = rem - chunk * G::kPx;
+            const int py = hp / G::kW, px = hp - py * G::kW;
+            int Y, X;
+            if (STRIDE == 1) Y = Y0 + py - P.pad, X = X0 + px - P.pad;
+            else Y = 2 * (Y0 + py) + (plane >> 1), X = 2 * (X0 + px) + (plane & 1);
+            const bool ok = in && Y >= 0 && X >= 0 && Y < P.b_h && X < P.b_w;
+            const int c0 = cb0 + chunk * 8;
+            const float *src = bb + (size_t)c0 * b_plane + (size_t)Y * P.b_w + X;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] *= sc[chunk * 8 + e];
-          *reinterpret_cast<uint4 *>(Bm + chunk * kBChunk + hp * 16) =
-              make_uint4(pack2<true>(v[0], v[1]), pack2<true>(v[2], v[3]), pack2<true>(v[4], v[5]), pack2<true>(v[6], v[7]));
-          hp += kStageThreads;
-          while (hp >= kHaloPx) hp -= kHaloPx, ++chunk;
+            for (int e = 0; e < 8; ++e) vb[j][e] = (ok && c0 + e < P.Cb) ? __ldg(src + (size_t)e * b_plane) : 0.0f;
+            dst[j] = in ? plane * G::kPlaneBytes + chunk * G::kChunk + hp * 16 : -1;
+            chs[j] = chunk * 8;
+          }
+#pragma unroll
+          for (int j = 0; j < kBatch; ++j) {
+            if (dst[j] >= 0) {
+              const float *s8 = sc + chs[j];
+              *reinterpret_cast<uint4 *>(Bm + dst[j]) =
+                  make_uint4(pack2<true>(vb[j][0] * s8[0], vb[j][1] * s8[1]), pack2<true>(vb[j][2] * s8[2], vb[j][3] * s8[3]),
+                             pack2<true>(vb[j][4] * s8[4], vb[j][5] * s8[5]), pack2<true>(vb[j][6] * s8[6], vb[j][7] * s8[7]));
+            }
+          }
         }
       }
       fence_async_smem();
       mbar_arrive_wg(bar_full + st * 8);
     }
-    // ---- epilogue: accumulator block `tap` holds dW[co lane][ci column]; memory order is [co][ci][kh][kw]
+    // ---- epilogue: accumulator block `tap` holds [A channel = TMEM lane][B channel = column]; dw is [Cout][Cin][kh][kw]
     if (it > 0) {
       mbar_wait_spin(bar_acc, 0);
       tc_fence_after();
       const int wq = warp_u & 3, half = warp_u >> 2;
-      const int row = wq * 32 + (tid & 31), co_e = co0 + row;
+      const int row = wq * 32 + (tid & 31), ca_e = ca0 + row;
       const uint32_t trow = tmem_acc + ((uint32_t)(wq * 32) << 16);
-      const bool vec_ok = P.dw_vec != 0;
+      const bool vec_ok = P.dw_vec != 0 && P.out_t == 0;
 #pragma unroll 1
-      for (int gi = half; gi < kNci / 8; gi += 2) {
+      for (int gi = half; gi < kNb / 8; gi += 2) {
         uint32_t r[taps][8];
 #pragma unroll
-        for (int tap = 0; tap < taps; ++tap) HAV_TMEM_LD8(r[tap], trow + tap * kNci + gi * 8);
+        for (int tap = 0; tap < taps; ++tap) HAV_TMEM_LD8(r[tap], trow + tap * kNb + gi * 8);
         tmem_wait_ld();
-        const int cb = ci0 + gi * 8;
-        if (co_e < P.Cout && cb < P.Cin) {
-          float *dst = P.dw + ((size_t)co_e * P.Cin + cb) * taps;
-          if (vec_ok && cb + 8 <= P.Cin) {
+        const int cb = cb0 + gi * 8;
+        if (ca_e < P.Ca && cb < P.Cb) {
+          if (vec_ok && cb + 8 <= P.Cb) {
+            float *dst = P.dw + ((size_t)ca_e * P.Cb + cb) * taps;
             float f[taps * 8];
 #pragma unroll
             for (int e = 0; e < 8; ++e)
@@ -229,9 +255,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const WgDev P) 
           } else {
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-              if (cb + e < P.Cin) {
+              if (cb + e < P.Cb) {
+                float *dst = P.out_t ? P.dw + ((size_t)(cb + e) * P.Ca + ca_e) * taps : P.dw + ((size_t)ca_e * P.Cb + cb + e) * taps;
 #pragma unroll
-                for (int tap = 0; tap < taps; ++tap) atomicAdd(dst + e * taps + tap, __uint_as_float(r[tap][e]) * P.wscale);
+                for (int tap = 0; tap < taps; ++tap) red_add(dst + tap, __uint_as_float(r[tap][e]) * P.wscale);
               }
           }
         }
@@ -315,45 +342,52 @@ extern "C" int hav_conv2d_wgrad(const hav_conv_wgrad_args *a, void *stream) {
   if (a->g == nullptr || a->x == nullptr) return HAV_E_NULL;
   wg::WgDev P;
   memset(&P, 0, sizeof(P));
-  P.B = a->batch, P.Cin = a->cin, P.Cout = a->cout, P.k = k, P.taps = taps;
-  P.x_h = a->in_h, P.x_w = a->in_w;
-  if (a->up == 2) {           // y = conv_transpose2d(x, stride 2, pad 0): g is (2H+1) x (2W+1)
-    P.g_h = 2 * a->in_h + 1, P.g_w = 2 * a->in_w + 1;
-    P.GH = P.g_h, P.GW = P.g_w, P.a_step = 1, P.x_step = 2, P.x_off = -2, P.mirror = 1;
-  } else if (a->down == 2) {  // y = conv2d(x, stride 2, pad 0): g is ((H-3)/2+1) x ((W-3)/2+1)
-    if (a->in_h < 3 || a->in_w < 3) return HAV_E_SHAPE;
-    P.g_h = (a->in_h - 3) / 2 + 1, P.g_w = (a->in_w - 3) / 2 + 1;
-    P.GH = 2 * P.g_h - 1, P.GW = 2 * P.g_w - 1, P.a_step = 2, P.x_step = 1, P.x_off = 0, P.mirror = 0;
+  P.B = a->batch;
+  int stride = 1;
+  if (a->up == 2) {           // y = conv_transpose2d(x, stride 2, pad 0), g is (2H+1) x (2W+1):  dw = sum_p x[p] g[2p + tap]
+    P.Ca = a->cin, P.Cb = a->cout, P.pa = a->x, P.pb = a->g, P.sa = a->in_scale, P.sb = a->out_scale;
+    P.a_h = a->in_h, P.a_w = a->in_w, P.b_h = 2 * a->in_h + 1, P.b_w = 2 * a->in_w + 1, P.out_t = 1, stride = 2;
   } else {
-    P.g_h = a->in_h, P.g_w = a->in_w;
-    P.GH = P.g_h, P.GW = P.g_w, P.a_step = 1, P.x_step = 1, P.x_off = -(k / 2), P.mirror = 0;
+    P.Ca = a->cout, P.Cb = a->cin, P.pa = a->g, P.pb = a->x, P.sa = a->out_scale, P.sb = a->in_scale;
+    P.b_h = a->in_h, P.b_w = a->in_w, P.out_t = 0;
+    if (a->down == 2) {       // y = conv2d(x, stride 2, pad 0), g is ((H-3)/2+1) x ((W-3)/2+1):  dw = sum_p g[p] x[2p + tap]
+      if (a->in_h < 3 || a->in_w < 3) return HAV_E_SHAPE;
+      P.a_h = (a->in_h - 3) / 2 + 1, P.a_w = (a->in_w - 3) / 2 + 1, stride = 2;
+    } else {                  // stride 1, pad k/2:  dw = sum_p g[p] x[p + tap - pad]
+      P.a_h = a->in_h, P.a_w = a->in_w, P.pad = k / 2;
+    }
   }
-  P.tiles_x = (P.GW + wg::kTW - 1) / wg::kTW, P.tiles_y = (P.GH + wg::kTH - 1) / wg::kTH;
+  P.tiles_x = (P.a_w + wg::kTW - 1) / wg::kTW, P.tiles_y = (P.a_h + wg::kTH - 1) / wg::kTH;
   const long ntiles = (long)a->batch * P.tiles_x * P.tiles_y;
   if (ntiles > 2147483647L) return HAV_E_SHAPE;
   P.ntiles = (int)ntiles;
-  P.co_tiles = (a->cout + wg::kMco - 1) / wg::kMco, P.ci_tiles = (a->cin + wg::kNci - 1) / wg::kNci;
-  const long blocks = (long)P.co_tiles * P.ci_tiles;
+  P.a_tiles = (P.Ca + wg::kMa - 1) / wg::kMa, P.b_tiles = (P.Cb + wg::kNb - 1) / wg::kNb;
+  const long blocks = (long)P.a_tiles * P.b_tiles;
   if (blocks > 2147483647L) return HAV_E_SHAPE;
-  long nsplit = (2 * 148 + blocks - 1) / blocks;      // about two waves of CTAs (one CTA per SM: 512 TMEM columns each)
+  // split-K so that the grid is at most two FULL waves of one CTA per SM (512 TMEM columns each): a third, nearly empty
+  // wave would cost as much as a full one; one wave when a CTA would otherwise see only a handful of tiles
+  long nsplit = (2 * 148) / blocks;
+  if (nsplit < 1) nsplit = 1;
+  if (ntiles / nsplit < 6 && 148 / blocks >= 1) nsplit = 148 / blocks;
   if (nsplit > ntiles) nsplit = ntiles;
   if (nsplit > 65535) nsplit = 65535;
   if (nsplit < 1) nsplit = 1;
   P.nsplit = (int)nsplit;
-  P.g = a->g, P.x = a->x, P.in_scale = a->in_scale, P.out_scale = a->out_scale, P.dw = a->dw, P.wscale = a->wscale;
-  P.a_vec = P.a_step == 1 && (P.g_w & 3) == 0 && ((uintptr_t)a->g & 15) == 0;
+  P.dw = a->dw, P.wscale = a->wscale;
+  P.a_vec = (P.a_w & 3) == 0 && ((uintptr_t)P.pa & 15) == 0;
   P.dw_vec = (((size_t)a->cin * taps) & 3) == 0 && ((uintptr_t)a->dw & 15) == 0;
   dim3 grid((unsigned)blocks, (unsigned)nsplit);
   cudaError_t e;
-  if (k == 3) {
-    e = cudaFuncSetAttribute(wg::conv_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    wg::conv_wgrad_kernel<3><<<grid, wg::kThreads, wg::kSmemBytes, (cudaStream_t)stream>>>(P);
-  } else {
-    e = cudaFuncSetAttribute(wg::conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    wg::conv_wgrad_kernel<1><<<grid, wg::kThreads, wg::kSmemBytes, (cudaStream_t)stream>>>(P);
-  }
+  auto launch = [&](auto kern, int smem_bytes) -> cudaError_t {
+    cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (er != cudaSuccess) return er;
+    kern<<<grid, wg::kThreads, smem_bytes, (cudaStream_t)stream>>>(P);
+    return cudaGetLastError();
+  };
+  if (k == 1) e = launch(wg::conv_wgrad_kernel<1, 1>, wg::Geo<1>::kSmemBytes);
+  else if (stride == 1) e = launch(wg::conv_wgrad_kernel<3, 1>, wg::Geo<1>::kSmemBytes);
+  else e = launch(wg::conv_wgrad_kernel<3, 2>, wg::Geo<2>::kSmemBytes);
+  if (e != cudaSuccess) return (int)e;
   e = cudaGetLastError();
   return e == cudaSuccess ? HAV_OK : (int)e;
 }

@@ -107,6 +107,16 @@ class InverseHaarTransform(nn.Module):
         return out
 
 
+# Derived tensors (packed weights, scaled linears, host copies of scalars) are cached per parameter version.  A CUDA-graph
+# replay changes parameters without touching their version counters, so train_step.Graphed bumps this epoch after every
+# replay and every cache key carries it.
+_EPOCH = [0]
+
+
+def invalidate_caches():
+    _EPOCH[0] += 1
+
+
 class _PackCache:
     """Packed 16-bit weight image of a conv parameter, rebuilt when the parameter is modified in place or replaced."""
 
@@ -114,7 +124,7 @@ class _PackCache:
         self.key, self.packed = None, None
 
     def get(self, weight, scale, up):
-        key = (weight.data_ptr(), weight._version, str(weight.device), up)
+        key = (weight.data_ptr(), weight._version, str(weight.device), up, _EPOCH[0])
         if key != self.key:
             w = weight.detach()
             if w.dim() == 5:
@@ -194,7 +204,8 @@ class EqualLinear(nn.Module):
 
     def _scaled(self):
         """weight * scale and bias * lr_mul, recomputed only when a parameter changes (two launches saved per call)."""
-        key = (self.weight.data_ptr(), self.weight._version, None if self.bias is None else (self.bias.data_ptr(), self.bias._version))
+        key = (self.weight.data_ptr(), self.weight._version, None if self.bias is None else (self.bias.data_ptr(), self.bias._version),
+               _EPOCH[0])
         if key != self._key:
             self._w = (self.weight.detach() * self.scale).contiguous()
             self._b = None if self.bias is None else (self.bias.detach() * self.lr_mul).contiguous()
@@ -252,13 +263,25 @@ class NoiseInjection(nn.Module):
     def __init__(self):
         super().__init__()
         self.weight = nn.Parameter(torch.zeros(1))
-        self._key, self._val = None, 0.0
+        self._key, self._val, self._misses = None, 0.0, 0
 
     def value(self):
-        key = (self.weight.data_ptr(), self.weight._version)
+        key = (self.weight.data_ptr(), self.weight._version, _EPOCH[0])
         if key != self._key:                      # one device->host read per weight update, not per forward
             self._val, self._key = float(self.weight.detach().cpu()), key
         return self._val
+
+    def scaled(self, noise):
+        """(noise tensor, host weight) for the fused epilogue.  While the weight is static (inference) the host copy of the
+        scalar is cached; while it changes every iteration (training: a device->host read per layer per step would serialise
+        the host with the GPU, and cannot be captured into a CUDA graph) the product is formed on the device instead."""
+        key = (self.weight.data_ptr(), self.weight._version, _EPOCH[0])
+        if key == self._key:
+            return noise, self._val
+        if torch.cuda.is_current_stream_capturing() or self._misses >= 2:
+            return self.weight.detach() * noise, 1.0
+        self._misses += 1
+        return noise, self.value()
 
     def forward(self, image, noise=None):
         if noise is None:
@@ -291,7 +314,8 @@ class StyledConv(nn.Module):
             h, w = (x.shape[1], x.shape[2]) if hconv.is_cl(x) else (x.shape[2], x.shape[3])
             f = 2 if self.conv.upsample else 1
             noise = torch.empty(x.shape[0], 1, h * f, w * f, dtype=torch.float32, device=x.device).normal_()
-        return self.conv.run(x, style, noise=noise, noise_weight=self.noise.value(), bias=self.activate.bias, act=True, out_cl=out_cl)
+        noise, nw = self.noise.scaled(noise)
+        return self.conv.run(x, style, noise=noise, noise_weight=nw, bias=self.activate.bias, act=True, out_cl=out_cl)
 
 
 class ToRGB(nn.Module):

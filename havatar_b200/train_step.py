@@ -58,12 +58,23 @@ def _distributed():
 
 
 class _Group:
-    """Parameters + Adam + (when distributed) the bucketed gradient all-reduce of one optimiser."""
+    """Parameters + Adam + (when distributed) the bucketed gradient all-reduce of one optimiser.  capturable=True keeps the
+    step count and the learning rate on the device so the whole update can live inside a CUDA graph."""
 
-    def __init__(self, modules, lr, betas=(0.9, 0.999)):
+    def __init__(self, modules, lr, betas=(0.9, 0.999), capturable=False):
         self.params = [p for m in modules for p in m.parameters()]
         self.sync = parallel.GradSync(self.params) if _distributed() else None
-        self.opt = torch.optim.Adam(self.params, lr=lr, betas=betas)
+        self.capturable = capturable
+        if capturable:
+            lr = torch.tensor(float(lr), dtype=torch.float32, device=self.params[0].device)
+        self.opt = torch.optim.Adam(self.params, lr=lr, betas=betas, capturable=capturable, foreach=True)
+
+    def set_lr(self, lr):
+        for grp in self.opt.param_groups:
+            if self.capturable:
+                grp["lr"].fill_(float(lr))
+            else:
+                grp["lr"] = float(lr)
 
     def step(self):
         if self.sync is not None:
@@ -82,24 +93,41 @@ class _Group:
 
 
 class StageOneStep:
-    def __init__(self, n_frames=4, device="cuda", cfg=None, precision="fp16", patch=64, lr=5e-4, with_discriminator=True, seed=0):
+    def __init__(self, n_frames=4, device="cuda", cfg=None, precision="fp16", patch=64, lr=5e-4, with_discriminator=True, seed=0,
+                 capturable=False):
         torch.manual_seed(seed)
         self.cfg = cfg or default_cfg()
         self.device = torch.device(device)
         self.net = trainer.Trainer(self.cfg, n_frames, precision=precision).to(self.device)
+        self.net.device_rng = capturable
         self.disc = styleunet.Discriminator(patch, img_channel=3).to(self.device) if with_discriminator else None
         mods = [self.net] + ([self.disc] if self.disc is not None else [])
         if _distributed():
             parallel.broadcast_parameters(mods)
-        self.g = _Group([self.net], lr)                                             # train_avatar.py:68-71
-        self.d = _Group([self.disc], 2e-3 * 16 / 17, betas=(0.0, 0.99 ** (16 / 17))) if self.disc is not None else None
-        self.patch, self.it = patch, 0
+        self.g = _Group([self.net], lr, capturable=capturable)                                             # train_avatar.py:68-71
+        self.d = _Group([self.disc], 2e-3 * 16 / 17, betas=(0.0, 0.99 ** (16 / 17)), capturable=capturable) if self.disc is not None else None
+        self.patch, self.it, self.lr0 = patch, 0, lr
+
+    def groups(self):
+        return [g for g in (self.g, self.d) if g is not None]
+
+    def pre_step(self):
+        """Host-side bookkeeping of one iteration (outside any CUDA graph): the exponential learning-rate decay of
+        train_avatar.py:154-158, applied to the coming step."""
+        self.g.set_lr(max(self.lr0 * (0.1 ** (self.it / 250000.0)), 5e-5))
+        self.it += 1
+
+    def parts(self):
+        return [("step", self.body, True)]
 
     def __call__(self, batch):
         """batch: dict with ray_batch [B,R,8], background_prior [B,R,3], target [B,R,3], mask [B,R,1], fidx [B], inv_head_T
         [B,4,3], {front,left,right}_render_cond [B,7,256,256] (device tensors).  Returns {'loss', 'd_loss'} (detached)."""
+        self.pre_step()
+        return self.body(batch)
+
+    def body(self, batch):
         cfg, P = self.cfg, self.patch
-        self.it += 1
         if self.d is not None:
             self.d.requires_grad(False)
         out = self.net(mode="train", fidx=batch["fidx"], render_full_img=False, ray_batch=batch["ray_batch"],
@@ -126,9 +154,6 @@ class StageOneStep:
         loss.backward()                                                                                             # :149
         self.g.step()                                                                                               # :151
         self.g.zero_grad()
-        lr_new = max(5e-4 * (0.1 ** (self.it / 250000.0)), 5e-5)                                                    # :154-158
-        for grp in self.g.opt.param_groups:
-            grp["lr"] = lr_new
         d_loss = None
         if self.disc is not None:
             self.d.requires_grad(True)
@@ -142,11 +167,12 @@ class StageOneStep:
 
 class StageTwoStep:
     def __init__(self, n_frames=8, device="cuda", cfg=None, precision="fp16", render_size=128, gen_size=512, d_reg_every=16,
-                 r1=10.0, latent=64, n_mlp=4, seed=0):
+                 r1=10.0, latent=64, n_mlp=4, seed=0, capturable=False):
         torch.manual_seed(seed)
         self.cfg = cfg or default_cfg(inp_size=render_size, out_size=gen_size)
         self.device = torch.device(device)
         self.net = trainer.Trainer(self.cfg, n_frames, precision=precision).to(self.device)                 # train_avatarHD.py:109
+        self.net.device_rng = capturable
         mk = lambda: styleunet.SWGAN_unet(inp_size=render_size, inp_ch=64, out_ch=3, out_size=gen_size, style_dim=latent,
                                           n_mlp=n_mlp).to(self.device)                                          # :110-111
         self.generator, self.g_ema = mk(), mk()
@@ -156,65 +182,136 @@ class StageTwoStep:
         if _distributed():
             parallel.broadcast_parameters([self.net, self.generator, self.g_ema, self.disc])
         g_ratio, d_ratio = 4 / 5, d_reg_every / (d_reg_every + 1)                                            # :117-122
-        self.nerf = _Group([self.net], 5e-4)
-        self.g = _Group([self.generator], 2e-3 * g_ratio, betas=(0.0, 0.99 ** g_ratio))
-        self.d = _Group([self.disc], 2e-3 * d_ratio, betas=(0.0, 0.99 ** d_ratio))
+        self.nerf = _Group([self.net], 5e-4, capturable=capturable)
+        self.g = _Group([self.generator], 2e-3 * g_ratio, betas=(0.0, 0.99 ** g_ratio), capturable=capturable)
+        self.d = _Group([self.disc], 2e-3 * d_ratio, betas=(0.0, 0.99 ** d_ratio), capturable=capturable)
         self.render_size, self.gen_size, self.latent = render_size, gen_size, latent
         self.d_reg_every, self.r1, self.it = d_reg_every, r1, 0
         self.accum = 0.5 ** (32 / (10 * 1000))                                                               # :162
+        self.gan_w = torch.tensor(1e-3, dtype=torch.float32, device=self.device)
+
+    def groups(self):
+        return [self.nerf, self.g, self.d]
 
     def _noise(self, b):                                             # mixing_noise with mixing = 0 (:170-175)
         return [torch.randn(b, self.latent, device=self.device)]
 
+    def pre_step(self):
+        self.it += 1
+        self.gan_w.fill_(min(1e-3 * 1.1 ** (self.it // 500), 0.1))                                             # :205-206
+
+    def parts(self):
+        return [("d", self.d_step, True), ("r1", self.r1_step, False), ("g", self.g_step, True)]
+
     def __call__(self, batch):
         """batch: the StageOneStep keys with full low-res frames (R = render_size^2) plus gt_hr_img [B,3,G,G] and gt_lr_mask
         [B,1,render,render]."""
-        self.it += 1
-        i, rs, gs = self.it, self.render_size, self.gen_size
+        self.pre_step()
+        out = {}
+        for _, fn, _ in self.parts():
+            out.update(fn(batch) or {})
+        return out
+
+    def _inp(self, batch):
+        return dict(mode="train", fidx=batch["fidx"], render_full_img=True, ray_batch=batch["ray_batch"],
+                    background_prior=batch["background_prior"], inv_head_T=batch["inv_head_T"],
+                    front_render_cond=batch["front_render_cond"], left_render_cond=batch["left_render_cond"],
+                    right_render_cond=batch["right_render_cond"])
+
+    def d_step(self, batch):                                                                                    # :211-231
         gt_hr = batch["gt_hr_img"]
-        inp = dict(mode="train", fidx=batch["fidx"], render_full_img=True, ray_batch=batch["ray_batch"],
-                   background_prior=batch["background_prior"], inv_head_T=batch["inv_head_T"],
-                   front_render_cond=batch["front_render_cond"], left_render_cond=batch["left_render_cond"],
-                   right_render_cond=batch["right_render_cond"])
+        B = gt_hr.shape[0]
+        self.nerf.requires_grad(False), self.g.requires_grad(False), self.d.requires_grad(True)
+        with torch.no_grad():
+            render, _, _ = self.net(**self._inp(batch))
+            fake = self.generator(self._noise(B), render[:, 3:].contiguous())
+        d_loss = d_logistic_loss(self.disc(gt_hr), self.disc(fake)) * self.gan_w
+        d_loss.backward()
+        self.d.step()
+        self.d.zero_grad()
+        return {"d_loss": d_loss.detach()}
+
+    def r1_step(self, batch):                                                                                   # :233-240
+        if self.it % self.d_reg_every != 0:
+            return {"r1": None}
+        self.nerf.requires_grad(False), self.g.requires_grad(False), self.d.requires_grad(True)
+        real = batch["gt_hr_img"].detach().requires_grad_(True)
+        with styleunet_train.library_convs():       # second-order gradients through the convolutions
+            pred = self.disc(real)
+        r1_loss = d_r1_loss(pred, real) * self.gan_w
+        (self.r1 / 2 * r1_loss * self.d_reg_every + 0 * pred[0]).sum().backward()
+        self.d.step()
+        self.d.zero_grad()
+        return {"r1": r1_loss.detach()}
+
+    def g_step(self, batch):                                                                                    # :243-303
+        gt_hr, rs, gs = batch["gt_hr_img"], self.render_size, self.gen_size
         B = gt_hr.shape[0]
         gt_lr = F.interpolate(F.interpolate(gt_hr, size=(rs, rs), mode="bilinear", align_corners=True), size=(gs, gs),
                               mode="bilinear", align_corners=True)                                              # :202-204
-        gan_w = min(1e-3 * 1.1 ** (i // 500), 0.1)                                                              # :205-206
-        # ---- D step (:211-231)
-        self.nerf.requires_grad(False), self.g.requires_grad(False), self.d.requires_grad(True)
-        with torch.no_grad():
-            render, _, _ = self.net(**inp)
-            fake = self.generator(self._noise(B), render[:, 3:].contiguous())
-        d_loss = d_logistic_loss(self.disc(gt_hr), self.disc(fake)) * gan_w
-        self.d.zero_grad()
-        d_loss.backward()
-        self.d.step()
-        r1_loss = None
-        if i % self.d_reg_every == 0:                                                                           # :233-240
-            real = gt_hr.detach().requires_grad_(True)
-            with styleunet_train.library_convs():       # second-order gradients through the convolutions
-                pred = self.disc(real)
-            r1_loss = d_r1_loss(pred, real) * gan_w
-            self.d.zero_grad()
-            (self.r1 / 2 * r1_loss * self.d_reg_every + 0 * pred[0]).sum().backward()
-            self.d.step()
-        # ---- G step (:243-280)
         self.nerf.requires_grad(True), self.g.requires_grad(True), self.d.requires_grad(False)
-        self.nerf.zero_grad(), self.g.zero_grad()
-        render, mask, lat = self.net(**inp)
+        render, mask, lat = self.net(**self._inp(batch))
         lr_img = F.interpolate(render[:, :3], size=(gs, gs), mode="bilinear", align_corners=True)
         g_loss = F.mse_loss(lr_img, gt_lr) + lat
         g_loss = g_loss + self.cfg.experiment.mask_weight * F.binary_cross_entropy(mask.clip(1e-3, 1.0 - 1e-3), batch["gt_lr_mask"])
         fake = self.generator(self._noise(B), render[:, 3:].contiguous())
-        g_loss = g_loss + g_nonsaturating_loss(self.disc(fake)) * gan_w + F.l1_loss(fake, gt_hr)
+        g_loss = g_loss + g_nonsaturating_loss(self.disc(fake)) * self.gan_w + F.l1_loss(fake, gt_hr)
         g_loss.backward()
         self.g.step()
         self.nerf.step()
+        self.g.zero_grad(), self.nerf.zero_grad()
         with torch.no_grad():                                                                                   # :303
             pe, pg = list(self.g_ema.parameters()), list(self.generator.parameters())
             torch._foreach_mul_(pe, self.accum)
             torch._foreach_add_(pe, pg, alpha=1 - self.accum)
-        return {"d_loss": d_loss.detach(), "g_loss": g_loss.detach(), "r1": None if r1_loss is None else r1_loss.detach()}
+        return {"g_loss": g_loss.detach()}
+
+
+class Graphed:
+    """A training step replayed as CUDA graphs: forward, backward, the gradient all-reduce, the Adam updates and the EMA of one
+    iteration become one graph launch per graphable part (StageOneStep: one; StageTwoStep: the D step and the G step, with the
+    every-16th R1 pass run eagerly between them), removing the ~1500 host-side kernel launches that bound the eager step.
+    The step must be built with capturable=True (device-side Adam state / learning rate, device RNG for sample_pdf).
+    `example` provides shapes; its tensors are cloned into the static input buffers every replay reads."""
+
+    def __init__(self, step, example, warmup=3):
+        self.step = step
+        self.static = {k: v.clone() for k, v in example.items() if isinstance(v, torch.Tensor)}
+        dev = step.device
+        self.stream = torch.cuda.Stream(device=dev)
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        self.graphs, self.outs = {}, {}
+        with torch.cuda.stream(self.stream):
+            for _ in range(warmup):                     # allocator / cuDNN / Adam-state warm-up on the capture stream
+                step(self.static)
+            for grp in step.groups():                   # gradients must be (re)allocated from the graphs' private pool
+                if grp.sync is None:
+                    grp.opt.zero_grad(set_to_none=True)
+            step.pre_step()
+            for name, fn, graphable in step.parts():
+                if graphable:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self.stream):
+                        self.outs[name] = fn(self.static)
+                    self.graphs[name] = g
+                    g.replay()                          # the captured iteration has not executed yet: run it once
+                else:
+                    fn(self.static)
+        torch.cuda.current_stream(dev).wait_stream(self.stream)
+
+    def __call__(self, batch):
+        for k, v in self.static.items():
+            v.copy_(batch[k], non_blocking=True)
+        self.step.pre_step()
+        out = {}
+        for name, fn, graphable in self.step.parts():
+            if graphable:
+                self.graphs[name].replay()
+                out.update(self.outs[name] or {})
+            else:
+                out.update(fn(self.static) or {})
+        styleunet.invalidate_caches()       # replays changed parameters behind their version counters
+        return out
 
 
 def synthetic_batch(stage, batch, device, seed=0, patch=64, render_size=128, gen_size=512, frame_offset=0):

@@ -112,7 +112,7 @@ class SkinningField(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.canonical_Wvolume.parameters()):
             self.last_volume = self.canonical_Wvolume()         # training: part of the graph (Skinning_Field.py:79)
             return self.last_volume
-        key = tuple((p.data_ptr(), p._version) for p in self.canonical_Wvolume.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in self.canonical_Wvolume.parameters()) + (styleunet._EPOCH[0],)
         if key != self._key:
             with torch.no_grad():
                 self._vol = self.canonical_Wvolume().detach().contiguous()
@@ -171,6 +171,9 @@ class Trainer(nn.Module):
         s, t = _box_warp(bounds[0], yb, bounds[2])
         self.headpose_skin_net = SkinningField(_BoxWarp(s, t))
         self.precision = precision
+        # True: draw sample_pdf's u on the device instead of the CPU generator (utils/nerf_util.py:93-96 draws on the CPU and
+        # copies; a pageable host->device copy cannot be captured into a CUDA graph -- train_step.Graphed sets this)
+        self.device_rng = False
 
     def _boxes(self):
         g, h = self.model_coarse.gridwarper, self.headpose_skin_net.gridwarper
@@ -198,7 +201,10 @@ class Trainer(nn.Module):
         elif opt.perturb:                                                           # :132-139, utils/nerf_util.py:93-96
             rnd["t_rand"] = torch.rand(B, R, nc, dtype=torch.float32, device=dev)
             if nf > 0:
-                rnd["u_rand"] = torch.rand([B * R, nf], dtype=torch.float32).to(dev).view(B, R, nf)   # CPU generator, like the reference
+                if self.device_rng:
+                    rnd["u_rand"] = torch.rand(B, R, nf, dtype=torch.float32, device=dev)
+                else:
+                    rnd["u_rand"] = torch.rand([B * R, nf], dtype=torch.float32).to(dev).view(B, R, nf)   # CPU generator, like the reference
         std = float(opt.radiance_field_noise_std)
         if given is None and std > 0.0:                                                             # utils/nerf_util.py:47-57
             rnd["noise_coarse"] = torch.randn(B, R, nc, device=dev) * std

@@ -51,3 +51,40 @@ def test_stage_two_step_runs_with_r1():
         moved, total = _moved(before[k], v)
         assert moved >= 0.8 * total, (k, moved, total)      # a few generator tensors are unused by the no_skip configuration
     assert _moved(ema0, [step.g_ema])[0] > 0
+
+
+def test_graphed_stage_one_step_matches_eager():
+    """The whole iteration (forward, fused render backward, convolution backward, Adam) captured as one CUDA graph must walk
+    the same trajectory as the eager step: deterministic configuration (no perturbation / density noise, no discriminator), ten
+    iterations each from the same seed."""
+    def make(capturable):
+        cfg = train_step.default_cfg(num_coarse=32, num_fine=8, perturb=False, noise_std=0.0)
+        return train_step.StageOneStep(n_frames=4, cfg=cfg, patch=64, seed=0, with_discriminator=False, capturable=capturable)
+
+    batch = train_step.synthetic_batch(1, 4, "cuda", seed=0, patch=64)
+    eager = make(False)
+    le = [float(eager(batch)["loss"]) for _ in range(10)]
+    step = make(True)
+    run = train_step.Graphed(step, batch, warmup=3)        # 3 eager warm-up iterations + the captured one = iterations 1..4
+    lg = [float(run(batch)["loss"]) for _ in range(6)]     # iterations 5..10
+    torch.cuda.synchronize()
+    assert step.it == eager.it == 10
+    assert le[-1] < le[0]                                  # the batch is being fitted
+    for a, b in zip(le[4:], lg):
+        assert abs(a - b) < 2e-2 * abs(a), (le, lg)
+    we, wg = eager.net.model_coarse.layers_xyz[1].weight, step.net.model_coarse.layers_xyz[1].weight
+    assert float((we - wg).abs().max()) < 5e-2 * float(we.abs().max())
+    assert all(torch.isfinite(p).all() for p in step.net.parameters())
+
+
+def test_graphed_stage_two_step_with_eager_r1():
+    step = train_step.StageTwoStep(n_frames=2, render_size=32, gen_size=128, d_reg_every=2, seed=0, capturable=True)
+    batch = train_step.synthetic_batch(2, 2, "cuda", seed=1, render_size=32, gen_size=128)
+    run = train_step.Graphed(step, batch)
+    g0 = _snap([step.generator])
+    outs = [run(batch) for _ in range(4)]
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(o["g_loss"]) and torch.isfinite(o["d_loss"]) for o in outs)
+    assert any(o["r1"] is not None for o in outs)
+    moved, total = _moved(g0, [step.generator])
+    assert moved >= 0.8 * total
