@@ -141,6 +141,9 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic frame of this rank (weak scaling: one frame per GPU per step, different head pose per rank)
@@ -276,19 +279,19 @@ def run_ours(args):
 
         torch.cuda.empty_cache()
         modes = ("eager", "graph") if args.train_mode == "both" else (args.train_mode,)
-        for name, mk, mkb, frames in (
+        # stage two runs its R1 pass every 16th iteration: warm up through the first one, then time one full period of 16
+        for name, mk, mkb, frames, n_warm, n_t in (
                 ("stage_one_b4_patch64", lambda c: train_step.StageOneStep(n_frames=4 * world, device=dev, capturable=c),
-                 lambda: train_step.synthetic_batch(1, 4, dev, seed=rank, patch=64, frame_offset=4 * rank), 4),
+                 lambda: train_step.synthetic_batch(1, 4, dev, seed=rank, patch=64, frame_offset=4 * rank), 4, 3, max(3, min(args.steps, 10))),
                 ("stage_two_b1_128_to_512", lambda c: train_step.StageTwoStep(n_frames=world, device=dev, capturable=c),
-                 lambda: train_step.synthetic_batch(2, 1, dev, seed=rank, render_size=128, gen_size=512, frame_offset=rank), 1)):
+                 lambda: train_step.synthetic_batch(2, 1, dev, seed=rank, render_size=128, gen_size=512, frame_offset=rank), 1, 16, 16)):
             entry = {"frames_per_gpu": frames}
             for mode in modes:
                 st, batch = mk(mode == "graph"), mkb()
                 run = train_step.Graphed(st, batch) if mode == "graph" else st
-                for _ in range(3):
+                for _ in range(n_warm):
                     run(batch)
                 barrier()
-                n_t = max(3, min(args.steps, 10))
                 a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a_.record()
                 for _ in range(n_t):
@@ -300,7 +303,12 @@ def run_ours(args):
                     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
                 ok = all(bool(torch.isfinite(v)) for v in res_t.values() if v is not None)
                 syncs = [g_.sync for g_ in st.groups() if g_.sync is not None]
-                entry[mode] = {"ms_per_step": float(ms), "frames_per_sec": world * frames * 1e3 / float(ms), "steps": n_t, "finite": ok}
+                if dist is not None:      # replicas must still hold identical weights after the timed iterations
+                    chk = torch.stack([p_.detach().double().sum() for g_ in st.groups() for p_ in g_.params[:8]])
+                    lo_, hi_ = chk.clone(), chk.clone()
+                    dist.all_reduce(lo_, op=dist.ReduceOp.MIN), dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+                    ok = ok and bool((hi_ - lo_).abs().max() <= 1e-9 * hi_.abs().max().clamp_min(1.0))
+                entry[mode] = {"ms_per_step": float(ms), "frames_per_sec": world * frames * 1e3 / float(ms), "steps": n_t, "finite_and_in_sync": ok}
                 entry["allreduce_bytes_per_step"] = sum(s_.bytes_per_step for s_ in syncs)
                 entry["allreduce_buckets"] = sum(len(s_.buckets) for s_ in syncs)
                 del st, batch, run
