@@ -232,10 +232,84 @@ def rowscale_dot(a, x=None, scale=None, want_out=True, want_dot=True):
     return out, dot
 
 
+def _dgrad_raw(g, weight, wscale, up, down, H, W, in_scale=None):
+    """Data gradient of conv(x, wscale * weight) = the forward kernel on g with the transposed weight image (mirrored taps for
+    stride 1); the gradient of a stride-2 convolution is a transposed stride-2 convolution and vice versa.  in_scale multiplies
+    g per (sample, output channel) while it is staged (the demodulation of a modulated layer)."""
+    if up == 2:
+        wp = pack_weights(weight, wscale, up=1, transpose_io=True, precision="bf16")
+        return conv2d(g, wp, in_scale=in_scale, down=2)
+    if down == 2:
+        wp = pack_weights(weight, wscale, up=2, transpose_io=True, precision="bf16")
+        dxs = conv2d(g, wp, in_scale=in_scale, up=2)
+        if dxs.shape[2] != H or dxs.shape[3] != W:       # even input: its last row / column never reached an output
+            dxs = torch.nn.functional.pad(dxs, (0, W - dxs.shape[3], 0, H - dxs.shape[2]))
+        return dxs
+    wp = pack_weights(weight, wscale, up=1, transpose_io=True, flip=True, precision="bf16")
+    return conv2d(g, wp, in_scale=in_scale)
+
+
+# The convolution is bilinear in (x, w), so its three kernels are closed under differentiation:
+#     y  = F(x, w)          dF:  dx = D(gy, w)   dw = W(gy, x)
+#     dx = D(g, w)          dD:  dg = F(h, w)    dw = W(g, h)
+#     dw = W(g, x)          dW:  dg = F(x, V)    dx = D(g, V)
+# Each is an autograd node whose backward applies the other two, which gives gradients of every order (the R1 penalty
+# differentiates the discriminator's input gradient, utils/styleUnet_util.py:72-79) without any library convolution.
+class _Fwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, wscale, up, down, precision):
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (wscale, up, down)
+        return conv2d(x, pack_weights(weight, wscale, up=up, precision=precision), up=up, down=down)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        wscale, up, down = ctx.cfg
+        dx = _Dgrad.apply(gy, weight, wscale, up, down, int(x.shape[2]), int(x.shape[3])) if ctx.needs_input_grad[0] else None
+        dw = _Wgrad.apply(gy, x, wscale, up, down, int(weight.shape[-1])) if ctx.needs_input_grad[1] else None
+        return dx, dw, None, None, None, None
+
+
+class _Dgrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, weight, wscale, up, down, H, W):
+        ctx.save_for_backward(g, weight)
+        ctx.cfg = (wscale, up, down)
+        return _dgrad_raw(g.contiguous(), weight, wscale, up, down, H, W)
+
+    @staticmethod
+    def backward(ctx, h):
+        g, weight = ctx.saved_tensors
+        wscale, up, down = ctx.cfg
+        dg = _Fwd.apply(h.contiguous(), weight, wscale, up, down, "bf16") if ctx.needs_input_grad[0] else None
+        dw = _Wgrad.apply(g, h.contiguous(), wscale, up, down, int(weight.shape[-1])) if ctx.needs_input_grad[1] else None
+        return dg, dw, None, None, None, None, None
+
+
+class _Wgrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, x, wscale, up, down, k):
+        ctx.save_for_backward(g, x)
+        ctx.cfg = (wscale, up, down)
+        return conv_wgrad(g.contiguous(), x.contiguous(), k, wscale=wscale, up=up, down=down)
+
+    @staticmethod
+    def backward(ctx, v):
+        g, x = ctx.saved_tensors
+        wscale, up, down = ctx.cfg
+        v = v.contiguous()
+        dg = _Fwd.apply(x, v, wscale, up, down, "bf16") if ctx.needs_input_grad[0] else None
+        dx = _Dgrad.apply(g, v, wscale, up, down, int(x.shape[2]), int(x.shape[3])) if ctx.needs_input_grad[1] else None
+        return dg, dx, None, None, None, None
+
+
 class _ConvFunction(torch.autograd.Function):
     """y = out_scale[b,co] * conv(in_scale[b,ci] * x, wscale * weight): ModulatedConv2d in its shared-weight form
     (model/styleUnet.py:225-251) and, with both scales None, EqualConv2d (:108-118).  Forward: fp16 operands; backward: bf16
-    operands (gradients have no fixed range), fp32 accumulation everywhere."""
+    operands (gradients have no fixed range), fp32 accumulation everywhere.  First-order backward is the fused path (scales
+    applied while staging, one row kernel for the modulation gradients); when the backward itself is being recorded
+    (create_graph=True) it is composed from the differentiable nodes _Dgrad / _Wgrad and torch elementwise ops instead."""
 
     @staticmethod
     def forward(ctx, x, weight, in_scale, out_scale, wscale, up, down):
@@ -247,39 +321,40 @@ class _ConvFunction(torch.autograd.Function):
         return y
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         x, weight, in_scale, out_scale, y = ctx.saved_tensors
         wscale, up, down, k = ctx.cfg
-        g = g.contiguous()
+        need = ctx.needs_input_grad
+        H, W = int(x.shape[2]), int(x.shape[3])
         dx = dw = ds = dd = None
-        if ctx.needs_input_grad[0] or (in_scale is not None and ctx.needs_input_grad[2]):
-            # data gradient = the forward kernel on g with the transposed weight image; stride 2 <-> transposed stride 2
-            if up == 2:
-                wp = pack_weights(weight, wscale, up=1, transpose_io=True, precision="bf16")
-                dxs = conv2d(g, wp, in_scale=out_scale, down=2)
-            elif down == 2:
-                wp = pack_weights(weight, wscale, up=2, transpose_io=True, precision="bf16")
-                dxs = conv2d(g, wp, in_scale=out_scale, up=2)
-                H, W = int(x.shape[2]), int(x.shape[3])
-                if dxs.shape[2] != H or dxs.shape[3] != W:       # even input: its last row / column never reached an output
-                    dxs = torch.nn.functional.pad(dxs, (0, W - dxs.shape[3], 0, H - dxs.shape[2]))
-            else:
-                wp = pack_weights(weight, wscale, up=1, transpose_io=True, flip=True, precision="bf16")
-                dxs = conv2d(g, wp, in_scale=out_scale)
+        if torch.is_grad_enabled():      # create_graph=True: every step below must itself be differentiable
+            gs = g if out_scale is None else g * out_scale[:, :, None, None]
+            if need[0] or (in_scale is not None and need[2]):
+                dxs = _Dgrad.apply(gs, weight, wscale, up, down, H, W)
+                dx = dxs if in_scale is None else dxs * in_scale[:, :, None, None]
+                if in_scale is not None and need[2]:
+                    ds = (dxs * x).sum(dim=(2, 3))
+            if need[1]:
+                dw = _Wgrad.apply(gs, x if in_scale is None else x * in_scale[:, :, None, None], wscale, up, down, k)
+            if out_scale is not None and need[3]:
+                dd = (g * y).sum(dim=(2, 3)) / out_scale
+            return dx, dw, ds, dd, None, None, None
+        g = g.contiguous()
+        if need[0] or (in_scale is not None and need[2]):
+            dxs = _dgrad_raw(g, weight, wscale, up, down, H, W, in_scale=out_scale)
             if in_scale is not None:
-                dx, ds = rowscale_dot(dxs, x, in_scale, want_out=ctx.needs_input_grad[0], want_dot=ctx.needs_input_grad[2])
+                dx, ds = rowscale_dot(dxs, x, in_scale, want_out=need[0], want_dot=need[2])
             else:
                 dx = dxs
-        if ctx.needs_input_grad[1]:
+        if need[1]:
             dw = conv_wgrad(g, x, k, in_scale=in_scale, out_scale=out_scale, wscale=wscale, up=up, down=down)
-        if out_scale is not None and ctx.needs_input_grad[3]:
+        if out_scale is not None and need[3]:
             _, gy = rowscale_dot(g, y, None, want_out=False)
             dd = gy / out_scale
         return dx, dw, ds, dd, None, None, None
 
 
 def conv2d_autograd(x, weight, in_scale=None, out_scale=None, wscale=1.0, up=1, down=1):
-    """Differentiable  out_scale * conv(in_scale * x, wscale * weight)  on the tcgen05 kernels (first-order gradients w.r.t. x,
-    weight [Cout,Cin,k,k], in_scale [B,Cin] and out_scale [B,Cout])."""
+    """Differentiable  out_scale * conv(in_scale * x, wscale * weight)  on the tcgen05 kernels: gradients of any order w.r.t. x,
+    weight [Cout,Cin,k,k], in_scale [B,Cin] and out_scale [B,Cout]."""
     return _ConvFunction.apply(x, weight, in_scale, out_scale, float(wscale), int(up), int(down))

@@ -11,9 +11,9 @@ autograd.  What runs underneath:
     transposed weight image (data gradient), the tcgen05 weight-gradient kernel (hav_conv2d_wgrad) and one row kernel for the
     modulation / demodulation gradients, in ModulatedConv2d's shared-weight formulation (the reference's own non-fused branch,
     styleUnet.py:225-251).
-    The one exception is a pass that needs SECOND-order gradients through the convolutions (the R1 penalty every 16th
-    discriminator step, utils/styleUnet_util.py:72-79): inside `library_convs()` the same formulas run on
-    torch.nn.functional.conv2d / conv_transpose2d (cuDNN), whose double backward autograd already has.
+    The three convolution kernels are closed under differentiation (conv.py: _Fwd / _Dgrad / _Wgrad), so second-order passes
+    (the R1 penalty every 16th discriminator step, utils/styleUnet_util.py:72-79) run on them too.  `library_convs()` switches the
+    same formulas to torch.nn.functional.conv2d / conv_transpose2d (cuDNN) -- used only by tests and timing comparisons.
 """
 import contextlib
 
@@ -28,7 +28,7 @@ _NATIVE = [True]
 
 @contextlib.contextmanager
 def library_convs():
-    """Run the convolutions of the enclosed forward on torch's own ops (needed only where the graph is differentiated twice)."""
+    """Run the convolutions of the enclosed forward on torch's own ops (a comparison arm for tests / timing, not the product path)."""
     prev, _NATIVE[0] = _NATIVE[0], False
     try:
         yield

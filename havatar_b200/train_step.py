@@ -7,7 +7,7 @@ SURVEY.md section 8e (BASELINE.json configs[2] and configs[4]).
                   patch term is the non-saturating GAN loss through a 64x64 `Discriminator` on the rendered patch (the
                   "GAN discriminator" BASELINE.json names for this config) and the discriminator takes its own logistic step.
   StageTwoStep  = one iteration of train_avatarHD.py:201-303: D step (render + generator without grad, logistic loss, Adam),
-                  R1 every d_reg_every (double backward through our upfirdn2d / fused_leaky_relu autograd), G step (render with
+                  R1 every d_reg_every (double backward through our convolution / upfirdn2d / fused_leaky_relu autograd), G step (render with
                   grad -> low-res losses; generator -> non-saturating + L1; one backward; generator and render Adam steps),
                   EMA accumulate (utils/styleUnet_util.py:51-56).  LPIPS omitted for the same reason.
 
@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
-from . import parallel, styleunet, styleunet_train, trainer
+from . import parallel, styleunet, trainer
 
 
 def default_cfg(num_coarse=64, num_fine=16, perturb=True, noise_std=0.1, inp_size=128, out_size=512):
@@ -236,8 +236,7 @@ class StageTwoStep:
             return {"r1": None}
         self.nerf.requires_grad(False), self.g.requires_grad(False), self.d.requires_grad(True)
         real = batch["gt_hr_img"].detach().requires_grad_(True)
-        with styleunet_train.library_convs():       # second-order gradients through the convolutions
-            pred = self.disc(real)
+        pred = self.disc(real)
         r1_loss = d_r1_loss(pred, real) * self.gan_w
         (self.r1 / 2 * r1_loss * self.d_reg_every + 0 * pred[0]).sum().backward()
         self.d.step()

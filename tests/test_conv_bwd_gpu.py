@@ -55,7 +55,7 @@ def test_conv_backward_matches_torch_autograd(B, Cin, Cout, H, W, k, up, down, m
     g_ref = torch.autograd.grad(y_ref, leaves, go)
     y = conv.conv2d_autograd(x, w, s, d, wscale, up=up, down=down)
     assert y.shape == y_ref.shape
-    assert float((y - y_ref).abs().max()) < 2e-2 * float(y_ref.abs().max())
+    assert float((y - y_ref).detach().abs().max()) < 2e-2 * float(y_ref.detach().abs().max())
     g = torch.autograd.grad(y, leaves, go)
     torch.cuda.synchronize()
     for name, a, b in zip(("x", "w", "s", "d"), g, g_ref):
@@ -83,3 +83,31 @@ def test_rowscale_dot():
         out, dot = conv.rowscale_dot(a, x, s)
         assert torch.equal(out, a * s[:, :, None, None])
         assert float((dot - (a * x).sum((2, 3))).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("Cin,Cout,H,k,up,down,mod", [(32, 48, 16, 3, 1, 1, False), (24, 32, 17, 3, 1, 2, False), (16, 8, 12, 1, 1, 1, False),
+                                                      (32, 32, 8, 3, 2, 1, True), (40, 24, 12, 3, 1, 1, True)])
+def test_conv_double_backward_matches_torch(Cin, Cout, H, k, up, down, mod):
+    """R1-style second order (utils/styleUnet_util.py:72-79): L = |d sum(phi(y)) / dx|^2, gradients of L w.r.t. the weight (and
+    the modulation).  The input gradient is recorded with create_graph=True through _Dgrad, whose backward runs _Fwd / _Wgrad."""
+    torch.manual_seed(Cin + Cout + H)
+    torch.backends.cudnn.allow_tf32 = False
+    dev = "cuda"
+    B = 2
+    x = torch.randn(B, Cin, H, H, device=dev, requires_grad=True)
+    w = torch.randn(Cout, Cin, k, k, device=dev, requires_grad=True)
+    s = (torch.rand(B, Cin, device=dev) + 0.5).requires_grad_(True) if mod else None
+    d = (torch.rand(B, Cout, device=dev) + 0.5).requires_grad_(True) if mod else None
+    wscale = 1.0 / (Cin * k * k) ** 0.5
+    leaves = [t for t in (w, s, d) if t is not None]
+
+    def penalty(y):
+        gx, = torch.autograd.grad((y * y).sum() * 0.5, x, create_graph=True)        # phi = y^2 / 2 so the first gradient depends on y
+        return gx.pow(2).sum()
+
+    ref = torch.autograd.grad(penalty(_ref(x, w, s, d, wscale, up, down)), leaves)
+    got = torch.autograd.grad(penalty(conv.conv2d_autograd(x, w, s, d, wscale, up=up, down=down)), leaves)
+    torch.cuda.synchronize()
+    for name, a, b in zip(("w", "s", "d"), got, ref):
+        err = float((a - b).abs().max()) / float(b.abs().max())
+        assert err < 3e-2, (name, err)      # three chained bf16-operand convolutions
