@@ -29,8 +29,9 @@ using namespace tc;
 
 constexpr int kTH = 8, kTW = 16;                   // position tile: 8 rows x 16 px = 8 K-steps of 16
 constexpr int kNb = 48, kMa = 128;                 // B-side channels (TMEM columns per tap) and A-side channels (TMEM lanes) per CTA
-constexpr int kABytes = (kTH * kTW / 8) * kMa * 16;   // 32768
-constexpr int kStageThreads = 256, kThreads = kStageThreads + 32;
+constexpr int kAChunk = kMa * 16 + 16;              // K-chunk stride of the A tile, +16 B so row-major stores spread over the banks
+constexpr int kABytes = (kTH * kTW / 8) * kAChunk;    // 33024
+constexpr int kStageThreads = 512, kThreads = kStageThreads + 32;   // 16 staging warps: the loads are latency-bound, not issue-bound
 constexpr int kTmemCols = 512;
 constexpr uint32_t kBMajorMN = 1u << 16;
 constexpr int kSmScale = 128, kSmA = 1024;         // [0,128): mbarriers + TMEM slot; [128,1024): B-side scale tables
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const WgDev P) 
         const uint32_t A0 = smem_base + kSmA + st * kABytes, B0 = smem_base + G::kSmB + st * G::kBBytes;
 #pragma unroll 1
         for (int r = 0; r < kTH; ++r) {
-          const uint64_t adesc = smem_desc(A0 + 2 * r * (kMa * 16), kMa * 16, 128);
+          const uint64_t adesc = smem_desc(A0 + 2 * r * kAChunk, kAChunk, 128);
 #pragma unroll
           for (int tap = 0; tap < taps; ++tap) {
             const int kh = tap / KS, kw = tap - kh * KS;
@@ -138,8 +139,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const WgDev P) 
   } else {
     // ================= staging warps =================
     const size_t a_plane = (size_t)P.a_h * P.a_w, b_plane = (size_t)P.b_h * P.b_w;
-    const int ca_l = tid & (kMa - 1), ca = ca0 + ca_l, a_half = tid >> 7;
-    const bool ca_ok = ca < P.Ca;
+    // A tile: one warp instruction = one channel x 8 rows x 64 B (lane = (row, float4 of the row)): 8 cache lines per 512 B
+    const int a_f4 = tid & 3, a_row = (tid >> 2) & 7, a_ch0 = (tid >> 5) * (kMa / 16);   // 16 warps x 8 channels
     const bool a_vec = P.a_vec != 0;
     int it = 0;
     for (int t = split; t < P.ntiles; t += P.nsplit, ++it) {
@@ -149,26 +150,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const WgDev P) 
       const int ty = sp % P.tiles_y;
       const int b = sp / P.tiles_y;
       const int Y0 = ty * kTH, X0 = tx * kTW;
-      // ---- A loads first (they do not depend on the ring slot): this thread's channel, the 8 rows of the tile, one 8-px half
-      float va[kTH][8];
+      // ---- A loads first (they do not depend on the ring slot): 8 channels of this warp, this lane's row and 4-px quarter
+      float4 va[kMa / 16];
+      float as[kMa / 16];
       {
-        const float *ab = P.pa + ((size_t)b * P.Ca + (ca_ok ? ca : 0)) * a_plane;
-        const int X = X0 + a_half * 8;
+        const int Y = Y0 + a_row, X = X0 + a_f4 * 4;
 #pragma unroll
-        for (int r = 0; r < kTH; ++r) {
-          const int Y = Y0 + r;
-          const bool row_ok = ca_ok && Y < P.a_h;
-          if (a_vec && row_ok && X + 8 <= P.a_w) {
-            const float4 p = __ldg(reinterpret_cast<const float4 *>(ab + (size_t)Y * P.a_w + X));
-            const float4 q = __ldg(reinterpret_cast<const float4 *>(ab + (size_t)Y * P.a_w + X + 4));
-            va[r][0] = p.x, va[r][1] = p.y, va[r][2] = p.z, va[r][3] = p.w, va[r][4] = q.x, va[r][5] = q.y, va[r][6] = q.z, va[r][7] = q.w;
+        for (int j = 0; j < kMa / 16; ++j) {
+          const int ca = ca0 + a_ch0 + j;
+          const bool ok = ca < P.Ca && Y < P.a_h;
+          const float *src = P.pa + (((size_t)b * P.Ca + (ok ? ca : 0)) * P.a_h + (ok ? Y : 0)) * P.a_w + X;
+          if (a_vec && ok && X + 4 <= P.a_w) {
+            va[j] = __ldg(reinterpret_cast<const float4 *>(src));
           } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) va[r][e] = (row_ok && X + e < P.a_w) ? __ldg(ab + (size_t)Y * P.a_w + X + e) : 0.0f;
+            va[j].x = (ok && X + 0 < P.a_w) ? __ldg(src + 0) : 0.0f;
+            va[j].y = (ok && X + 1 < P.a_w) ? __ldg(src + 1) : 0.0f;
+            va[j].z = (ok && X + 2 < P.a_w) ? __ldg(src + 2) : 0.0f;
+            va[j].w = (ok && X + 3 < P.a_w) ? __ldg(src + 3) : 0.0f;
           }
+          as[j] = (ca < P.Ca && P.sa != nullptr) ? __ldg(P.sa + (size_t)b * P.Ca + ca) : 1.0f;
         }
       }
-      const float as = ca_ok ? (P.sa != nullptr ? __ldg(P.sa + (size_t)b * P.Ca + ca) : 1.0f) : 0.0f;
       if (it >= G::kStages) mbar_wait_spin(bar_free + st * 8, ((it / G::kStages) - 1) & 1);
       float *sc = reinterpret_cast<float *>(smem + kSmScale) + st * kNb;
       if (tid < kNb) {
@@ -176,20 +178,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const WgDev P) 
         sc[tid] = cb < P.Cb ? (P.sb != nullptr ? __ldg(P.sb + (size_t)b * P.Cb + cb) : 1.0f) : 0.0f;
       }
       {
-        uint8_t *A = smem + kSmA + st * kABytes;
+        uint8_t *A = smem + kSmA + st * kABytes + (2 * a_row + (a_f4 >> 1)) * kAChunk + (a_f4 & 1) * 8;
 #pragma unroll
-        for (int r = 0; r < kTH; ++r)
-          *reinterpret_cast<uint4 *>(A + (2 * r + a_half) * (kMa * 16) + ca_l * 16) =
-              make_uint4(pack2<true>(va[r][0] * as, va[r][1] * as), pack2<true>(va[r][2] * as, va[r][3] * as),
-                         pack2<true>(va[r][4] * as, va[r][5] * as), pack2<true>(va[r][6] * as, va[r][7] * as));
+        for (int j = 0; j < kMa / 16; ++j)
+          *reinterpret_cast<uint2 *>(A + (a_ch0 + j) * 16) =
+              make_uint2(pack2<true>(va[j].x * as[j], va[j].y * as[j]), pack2<true>(va[j].z * as[j], va[j].w * as[j]));
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kStageThreads) : "memory");   // the scale table of this stage is complete
       // ---- B: MN-major planes.  unit = (plane, 8-channel chunk, pixel); consecutive threads take consecutive pixels.
-      //      Batches of 5 units: 40 independent loads in flight per thread before the first conversion.
+      //      Batches of 3-4 units: 24-32 independent loads in flight per thread before the first conversion.
       {
         uint8_t *Bm = smem + G::kSmB + st * G::kBBytes;
         const float *bb = P.pb + (size_t)b * P.Cb * b_plane;
-        constexpr int kBatch = 5, kIters = (G::kUnits + kStageThreads * kBatch - 1) / (kStageThreads * kBatch);
+        constexpr int kBatch = STRIDE == 1 ? 3 : 4, kIters = (G::kUnits + kStageThreads * kBatch - 1) / (kStageThreads * kBatch);
 #pragma unroll 1
         for (int bi = 0; bi < kIters; ++bi) {
           float vb[kBatch][8];
@@ -231,30 +232,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const WgDev P) 
     if (it > 0) {
       mbar_wait_spin(bar_acc, 0);
       tc_fence_after();
-      const int wq = warp_u & 3, half = warp_u >> 2;
+      const int wq = warp_u & 3, part = warp_u >> 2;          // 4 warps per lane quadrant share the column groups
       const int row = wq * 32 + (tid & 31), ca_e = ca0 + row;
       const uint32_t trow = tmem_acc + ((uint32_t)(wq * 32) << 16);
       const bool vec_ok = P.dw_vec != 0 && P.out_t == 0;
 #pragma unroll 1
-      for (int gi = half; gi < kNb / 8; gi += 2) {
-        uint32_t r[taps][8];
+      for (int gi = part; gi < kNb / 4; gi += kStageThreads / 128) {
+        uint32_t r[taps][4];
 #pragma unroll
-        for (int tap = 0; tap < taps; ++tap) HAV_TMEM_LD8(r[tap], trow + tap * kNb + gi * 8);
+        for (int tap = 0; tap < taps; ++tap) HAV_TMEM_LD4(r[tap], trow + tap * kNb + gi * 4);
         tmem_wait_ld();
-        const int cb = cb0 + gi * 8;
+        const int cb = cb0 + gi * 4;
         if (ca_e < P.Ca && cb < P.Cb) {
-          if (vec_ok && cb + 8 <= P.Cb) {
+          if (vec_ok && cb + 4 <= P.Cb) {
             float *dst = P.dw + ((size_t)ca_e * P.Cb + cb) * taps;
-            float f[taps * 8];
+            float f[taps * 4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
+            for (int e = 0; e < 4; ++e)
 #pragma unroll
               for (int tap = 0; tap < taps; ++tap) f[e * taps + tap] = __uint_as_float(r[tap][e]) * P.wscale;
 #pragma unroll
-            for (int j = 0; j < taps * 8; j += 4) red_add_v4(dst + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
+            for (int j = 0; j < taps * 4; j += 4) red_add_v4(dst + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
           } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
+            for (int e = 0; e < 4; ++e)
               if (cb + e < P.Cb) {
                 float *dst = P.out_t ? P.dw + ((size_t)(cb + e) * P.Ca + ca_e) * taps : P.dw + ((size_t)ca_e * P.Cb + cb + e) * taps;
 #pragma unroll
@@ -374,7 +375,7 @@ extern "C" int hav_conv2d_wgrad(const hav_conv_wgrad_args *a, void *stream) {
   if (nsplit < 1) nsplit = 1;
   P.nsplit = (int)nsplit;
   P.dw = a->dw, P.wscale = a->wscale;
-  P.a_vec = (P.a_w & 3) == 0 && ((uintptr_t)P.pa & 15) == 0;
+  P.a_vec = (P.a_w & 3) == 0 && ((uintptr_t)P.pa & 15) == 0;   // every 4-px quarter of a tile row is a 16-byte aligned float4
   P.dw_vec = (((size_t)a->cin * taps) & 3) == 0 && ((uintptr_t)a->dw & 15) == 0;
   dim3 grid((unsigned)blocks, (unsigned)nsplit);
   cudaError_t e;
