@@ -27,6 +27,23 @@ def _check(t, name):
     return t.detach().contiguous()
 
 
+def pack_weights_cached(weight, scale=1.0, up=1, transpose_io=False, precision="fp16", flip=False, cache=None):
+    """pack_weights memoised in `cache` (a dict owned by the module that owns `weight`) on (storage, version, cache epoch):
+    within one training iteration the same parameter is packed once per (layout, precision) even when several passes use it
+    (the D step and the G step both run the generator forward).  cache=None packs unconditionally."""
+    if cache is None:
+        return pack_weights(weight, scale, up=up, transpose_io=transpose_io, precision=precision, flip=flip)
+    from . import styleunet          # the epoch that CUDA-graph replays bump (parameters change behind their version counters)
+
+    key = (weight.data_ptr(), weight._version, styleunet._EPOCH[0], tuple(weight.shape), float(scale))
+    slot = (int(up), bool(transpose_io), precision, bool(flip))
+    hit = cache.get(slot)
+    if hit is None or hit[0] != key:
+        hit = (key, pack_weights(weight, scale, up=up, transpose_io=transpose_io, precision=precision, flip=flip))
+        cache[slot] = hit
+    return hit[1]
+
+
 def pack_weights(weight, scale=1.0, up=1, transpose_io=False, precision="fp16", flip=False):
     """weight [Cout,Cin,k,k] (or [Cin,Cout,k,k] with transpose_io) -> PackedConvWeight holding scale * weight, laid out for
     conv2d(..., up=up) (the transposed convolution uses 64-channel tiles and four phase accumulators).  flip mirrors the taps
@@ -312,9 +329,9 @@ class _ConvFunction(torch.autograd.Function):
     (create_graph=True) it is composed from the differentiable nodes _Dgrad / _Wgrad and torch elementwise ops instead."""
 
     @staticmethod
-    def forward(ctx, x, weight, in_scale, out_scale, wscale, up, down):
+    def forward(ctx, x, weight, in_scale, out_scale, wscale, up, down, cache):
         k = int(weight.shape[-1])
-        packed = pack_weights(weight, wscale, up=up, precision="fp16")
+        packed = pack_weights_cached(weight, wscale, up=up, precision="fp16", cache=cache)
         y = conv2d(x, packed, in_scale=in_scale, out_scale=out_scale, up=up, down=down)
         ctx.save_for_backward(x, weight, in_scale, out_scale, y if out_scale is not None else None)
         ctx.cfg = (float(wscale), int(up), int(down), k)
@@ -338,7 +355,7 @@ class _ConvFunction(torch.autograd.Function):
                 dw = _Wgrad.apply(gs, x if in_scale is None else x * in_scale[:, :, None, None], wscale, up, down, k)
             if out_scale is not None and need[3]:
                 dd = (g * y).sum(dim=(2, 3)) / out_scale
-            return dx, dw, ds, dd, None, None, None
+            return dx, dw, ds, dd, None, None, None, None
         g = g.contiguous()
         if need[0] or (in_scale is not None and need[2]):
             dxs = _dgrad_raw(g, weight, wscale, up, down, H, W, in_scale=out_scale)
@@ -351,10 +368,11 @@ class _ConvFunction(torch.autograd.Function):
         if out_scale is not None and need[3]:
             _, gy = rowscale_dot(g, y, None, want_out=False)
             dd = gy / out_scale
-        return dx, dw, ds, dd, None, None, None
+        return dx, dw, ds, dd, None, None, None, None
 
 
-def conv2d_autograd(x, weight, in_scale=None, out_scale=None, wscale=1.0, up=1, down=1):
+def conv2d_autograd(x, weight, in_scale=None, out_scale=None, wscale=1.0, up=1, down=1, cache=None):
     """Differentiable  out_scale * conv(in_scale * x, wscale * weight)  on the tcgen05 kernels: gradients of any order w.r.t. x,
-    weight [Cout,Cin,k,k], in_scale [B,Cin] and out_scale [B,Cout]."""
-    return _ConvFunction.apply(x, weight, in_scale, out_scale, float(wscale), int(up), int(down))
+    weight [Cout,Cin,k,k], in_scale [B,Cin] and out_scale [B,Cout].  cache: the owning module's dict of packed weight images
+    (pack_weights_cached), shared with its inference path."""
+    return _ConvFunction.apply(x, weight, in_scale, out_scale, float(wscale), int(up), int(down), cache)

@@ -66,10 +66,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 // One thread per (output row n, 8-channel K chunk): it reads the 8 x k*k source values (a contiguous 8*k*k run when the weight
 // is [Cout,Cin,k,k]; k*k-float runs that neighbouring threads continue when it is [Cin,Cout,k,k]) and writes one 16-byte unit
 // per tap, consecutive threads -> consecutive units.
-template <bool kBF16>
-__global__ void pack_conv_weights_kernel(const float *__restrict__ w, uint16_t *__restrict__ out, int Cout, int Cin, int k,
-                                         int n_tile, int n_tiles, int kblocks, float scale, int flip, int transpose_io) {
-  const int taps = k * k;
+template <bool kBF16, int taps>
+__global__ void __launch_bounds__(128) pack_conv_weights_kernel(const float *__restrict__ w, uint16_t *__restrict__ out, int Cout, int Cin,
+                                                                int n_tile, int n_tiles, int kblocks, float scale, int flip,
+                                                                int transpose_io) {
   const long total = (long)n_tiles * kblocks * (kCinBlk / 8) * n_tile;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long r = i;
@@ -79,19 +79,23 @@ __global__ void pack_conv_weights_kernel(const float *__restrict__ w, uint16_t *
     const int nt = (int)r;
     const int co = nt * n_tile + n, ci0 = kb * kCinBlk + chunk * 8;
     uint4 *dst = reinterpret_cast<uint4 *>(out) + (((long)nt * kblocks + kb) * taps * (kCinBlk / 8) + chunk) * n_tile + n;
+    float v[taps][8];      // all 8 x taps loads are issued before the first conversion
+#pragma unroll
     for (int tap = 0; tap < taps; ++tap) {
       const int src_tap = flip ? taps - 1 - tap : tap;
-      float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int ci = ci0 + e;
-        v[e] = 0.0f;
+        v[tap][e] = 0.0f;
         if (co < Cout && ci < Cin)
-          v[e] = scale * __ldg(transpose_io ? w + ((long)ci * Cout + co) * taps + src_tap : w + ((long)co * Cin + ci) * taps + src_tap);
+          v[tap][e] = __ldg(transpose_io ? w + ((long)ci * Cout + co) * taps + src_tap : w + ((long)co * Cin + ci) * taps + src_tap);
       }
-      dst[(long)tap * (kCinBlk / 8) * n_tile] = make_uint4(pack2<kBF16>(v[0], v[1]), pack2<kBF16>(v[2], v[3]), pack2<kBF16>(v[4], v[5]),
-                                                           pack2<kBF16>(v[6], v[7]));
     }
+#pragma unroll
+    for (int tap = 0; tap < taps; ++tap)
+      dst[(long)tap * (kCinBlk / 8) * n_tile] =
+          make_uint4(pack2<kBF16>(scale * v[tap][0], scale * v[tap][1]), pack2<kBF16>(scale * v[tap][2], scale * v[tap][3]),
+                     pack2<kBF16>(scale * v[tap][4], scale * v[tap][5]), pack2<kBF16>(scale * v[tap][6], scale * v[tap][7]));
   }
 }
 
@@ -355,12 +359,14 @@ extern "C" int hav_conv_pack_weights(void *wpack, const float *w, int cout, int 
   const int flip = (transpose_io >> 1) & 1;
   transpose_io &= 1;
   const int n_tile = conv_n_tile(cout, up), n_tiles = (cout + n_tile - 1) / n_tile, kblocks = (cin + conv::kCinBlk - 1) / conv::kCinBlk;
-  if (precision == HAV_PREC_BF16)
-    conv::pack_conv_weights_kernel<true><<<296, 256, 0, (cudaStream_t)stream>>>(w, (uint16_t *)wpack, cout, cin, ksize, n_tile, n_tiles,
-                                                                                kblocks, scale, flip, transpose_io);
-  else
-    conv::pack_conv_weights_kernel<false><<<296, 256, 0, (cudaStream_t)stream>>>(w, (uint16_t *)wpack, cout, cin, ksize, n_tile, n_tiles,
-                                                                                 kblocks, scale, flip, transpose_io);
+  const long units = (long)n_tiles * kblocks * (conv::kCinBlk / 8) * n_tile;
+  const int grid = (int)((units + 127) / 128 < 148 * 16 ? (units + 127) / 128 : 148 * 16);
+  auto go = [&](auto kern) {
+    kern<<<grid, 128, 0, (cudaStream_t)stream>>>(w, (uint16_t *)wpack, cout, cin, n_tile, n_tiles, kblocks, scale, flip, transpose_io);
+  };
+  const bool bf = precision == HAV_PREC_BF16;
+  if (ksize == 3) bf ? go(conv::pack_conv_weights_kernel<true, 9>) : go(conv::pack_conv_weights_kernel<false, 9>);
+  else bf ? go(conv::pack_conv_weights_kernel<true, 1>) : go(conv::pack_conv_weights_kernel<false, 1>);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? HAV_OK : (int)e;
 }

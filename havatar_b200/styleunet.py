@@ -118,20 +118,17 @@ def invalidate_caches():
 
 
 class _PackCache:
-    """Packed 16-bit weight image of a conv parameter, rebuilt when the parameter is modified in place or replaced."""
+    """Packed 16-bit weight images of one conv parameter (one per layout / precision), rebuilt when the parameter is modified
+    in place or replaced; shared by the module's inference path and its differentiable path (conv.pack_weights_cached)."""
 
     def __init__(self):
-        self.key, self.packed = None, None
+        self.store = {}
 
     def get(self, weight, scale, up):
-        key = (weight.data_ptr(), weight._version, str(weight.device), up, _EPOCH[0])
-        if key != self.key:
-            w = weight.detach()
-            if w.dim() == 5:
-                w = w[0]
-            self.packed = hconv.pack_weights(w.float(), scale, up=2 if up else 1)
-            self.key = key
-        return self.packed
+        w = weight.detach()
+        if w.dim() == 5:
+            w = w[0]
+        return hconv.pack_weights_cached(w.float(), scale, up=2 if up else 1, cache=self.store)
 
 
 class EqualConv2d(nn.Module):

@@ -62,7 +62,7 @@ def conv_layer(m, x):
     conv = mods[0]
     k = conv.weight.shape[-1]
     if _native(x) and k in (1, 3) and ((conv.stride == 1 and conv.padding == k // 2) or (conv.stride == 2 and conv.padding == 0 and k == 3)):
-        out = hconv.conv2d_autograd(x, conv.weight, None, None, conv.scale, down=conv.stride)
+        out = hconv.conv2d_autograd(x, conv.weight, None, None, conv.scale, down=conv.stride, cache=conv._cache.store)
         if conv.bias is not None:
             out = out + conv.bias[None, :, None, None]
     else:
@@ -81,7 +81,7 @@ def mod_conv(m, x, style):
         d = None
         if m.demodulate:                                                   # :256-258
             d = torch.rsqrt((s * s) @ (w0 * w0).sum(dim=(2, 3)).t() * (m.scale * m.scale) + m.eps)
-        out = hconv.conv2d_autograd(x, w0, s, d, m.scale, up=2 if m.upsample else 1)
+        out = hconv.conv2d_autograd(x, w0, s, d, m.scale, up=2 if m.upsample else 1, cache=m._cache.store)
         return m.blur(out) if m.upsample else out                          # :271-277
     w = m.weight[0] * m.scale                                              # [Cout,Cin,k,k]
     x = x * s[:, :, None, None]

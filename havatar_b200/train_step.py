@@ -288,6 +288,9 @@ class Graphed:
                     grp.opt.zero_grad(set_to_none=True)
             step.pre_step()
             for name, fn, graphable in step.parts():
+                # derived-tensor caches (packed weights, ...) must not cross a capture boundary: a hit on an eagerly built
+                # entry would leave the graph without the kernel that refreshes it, and eager code must not reuse graph memory
+                styleunet.invalidate_caches()
                 if graphable:
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=self.stream):
@@ -296,6 +299,7 @@ class Graphed:
                     g.replay()                          # the captured iteration has not executed yet: run it once
                 else:
                     fn(self.static)
+            styleunet.invalidate_caches()
         torch.cuda.current_stream(dev).wait_stream(self.stream)
 
     def __call__(self, batch):
@@ -308,8 +312,9 @@ class Graphed:
                 self.graphs[name].replay()
                 out.update(self.outs[name] or {})
             else:
+                styleunet.invalidate_caches()       # replays changed parameters behind their version counters
                 out.update(fn(self.static) or {})
-        styleunet.invalidate_caches()       # replays changed parameters behind their version counters
+        styleunet.invalidate_caches()
         return out
 
 
