@@ -58,31 +58,39 @@ def _distributed():
 
 
 class _Group:
-    """Parameters + Adam + (when distributed) the bucketed gradient all-reduce of one optimiser.  capturable=True keeps the
-    step count and the learning rate on the device so the whole update can live inside a CUDA graph."""
+    """Parameters + Adam + (when distributed) the bucketed gradient all-reduce of one optimiser.  On a CUDA device the
+    parameters, gradients and both moments are flat buffers and the update is the one-pass hav_adam_flat kernel
+    (parallel.FlatAdam; step count and learning rate on the device, so the whole update can live inside a CUDA graph)."""
 
     def __init__(self, modules, lr, betas=(0.9, 0.999), capturable=False):
         self.params = [p for m in modules for p in m.parameters()]
-        self.sync = parallel.GradSync(self.params) if _distributed() else None
-        self.capturable = capturable
-        if capturable:
-            lr = torch.tensor(float(lr), dtype=torch.float32, device=self.params[0].device)
-        self.opt = torch.optim.Adam(self.params, lr=lr, betas=betas, capturable=capturable, foreach=True)
+        self.flat = self.params[0].is_cuda
+        if self.flat:
+            self.opt = parallel.FlatAdam(self.params, lr, betas)
+            self.sync = parallel.GradSync(self.params, layout=self.opt.layout) if _distributed() else None
+        else:       # construction on a CPU device (checkpoint / shape inspection): the steps themselves need the CUDA kernels
+            self.sync = parallel.GradSync(self.params) if _distributed() else None
+            self.opt = torch.optim.Adam(self.params, lr=lr, betas=betas)
 
     def set_lr(self, lr):
-        for grp in self.opt.param_groups:
-            if self.capturable:
-                grp["lr"].fill_(float(lr))
-            else:
+        if self.flat:
+            self.opt.set_lr(lr)
+        else:
+            for grp in self.opt.param_groups:
                 grp["lr"] = float(lr)
 
     def step(self):
+        """All-reduce (if distributed), Adam update, gradients cleared."""
         if self.sync is not None:
             self.sync.finish()
         self.opt.step()
+        if not self.flat:
+            self.zero_grad()
 
     def zero_grad(self):
-        if self.sync is not None:
+        if self.flat:
+            self.opt.zero_grad()
+        elif self.sync is not None:
             self.sync.zero_grad()
         else:
             self.opt.zero_grad(set_to_none=True)
@@ -152,8 +160,7 @@ class StageOneStep:
             fake = rgb[..., :3].reshape(B, P, P, 3).permute(0, 3, 1, 2).contiguous()
             loss = loss + 0.05 * g_nonsaturating_loss(self.disc(fake))       # in the slot of the 0.05-weighted patch term (:144)
         loss.backward()                                                                                             # :149
-        self.g.step()                                                                                               # :151
-        self.g.zero_grad()
+        self.g.step()                                                                                               # :151 (clears the gradients)
         d_loss = None
         if self.disc is not None:
             self.d.requires_grad(True)
@@ -161,7 +168,6 @@ class StageOneStep:
             d_loss = d_logistic_loss(self.disc(real), self.disc(fake.detach()))
             d_loss.backward()
             self.d.step()
-            self.d.zero_grad()
         return {"loss": loss.detach(), "d_loss": None if d_loss is None else d_loss.detach()}
 
 
@@ -228,7 +234,6 @@ class StageTwoStep:
         d_loss = d_logistic_loss(self.disc(gt_hr), self.disc(fake)) * self.gan_w
         d_loss.backward()
         self.d.step()
-        self.d.zero_grad()
         return {"d_loss": d_loss.detach()}
 
     def r1_step(self, batch):                                                                                   # :233-240
@@ -240,7 +245,6 @@ class StageTwoStep:
         r1_loss = d_r1_loss(pred, real) * self.gan_w
         (self.r1 / 2 * r1_loss * self.d_reg_every + 0 * pred[0]).sum().backward()
         self.d.step()
-        self.d.zero_grad()
         return {"r1": r1_loss.detach()}
 
     def g_step(self, batch):                                                                                    # :243-303
@@ -258,7 +262,6 @@ class StageTwoStep:
         g_loss.backward()
         self.g.step()
         self.nerf.step()
-        self.g.zero_grad(), self.nerf.zero_grad()
         with torch.no_grad():                                                                                   # :303
             pe, pg = list(self.g_ema.parameters()), list(self.generator.parameters())
             torch._foreach_mul_(pe, self.accum)
@@ -283,8 +286,8 @@ class Graphed:
         with torch.cuda.stream(self.stream):
             for _ in range(warmup):                     # allocator / cuDNN / Adam-state warm-up on the capture stream
                 step(self.static)
-            for grp in step.groups():                   # gradients must be (re)allocated from the graphs' private pool
-                if grp.sync is None:
+            for grp in step.groups():                   # non-flat groups: gradients must be (re)allocated from the graphs' pool
+                if not grp.flat and grp.sync is None:
                     grp.opt.zero_grad(set_to_none=True)
             step.pre_step()
             for name, fn, graphable in step.parts():

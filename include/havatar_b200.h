@@ -20,6 +20,7 @@
  *                            reference calls cuDNN grouped conv2d / conv_transpose2d through model/op/conv2d_gradfix.py:22-75
  *   hav_pack_planes      <- model/nerf_model.py:85 (plane stacking; layout change for the bf16 path)
  *   hav_conv2d_wgrad     <- autograd's convolution_backward under the same modules (model/op/conv2d_gradfix.py:94-227)
+ *   hav_adam_flat        <- torch.optim.Adam.step() in the training loops (train_avatar.py:151, train_avatarHD.py:231,279-280)
  * INTEGRATION.md shows the reference-side binding for each.
  */
 #ifndef HAVATAR_B200_H_
@@ -250,6 +251,16 @@ typedef struct hav_conv_wgrad_args {
 int hav_conv2d_wgrad(const hav_conv_wgrad_args *args, void *stream);
 int hav_rowscale_dot(float *out, float *dot, const float *a, const float *x, const float *scale, int64_t rows, int64_t n,
                      void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Adam over flat fp32 buffers (replaces the torch.optim.Adam steps of train_avatar.py:151 and train_avatarHD.py:231,279-280;
+ * same update rule as torch/optim/adam.py with amsgrad=False, weight_decay=0, maximize=False).
+ *   state[0] = number of steps taken so far (incremented by the call), state[1] = learning rate -- device memory, so the call
+ *   can be captured in a CUDA graph.  grad is multiplied by grad_scale before use; zero_grad != 0 clears it in the same pass.
+ *   n must be a multiple of 4 and the buffers 16-byte aligned (pad the flat layout).
+ */
+int hav_adam_flat(float *param, float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float *state, float beta1, float beta2,
+                  float eps, float grad_scale, int zero_grad, void *stream);
 
 #ifdef __cplusplus
 }

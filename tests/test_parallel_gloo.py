@@ -38,13 +38,14 @@ def _loss(net, x, y, fidx):
     return ((net(x + net.codes[fidx][:, None, :]) - y) ** 2).mean()
 
 
-def _worker(rank, world, port, bucket_bytes, ret):
+def _worker(rank, world, port, bucket_bytes, use_layout, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         net = _net(seed=100 + rank)                             # different init per rank: the broadcast must fix that
         parallel.broadcast_parameters(net)
-        sync = parallel.GradSync(net.parameters(), bucket_bytes=bucket_bytes)
+        layout = parallel.FlatLayout(net.parameters()) if use_layout else None      # buckets = slices of one flat gradient buffer
+        sync = parallel.GradSync(net.parameters(), bucket_bytes=bucket_bytes, layout=layout)
         opt = torch.optim.Adam(net.parameters(), lr=1e-2)
         x, y = _data()
         lo, hi = shard.frames_of_rank(6, world, rank)
@@ -57,6 +58,9 @@ def _worker(rank, world, port, bucket_bytes, ret):
                 grads = {k: p.grad.clone() for k, p in net.named_parameters()}
             opt.step()
             sync.zero_grad()
+        if layout is not None:
+            layout.check()
+            assert all(p.data_ptr() >= layout.flat_p.data_ptr() for p in net.parameters())
         if rank == 0:
             ret["grads"] = {k: v.numpy() for k, v in grads.items()}
             ret["weights"] = {k: p.detach().numpy() for k, p in net.named_parameters()}
@@ -67,12 +71,12 @@ def _worker(rank, world, port, bucket_bytes, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("bucket_bytes", [64 << 20, 4096])
-def test_bucketed_allreduce_equals_full_batch(bucket_bytes):
+@pytest.mark.parametrize("bucket_bytes,use_layout", [(64 << 20, False), (4096, False), (4096, True)])
+def test_bucketed_allreduce_equals_full_batch(bucket_bytes, use_layout):
     world, port = 2, _free_port()
     with mp.Manager() as m:
         ret = m.dict()
-        mp.spawn(_worker, args=(world, port, bucket_bytes, ret), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, bucket_bytes, use_layout, ret), nprocs=world, join=True)
         got_g, got_w = dict(ret["grads"]), dict(ret["weights"])
         nb, nc, early = ret["buckets"], ret["collectives"], ret["issued_in_backward"]
     net = _net(seed=100)                                        # rank 0's init is what the broadcast spreads
