@@ -123,6 +123,48 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def reference_formulation_stage_one(dev, train_step):
+    import torch
+
+    from havatar_b200 import render as hrender
+    from havatar_b200 import styleunet_train
+    from oracle import render_oracle_torch as rt
+
+    def aten_render(ray_batch, bg, inv_head_T, planes, wvol, weights, num_coarse, num_fine=0, boxes=None, t_rand=None,
+                    noise_coarse=None, u_rand=None, noise_fine=None, precision=None):
+        bx = tuple(torch.tensor(b, dtype=torch.float32, device=ray_batch.device) for b in boxes)
+        o = rt.render_rays.__wrapped__(ray_batch, bg, inv_head_T, planes, wvol, weights, bx, num_coarse, num_fine, t_rand=t_rand,
+                                       noise_coarse=noise_coarse, u_rand=u_rand, noise_fine=noise_fine, chunk=2048,
+                                       device=ray_batch.device, to_numpy=False)
+        un = lambda t: None if t is None else (t.unsqueeze(-1) if t.dim() == 2 else t)
+        return hrender.RenderOut(o["rgb_coarse"], un(o["depth_coarse"]), un(o["acc_coarse"]), un(o["weights_max"]), o["rgb_fine"],
+                                 un(o["depth_fine"]), un(o["acc_fine"]), None)
+
+    saved, train_step.FLAT_ADAM[0] = hrender.render_rays_autograd, False
+    hrender.render_rays_autograd = aten_render
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        st = train_step.StageOneStep(n_frames=4, device=dev)
+        batch = train_step.synthetic_batch(1, 4, dev, seed=0, patch=64)
+        with styleunet_train.library_convs():
+            for _ in range(2):
+                st(batch)
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for _ in range(3):
+                res = st(batch)
+            b_.record()
+            torch.cuda.synchronize()
+        return {"ms_per_step": a_.elapsed_time(b_) / 3, "finite": bool(torch.isfinite(res["loss"])),
+                "what": "same iteration with the reference's formulation: ATen render + torch autograd (fp32, 2048-ray chunks), cuDNN "
+                        "convolutions (TF32 allowed, torch default), torch.optim.Adam, eager; our upfirdn2d / fused_bias_act kernels"}
+    finally:
+        hrender.render_rays_autograd = saved
+        train_step.FLAT_ADAM[0] = True
+        torch.cuda.empty_cache()
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -316,6 +358,14 @@ def run_ours(args):
             best = min((entry[m] for m in modes), key=lambda e: e["ms_per_step"])
             entry.update(ms_per_step=best["ms_per_step"], frames_per_sec=best["frames_per_sec"])
             train[name] = entry
+        # the reference's own formulation of the stage-one iteration on this GPU, as far as it can be had here: render through
+        # the ATen call sequence + torch autograd (oracle/render_oracle_torch.py, 2048-ray chunks like chunksize // B), cuDNN
+        # convolutions through autograd, torch.optim.Adam, eager launches.  Rank 0 only, no gradient exchange.
+        if rank == 0 and world == 1:
+            try:
+                train["stage_one_b4_patch64"]["reference_formulation"] = reference_formulation_stage_one(dev, train_step)
+            except Exception as exc:
+                train["stage_one_b4_patch64"]["reference_formulation"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
       except Exception as exc:
         train["error"] = "%s: %s" % (type(exc).__name__, exc)
 

@@ -57,6 +57,9 @@ def _distributed():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
+FLAT_ADAM = [True]      # bench.py's reference-formulation leg switches the steps back to torch.optim.Adam
+
+
 class _Group:
     """Parameters + Adam + (when distributed) the bucketed gradient all-reduce of one optimiser.  On a CUDA device the
     parameters, gradients and both moments are flat buffers and the update is the one-pass hav_adam_flat kernel
@@ -64,7 +67,7 @@ class _Group:
 
     def __init__(self, modules, lr, betas=(0.9, 0.999), capturable=False):
         self.params = [p for m in modules for p in m.parameters()]
-        self.flat = self.params[0].is_cuda
+        self.flat = self.params[0].is_cuda and FLAT_ADAM[0]
         if self.flat:
             self.opt = parallel.FlatAdam(self.params, lr, betas)
             self.sync = parallel.GradSync(self.params, layout=self.opt.layout) if _distributed() else None
