@@ -33,6 +33,7 @@ constexpr int kAChunk = kMa * 16 + 16;              // K-chunk stride of the A t
 constexpr int kABytes = (kTH * kTW / 8) * kAChunk;    // 33024
 constexpr int kStageThreads = 512, kThreads = kStageThreads + 32;   // 16 staging warps: the loads are latency-bound, not issue-bound
 constexpr int kTmemCols = 512;
+constexpr int kTmemA = 9 * kNb;                    // columns [432, 496): the A tile, 8 K-steps x 8 columns (two bf16 per column)
 constexpr uint32_t kBMajorMN = 1u << 16;
 constexpr int kSmScale = 128, kSmA = 1024;         // [0,128): mbarriers + TMEM slot; [128,1024): B-side scale tables
 
@@ -57,6 +58,7 @@ struct WgDev {
   int a_h, a_w, b_h, b_w;             // spatial sizes; position tiles run over the A tensor
   int pad;                            // stride 1: B coordinate = position + tap - pad;  stride 2: 2 * position + tap
   int out_t;                          // 0: dw[(a_ch * Cb + b_ch) * taps + tap]   1: dw[(b_ch * Ca + a_ch) * taps + tap]
+  int dbg;                            // HAV_WG_DEBUG: 1 = skip operand staging after the first ring fill (timing experiments only)
   int a_vec, dw_vec;                  // 16-byte vector loads of the A tensor / vector reductions into dw are aligned
   int tiles_x, tiles_y, ntiles, nsplit, a_tiles, b_tiles;
   const float *pa, *pb, *sa, *sb;     // tensors [B,C,h,w] and their per-(sample, channel) scales [B,C] (NULL = 1)
@@ -72,6 +74,12 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
 }
 __device__ __forceinline__ void red_add(float *p, float a) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+
+// 128 rows x 256 bits (one K = 16 step of a 16-bit A operand) from a K-major shared-memory matrix into TMEM lanes 0..127,
+// 8 columns: the layout tcgen05.mma reads an A operand from when it is given a TMEM address
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
 }
 
 #define HAV_TMEM_LD8(r, taddr)                                                                          \
@@ -118,9 +126,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const WgDev P) 
         mbar_wait_spin(bar_full + st * 8, (it / G::kStages) & 1);
         tc_fence_after();
         const uint32_t A0 = smem_base + kSmA + st * kABytes, B0 = smem_base + G::kSmB + st * G::kBBytes;
+        // the A tile goes to TMEM once (8 copies of 128 x 32 B): each of its K-steps is then read by `taps` MMAs without
+        // touching shared memory again (an SS-mode M128 x N48 MMA is bound by its 4 KB A-operand fetch, not by the math).
+        // tcgen05.cp and tcgen05.mma of one thread execute in issue order, so the copies of tile t+1 cannot overtake the
+        // MMAs of tile t that still read these columns.
+#pragma unroll
+        for (int r = 0; r < kTH; ++r) tmem_cp_128x256b(tmem_acc + kTmemA + r * 8, smem_desc(A0 + 2 * r * kAChunk, kAChunk, 128));
 #pragma unroll 1
         for (int r = 0; r < kTH; ++r) {
-          const uint64_t adesc = smem_desc(A0 + 2 * r * kAChunk, kAChunk, 128);
 #pragma unroll
           for (int tap = 0; tap < taps; ++tap) {
             const int kh = tap / KS, kw = tap - kh * KS;
@@ -128,7 +141,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const WgDev P) 
             if (STRIDE == 1) b_addr = B0 + ((r + kh) * G::kW + kw) * 16;
             else b_addr = B0 + (((kh & 1) << 1) | (kw & 1)) * G::kPlaneBytes + ((r + (kh >> 1)) * G::kW + (kw >> 1)) * 16;
             // MN-major: LBO = distance between 8-pixel K groups (128 B), SBO = distance between 8-channel groups (one chunk)
-            umma_ss(tmem_acc + tap * kNb, adesc, smem_desc(b_addr, 128, G::kChunk), idesc, (it > 0 || r > 0) ? 1u : 0u);
+            umma_ts(tmem_acc + tap * kNb, tmem_acc + kTmemA + r * 8, smem_desc(b_addr, 128, G::kChunk), idesc, (it > 0 || r > 0) ? 1u : 0u);
           }
         }
         umma_commit(bar_free + st * 8);
@@ -150,6 +163,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const WgDev P) 
       const int ty = sp % P.tiles_y;
       const int b = sp / P.tiles_y;
       const int Y0 = ty * kTH, X0 = tx * kTW;
+      if (P.dbg == 1 && it >= G::kStages) {   // experiment: the MMA side alone (operands of the first ring fill are reused)
+        mbar_wait_spin(bar_free + st * 8, ((it / G::kStages) - 1) & 1);
+        mbar_arrive_wg(bar_full + st * 8);
+        continue;
+      }
       // ---- A loads first (they do not depend on the ring slot): 8 channels of this warp, this lane's row and 4-px quarter
       float4 va[kMa / 16];
       float as[kMa / 16];
@@ -375,6 +393,10 @@ extern "C" int hav_conv2d_wgrad(const hav_conv_wgrad_args *a, void *stream) {
   if (nsplit < 1) nsplit = 1;
   P.nsplit = (int)nsplit;
   P.dw = a->dw, P.wscale = a->wscale;
+  {
+    static const int dbg = getenv("HAV_WG_DEBUG") != nullptr ? atoi(getenv("HAV_WG_DEBUG")) : 0;
+    P.dbg = dbg;
+  }
   P.a_vec = (P.a_w & 3) == 0 && ((uintptr_t)P.pa & 15) == 0;   // every 4-px quarter of a tile row is a 16-byte aligned float4
   P.dw_vec = (((size_t)a->cin * taps) & 3) == 0 && ((uintptr_t)a->dw & 15) == 0;
   dim3 grid((unsigned)blocks, (unsigned)nsplit);
