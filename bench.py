@@ -271,6 +271,21 @@ def run_ours(args):
     e2e_ms = (time.perf_counter() - e0) * 1e3 / args.steps
     h2d, d2h = hr.h2d_bytes, hr.d2h_bytes
     assert abs(float(res["acc_coarse"].mean()) - acc_mean) < 1e-6
+    # the same with only the maps the reference's validation loop reads back (rgb[..., :3], depth, acc); secondary number
+    hi_ = render.PipelinedHostRenderer(sc["weights"], sc["wvol"], S, 0, precision=args.precision, device=dev, maps="image")
+    for _ in range(3):
+        hi_.submit(**host)
+    hi_.drain()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        hi_.submit(**host)
+    res_i = hi_.drain()
+    torch.cuda.synchronize()
+    e2e_img_ms = (time.perf_counter() - e0) * 1e3 / args.steps
+    e2e_img_d2h = hi_.d2h_bytes
+    assert abs(float(res_i["acc_coarse"].mean()) - acc_mean) < 1e-6 and res_i["rgb_coarse"].shape[-1] == 3
+    del hi_
     # the same, strictly serial (no overlap between frames), for reference
     hs = render.HostRenderer(sc["weights"], sc["wvol"], S, 0, precision=args.precision, device=dev)
     hs(**host)
@@ -428,6 +443,8 @@ def run_ours(args):
         "e2e": {"value": world * R / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "serial_ms_per_step": e2e_serial_ms,
+                "image_maps_only": {"value": R / (e2e_img_ms * 1e-3), "ms_per_step": e2e_img_ms, "d2h_bytes_per_step": e2e_img_d2h,
+                                    "note": "per-rank; downloads rgb[..., :3], depth, acc only (what train_avatar.py:182-218 reads back)"},
                 "api": "havatar_b200.render.PipelinedHostRenderer (pinned host in/out; H2D, hav_render_forward and D2H of consecutive frames overlap)"},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",

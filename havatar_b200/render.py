@@ -330,7 +330,13 @@ class PipelinedHostRenderer:
 
     DEPTH = 2
 
-    def __init__(self, weights, wvol, num_coarse, num_fine=0, boxes=None, precision="fp16", device="cuda"):
+    def __init__(self, weights, wvol, num_coarse, num_fine=0, boxes=None, precision="fp16", device="cuda", maps="all"):
+        """maps="all": every rendered map comes back (67-channel rgb + feature map, depth, acc, weights_max of each pass);
+        maps="image": what the reference's validation loop reads back (train_avatar.py:182-218: rgb[..., :3], depth, acc) --
+        the 64 feature channels are consumed on the device by the StyleUNet (avatarHD_reenactment.py:160-166)."""
+        if maps not in ("all", "image"):
+            raise ValueError("maps must be 'all' or 'image'")
+        self.maps = maps
         self.dev = torch.device(device)
         self.weights = {k: torch.as_tensor(v).to(self.dev, torch.float32).contiguous() for k, v in weights.items()}
         self.wvol = torch.as_tensor(wvol).to(self.dev, torch.float32).contiguous()
@@ -365,14 +371,17 @@ class PipelinedHostRenderer:
             sl["out"] = render_rays(a["ray_batch"], a["background_prior"], a["inv_head_T"], a["planes"], self.wvol,
                                     self.weights, self.num_coarse, self.num_fine, boxes=self.boxes, precision=self.precision,
                                     out=sl["out"], **{k: a[k] for k in rand if rand[k] is not None})
+            send = {k: v for k, v in sl["out"]._asdict().items() if v is not None}
+            if self.maps == "image":      # compact the colour channels on the device; the feature channels stay there
+                send = {k: (v[..., :3].contiguous() if k.startswith("rgb") else v) for k, v in send.items() if k != "weights_max"}
+            sl["send"] = send
             sl["ev_comp"].record(self.s_comp)
         with torch.cuda.stream(self.s_d2h):
             self.s_d2h.wait_event(sl["ev_comp"])
-            if sl["host"] is None or sl["host"]["rgb_coarse"].shape != sl["out"].rgb_coarse.shape:
-                sl["host"] = {k: torch.empty(v.shape, dtype=torch.float32, pin_memory=True)
-                              for k, v in sl["out"]._asdict().items() if v is not None}
+            if sl["host"] is None or any(sl["host"][k].shape != v.shape for k, v in send.items()):
+                sl["host"] = {k: torch.empty(v.shape, dtype=torch.float32, pin_memory=True) for k, v in send.items()}
             for k, h in sl["host"].items():
-                h.copy_(getattr(sl["out"], k), non_blocking=True)
+                h.copy_(send[k], non_blocking=True)
                 self.d2h_bytes += h.numel() * 4
             sl["ev_out"].record(self.s_d2h)
         sl["busy"] = True
