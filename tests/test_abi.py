@@ -80,3 +80,45 @@ def test_cpu_tensors_are_rejected():
         op.fused_leaky_relu(torch.zeros(1, 2, 3, 3))
     with pytest.raises(RuntimeError):
         op.upfirdn2d(torch.zeros(1, 1, 4, 4), torch.ones(2, 2))
+
+
+def test_training_entry_points_validate_before_any_launch(lib):
+    """hav_conv2d_wgrad / hav_rowscale_dot / hav_adam_flat: argument errors are reported without touching the device."""
+    assert lib.hav_conv2d_wgrad(None, None) == -1
+    a = _lib.ConvWgradArgs()
+    a.struct_bytes = C.sizeof(_lib.ConvWgradArgs) - 4
+    assert lib.hav_conv2d_wgrad(C.byref(a), None) == -5
+    a.struct_bytes = C.sizeof(_lib.ConvWgradArgs)
+    a.batch, a.cin, a.cout, a.in_h, a.in_w, a.ksize, a.up, a.down = 1, 8, 8, 0, 4, 3, 1, 1
+    assert lib.hav_conv2d_wgrad(C.byref(a), None) == -2                       # empty image
+    a.in_h, a.ksize = 4, 5
+    assert lib.hav_conv2d_wgrad(C.byref(a), None) == -5                       # only 1x1 and 3x3
+    a.ksize, a.up, a.down = 3, 2, 2
+    assert lib.hav_conv2d_wgrad(C.byref(a), None) == -5                       # up and down together
+    a.up, a.down = 1, 1
+    assert lib.hav_conv2d_wgrad(C.byref(a), None) == -1                       # dw is NULL
+    assert lib.hav_rowscale_dot(None, None, None, None, None, 4, 4, None) == -1
+    assert lib.hav_adam_flat(None, None, None, None, 8, None, 0.9, 0.999, 1e-8, 1.0, 1, None) == -1
+    buf = (C.c_float * 16)()
+    p = C.cast(buf, C.c_void_p)
+    assert lib.hav_adam_flat(p, p, p, p, 6, p, 0.9, 0.999, 1e-8, 1.0, 1, None) == -2     # n must be a multiple of 4
+
+
+def test_flat_layout_views_on_cpu():
+    """parallel.FlatLayout is pure tensor plumbing: parameters and gradients become views of two flat buffers."""
+    import torch
+    from torch import nn
+
+    from havatar_b200 import parallel
+
+    net = nn.Sequential(nn.Linear(5, 7), nn.Linear(7, 3))
+    want = [p.detach().clone() for p in net.parameters()]
+    lay = parallel.FlatLayout(net.parameters())
+    assert lay.numel % 32 == 0 and all(o % 32 == 0 for o in lay.offsets)
+    for p, w in zip(net.parameters(), want):
+        assert torch.equal(p.detach(), w) and p.grad is not None and float(p.grad.abs().sum()) == 0.0
+    net(torch.randn(4, 5)).sum().backward()
+    lay.check()
+    assert float(lay.flat_g.abs().sum()) > 0.0
+    lay.flat_p.zero_()
+    assert all(float(p.detach().abs().sum()) == 0.0 for p in net.parameters())
