@@ -123,6 +123,84 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_train_legs(args, torch, dist, dev, rank, world, barrier, headline):
+    """The two training iterations (BASELINE.json configs[2] and configs[4]) on every rank.  A watchdog guards the headline: if
+    these legs have not finished by the deadline (a wedged collective, say), rank 0 prints the headline JSON line it already has
+    with train = {"error": ...} and every rank exits, so the render numbers can never be lost to the secondary legs."""
+    import threading
+
+    def bail():
+        if headline is not None:
+            out = dict(headline)
+            out.pop("train_note", None)
+            out["train"] = {"error": "training legs did not finish within %d s; skipped" % args.train_deadline}
+            print(json.dumps(out), flush=True)
+        os._exit(0)
+
+    dog = threading.Timer(args.train_deadline, bail)
+    dog.daemon = True
+    dog.start()
+    # ---- the two training steps (BASELINE.json configs[2] and configs[4]): per-rank frames, gradients all-reduced over NCCL
+    #      in buckets from inside backward (havatar_b200/parallel.py); device-timed, max over ranks
+    train = {}
+    if not args.no_train:
+      try:
+        from havatar_b200 import train_step
+
+        torch.cuda.empty_cache()
+        modes = ("eager", "graph") if args.train_mode == "both" else (args.train_mode,)
+        # stage two runs its R1 pass every 16th iteration: warm up through the first one, then time one full period of 16
+        for name, mk, mkb, frames, n_warm, n_t in (
+                ("stage_one_b4_patch64", lambda c: train_step.StageOneStep(n_frames=4 * world, device=dev, capturable=c),
+                 lambda: train_step.synthetic_batch(1, 4, dev, seed=rank, patch=64, frame_offset=4 * rank), 4, 3, max(3, min(args.steps, 10))),
+                ("stage_two_b1_128_to_512", lambda c: train_step.StageTwoStep(n_frames=world, device=dev, capturable=c),
+                 lambda: train_step.synthetic_batch(2, 1, dev, seed=rank, render_size=128, gen_size=512, frame_offset=rank), 1, 16, 16)):
+            entry = {"frames_per_gpu": frames}
+            for mode in modes:
+                st, batch = mk(mode == "graph"), mkb()
+                run = train_step.Graphed(st, batch) if mode == "graph" else st
+                for _ in range(n_warm):
+                    run(batch)
+                barrier()
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record()
+                for _ in range(n_t):
+                    res_t = run(batch)
+                b_.record()
+                barrier()
+                ms = torch.tensor([a_.elapsed_time(b_) / n_t], dtype=torch.float64, device=dev)
+                if dist is not None:
+                    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                ok = all(bool(torch.isfinite(v)) for v in res_t.values() if v is not None)
+                syncs = [g_.sync for g_ in st.groups() if g_.sync is not None]
+                if dist is not None:      # replicas must still hold identical weights after the timed iterations
+                    chk = torch.stack([p_.detach().double().sum() for g_ in st.groups() for p_ in g_.params[:8]])
+                    lo_, hi_ = chk.clone(), chk.clone()
+                    dist.all_reduce(lo_, op=dist.ReduceOp.MIN), dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+                    ok = ok and bool((hi_ - lo_).abs().max() <= 1e-9 * hi_.abs().max().clamp_min(1.0))
+                entry[mode] = {"ms_per_step": float(ms), "frames_per_sec": world * frames * 1e3 / float(ms), "steps": n_t, "finite_and_in_sync": ok}
+                entry["allreduce_bytes_per_step"] = sum(s_.bytes_per_step for s_ in syncs)
+                entry["allreduce_buckets"] = sum(len(s_.buckets) for s_ in syncs)
+                del st, batch, run
+                torch.cuda.empty_cache()
+            best = min((entry[m] for m in modes), key=lambda e: e["ms_per_step"])
+            entry.update(ms_per_step=best["ms_per_step"], frames_per_sec=best["frames_per_sec"])
+            train[name] = entry
+        # the reference's own formulation of the stage-one iteration on this GPU, as far as it can be had here: render through
+        # the ATen call sequence + torch autograd (oracle/render_oracle_torch.py, 2048-ray chunks like chunksize // B), cuDNN
+        # convolutions through autograd, torch.optim.Adam, eager launches.  Rank 0 only, no gradient exchange.
+        if rank == 0 and world == 1:
+            try:
+                train["stage_one_b4_patch64"]["reference_formulation"] = reference_formulation_stage_one(dev, train_step)
+            except Exception as exc:
+                train["stage_one_b4_patch64"]["reference_formulation"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+      except Exception as exc:
+        train["error"] = "%s: %s" % (type(exc).__name__, exc)
+
+    dog.cancel()
+    return train
+
+
 def reference_formulation_stage_one(dev, train_step):
     import torch
 
@@ -256,8 +334,12 @@ def run_ours(args):
         del ref32
 
     # ---- timed region 2: end to end through the host-buffer API: every step uploads its inputs from pinned host
-    #      memory and downloads all rendered maps to pinned host memory; copies of neighbouring frames overlap the
-    #      render (PipelinedHostRenderer: H2D / compute / D2H streams, two buffer sets)
+    #      memory and downloads rendered maps to pinned host memory; copies of neighbouring frames overlap the
+    #      render (PipelinedHostRenderer: H2D / compute / D2H streams, two buffer sets).  Two variants: ALL maps (the
+    #      67-channel colour + feature map of the pass, depth, acc, weights_max: 73 MB per frame, PCIe-bound) and the
+    #      IMAGE maps the reference's callers read back on the host (rgb[..., :3], depth, acc: train_avatar.py:182-218;
+    #      the 64 feature channels are consumed on the device by the StyleUNet, avatarHD_reenactment.py:160-166).
+    #      The image variant is the headline `e2e`; the all-maps variant is reported next to it.
     hr = render.PipelinedHostRenderer(sc["weights"], sc["wvol"], S, 0, precision=args.precision, device=dev)
     for _ in range(3):
         hr.submit(**host)
@@ -268,10 +350,10 @@ def run_ours(args):
         hr.submit(**host)
     res = hr.drain()
     torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - e0) * 1e3 / args.steps
-    h2d, d2h = hr.h2d_bytes, hr.d2h_bytes
+    e2e_all_ms = (time.perf_counter() - e0) * 1e3 / args.steps
+    h2d, d2h_all = hr.h2d_bytes, hr.d2h_bytes
     assert abs(float(res["acc_coarse"].mean()) - acc_mean) < 1e-6
-    # the same with only the maps the reference's validation loop reads back (rgb[..., :3], depth, acc); secondary number
+    del hr, res
     hi_ = render.PipelinedHostRenderer(sc["weights"], sc["wvol"], S, 0, precision=args.precision, device=dev, maps="image")
     for _ in range(3):
         hi_.submit(**host)
@@ -282,8 +364,8 @@ def run_ours(args):
         hi_.submit(**host)
     res_i = hi_.drain()
     torch.cuda.synchronize()
-    e2e_img_ms = (time.perf_counter() - e0) * 1e3 / args.steps
-    e2e_img_d2h = hi_.d2h_bytes
+    e2e_ms = (time.perf_counter() - e0) * 1e3 / args.steps
+    d2h = hi_.d2h_bytes
     assert abs(float(res_i["acc_coarse"].mean()) - acc_mean) < 1e-6 and res_i["rgb_coarse"].shape[-1] == 3
     del hi_
     # the same, strictly serial (no overlap between frames), for reference
@@ -327,69 +409,15 @@ def run_ours(args):
       except Exception as exc:  # the secondary metric must never take the headline line down with it
         hd["error"] = "%s: %s" % (type(exc).__name__, exc)
 
-    # ---- the two training steps (BASELINE.json configs[2] and configs[4]): per-rank frames, gradients all-reduced over NCCL
-    #      in buckets from inside backward (havatar_b200/parallel.py); device-timed, max over ranks
-    train = {}
-    if not args.no_train:
-      try:
-        from havatar_b200 import train_step
-
-        torch.cuda.empty_cache()
-        modes = ("eager", "graph") if args.train_mode == "both" else (args.train_mode,)
-        # stage two runs its R1 pass every 16th iteration: warm up through the first one, then time one full period of 16
-        for name, mk, mkb, frames, n_warm, n_t in (
-                ("stage_one_b4_patch64", lambda c: train_step.StageOneStep(n_frames=4 * world, device=dev, capturable=c),
-                 lambda: train_step.synthetic_batch(1, 4, dev, seed=rank, patch=64, frame_offset=4 * rank), 4, 3, max(3, min(args.steps, 10))),
-                ("stage_two_b1_128_to_512", lambda c: train_step.StageTwoStep(n_frames=world, device=dev, capturable=c),
-                 lambda: train_step.synthetic_batch(2, 1, dev, seed=rank, render_size=128, gen_size=512, frame_offset=rank), 1, 16, 16)):
-            entry = {"frames_per_gpu": frames}
-            for mode in modes:
-                st, batch = mk(mode == "graph"), mkb()
-                run = train_step.Graphed(st, batch) if mode == "graph" else st
-                for _ in range(n_warm):
-                    run(batch)
-                barrier()
-                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a_.record()
-                for _ in range(n_t):
-                    res_t = run(batch)
-                b_.record()
-                barrier()
-                ms = torch.tensor([a_.elapsed_time(b_) / n_t], dtype=torch.float64, device=dev)
-                if dist is not None:
-                    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-                ok = all(bool(torch.isfinite(v)) for v in res_t.values() if v is not None)
-                syncs = [g_.sync for g_ in st.groups() if g_.sync is not None]
-                if dist is not None:      # replicas must still hold identical weights after the timed iterations
-                    chk = torch.stack([p_.detach().double().sum() for g_ in st.groups() for p_ in g_.params[:8]])
-                    lo_, hi_ = chk.clone(), chk.clone()
-                    dist.all_reduce(lo_, op=dist.ReduceOp.MIN), dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
-                    ok = ok and bool((hi_ - lo_).abs().max() <= 1e-9 * hi_.abs().max().clamp_min(1.0))
-                entry[mode] = {"ms_per_step": float(ms), "frames_per_sec": world * frames * 1e3 / float(ms), "steps": n_t, "finite_and_in_sync": ok}
-                entry["allreduce_bytes_per_step"] = sum(s_.bytes_per_step for s_ in syncs)
-                entry["allreduce_buckets"] = sum(len(s_.buckets) for s_ in syncs)
-                del st, batch, run
-                torch.cuda.empty_cache()
-            best = min((entry[m] for m in modes), key=lambda e: e["ms_per_step"])
-            entry.update(ms_per_step=best["ms_per_step"], frames_per_sec=best["frames_per_sec"])
-            train[name] = entry
-        # the reference's own formulation of the stage-one iteration on this GPU, as far as it can be had here: render through
-        # the ATen call sequence + torch autograd (oracle/render_oracle_torch.py, 2048-ray chunks like chunksize // B), cuDNN
-        # convolutions through autograd, torch.optim.Adam, eager launches.  Rank 0 only, no gradient exchange.
-        if rank == 0 and world == 1:
-            try:
-                train["stage_one_b4_patch64"]["reference_formulation"] = reference_formulation_stage_one(dev, train_step)
-            except Exception as exc:
-                train["stage_one_b4_patch64"]["reference_formulation"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
-      except Exception as exc:
-        train["error"] = "%s: %s" % (type(exc).__name__, exc)
-
-    t = torch.tensor([step_ms, kern_ms, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([step_ms, kern_ms, e2e_ms, e2e_all_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms, kern_ms, e2e_ms = [float(v) for v in t.tolist()]
+    step_ms, kern_ms, e2e_ms, e2e_all_ms = [float(v) for v in t.tolist()]
     if rank != 0:
+        tr = run_train_legs(args, torch, dist, dev, rank, world, barrier, None)
         if dist is not None:
+            if "error" in tr:
+                os._exit(0)
             dist.destroy_process_group()
         return
 
@@ -443,8 +471,9 @@ def run_ours(args):
         "e2e": {"value": world * R / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "serial_ms_per_step": e2e_serial_ms,
-                "image_maps_only": {"value": R / (e2e_img_ms * 1e-3), "ms_per_step": e2e_img_ms, "d2h_bytes_per_step": e2e_img_d2h,
-                                    "note": "per-rank; downloads rgb[..., :3], depth, acc only (what train_avatar.py:182-218 reads back)"},
+                "maps": "image: rgb[..., :3], depth, acc read back per frame (train_avatar.py:182-218); feature channels stay on the device",
+                "all_maps": {"value": world * R / (e2e_all_ms * 1e-3), "ms_per_step": e2e_all_ms, "d2h_bytes_per_step": d2h_all,
+                             "note": "same call downloading every map (67-channel colour + feature map, depth, acc, weights_max): PCIe / host-memory bound"},
                 "api": "havatar_b200.render.PipelinedHostRenderer (pinned host in/out; H2D, hav_render_forward and D2H of consecutive frames overlap)"},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
@@ -457,14 +486,19 @@ def run_ours(args):
                          "seconds": cpu_s},
         "reference_gpu_port": ref_gpu,
         "clocks": clocks,
-        "train": dict(train, note="one optimiser iteration per step (eager = ~1500 host launches; graph = the iteration replayed as CUDA graphs), synthetic data, LPIPS omitted (weights unavailable offline): stage one = "
+        "train_note": dict(note="one optimiser iteration per step (eager = ~1500 host launches; graph = the iteration replayed as CUDA graphs), synthetic data, LPIPS omitted (weights unavailable offline): stage one = "
                                   "train_avatar.py:112-158 on 4 frames x 64x64-ray patches per GPU (64+16 samples, fused render fwd+bwd, patch "
                                   "discriminator); stage two = train_avatarHD.py:201-303 on 1 frame per GPU (D step + G step, 128^2 render -> 512^2)"),
         "hd": dict(hd, note="HD frames/s = XY/YZ plane generators (StyleGAN_zxc) + 512x512x64 or 128x128x64 render + SWGAN_unet, "
                             "one frame per GPU, CUDA-graph replay, random-init weights, per-rank values (not max-reduced)"),
     }
+    note = line.pop("train_note")["note"]
+    train = run_train_legs(args, torch, dist, dev, rank, world, barrier, line)
+    line["train"] = dict(train, note=note)
     print(json.dumps(line), flush=True)
     if dist is not None:
+        if "error" in train:      # a rank that failed inside a training leg leaves its peers in a collective: do not wait for them
+            os._exit(0)
         dist.destroy_process_group()
 
 
@@ -477,6 +511,7 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--train-mode", default="both", choices=["both", "eager", "graph"],
                     help="training-step leg: eager launches, whole-iteration CUDA graphs (train_step.Graphed), or both")
+    ap.add_argument("--train-deadline", type=int, default=300, help="seconds after which the training legs are abandoned")
     ap.add_argument("--no-train", dest="no_train", action="store_true", help="skip the training-step measurement")
     ap.add_argument("--no-hd", dest="no_hd", action="store_true", help="skip the secondary HD frames/s measurement")
     args = ap.parse_args()
