@@ -16,8 +16,9 @@
 // up = 2 (conv_transpose2d stride 2, :264-277) is polyphase: a tile is 128 INPUT positions (i,j); the four output
 // parities out[2i+a, 2j+b] are four accumulators (TMEM column blocks) fed by the taps with kh = a (mod 2), kw = b (mod 2)
 // reading x[i - kh/2, j - kw/2] -- 9 tap-GEMMs per tile like a plain 3x3 conv, no multiplications by inserted zeros.
-// down = 2 (:279-287, after the blur) computes stride-1 positions and stores the even ones (4x MMA work on the few
-// encoder layers that use it; a space-to-depth variant is the next step).
+// down = 2 (:279-287, after the blur; also the data gradient of the transposed convolution) is polyphase too: a tile is 128
+// OUTPUT positions, the input patch is staged as its four parity planes x[2i+a, 2j+b] and tap (kh,kw) reads plane
+// (kh&1, kw&1) shifted by (kh>>1, kw>>1) -- 9 tap-GEMMs per tile, no stride-1 positions computed and thrown away.
 #include "tc_common.cuh"
 
 namespace hav {
@@ -32,11 +33,15 @@ constexpr int kBStages = 4;
 constexpr int kBSlotBytes = kNTileMax * kCinBlk * 2;   // 16 KB
 constexpr int kMaxHaloPx = (kTileH + 2) * (kTileW + 2);   // 180
 constexpr int kASlotBytes = (kCinBlk / 8) * kMaxHaloPx * 16;   // 23040
+// stride-2 (polyphase) variant: the input patch is staged as its four parity planes x[2i+a, 2j+b] of (16+1) x (8+1) pixels
+constexpr int kDnHaloPx = (kTileH + 1) * (kTileW + 1);    // 153
+constexpr int kASlotBytesDN = 4 * (kCinBlk / 8) * kDnHaloPx * 16;   // 78336
 constexpr int kSmB = 0;
-constexpr int kSmA = kSmB + kBStages * kBSlotBytes;
-constexpr int kSmBar = kSmA + 2 * kASlotBytes;
+constexpr int kSmBar = kSmB + kBStages * kBSlotBytes;
 constexpr int kSmScale = kSmBar + 128;
-constexpr int kSmemBytes = kSmScale + 2 * kCinBlk * 4;
+constexpr int kSmA = kSmScale + 2 * kCinBlk * 4;
+constexpr int kSmemBytes = kSmA + 2 * kASlotBytes;
+constexpr int kSmemBytesDN = kSmA + 2 * kASlotBytesDN;     // 222848: one CTA per SM
 constexpr int kThreads = 128;
 
 struct ConvDev {
@@ -125,8 +130,9 @@ constexpr int kStageThreads = 256;
 constexpr int kThreadsV2 = kStageThreads + 32;
 
 // INCL / OUTCL: input / output tensor is channels-last fp16 ([B,H,W,C] half) instead of NCHW fp32
-template <bool kBF16, int KS, bool UPP, bool INCL, bool OUTCL>
+template <bool kBF16, int KS, bool UPP, bool INCL, bool OUTCL, bool DN = false>
 __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
+  static_assert(!DN || (KS == 3 && !UPP), "the polyphase stride-2 variant is 3x3 only");
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -143,8 +149,10 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
   const int b = sp / P.tiles_y;
   const int vy0 = ty * kTileH, vx0 = tx * kTileW;
   // staged patch: plain conv = tile + (KS-1) halo; polyphase transposed conv = tile + one row above / column left
-  constexpr int hw = UPP ? kTileW + 1 : kTileW + KS - 1, hh = UPP ? kTileH + 1 : kTileH + KS - 1;
+  constexpr int hw = (UPP || DN) ? kTileW + 1 : kTileW + KS - 1, hh = (UPP || DN) ? kTileH + 1 : kTileH + KS - 1;
   constexpr int halo_px = hh * hw, chunk_bytes = halo_px * 16, taps = KS * KS;
+  constexpr int a_slot = DN ? kASlotBytesDN : kASlotBytes;
+  constexpr int n_chunks = DN ? 4 * (kCinBlk / 8) : kCinBlk / 8;   // DN: chunk index = parity plane * 8 + channel chunk
   const int total_steps = P.kblocks * taps;
   const uint32_t b_bytes = (uint32_t)P.n_tile * kCinBlk * 2;
 
@@ -175,7 +183,7 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
       for (int kb = 0; kb < P.kblocks; ++kb) {
         mbar_wait_spin(bar_afull + (kb & 1) * 8, (kb >> 1) & 1);
         tc_fence_after();
-        const uint32_t A_addr = smem_base + kSmA + (kb & 1) * kASlotBytes;
+        const uint32_t A_addr = smem_base + kSmA + (kb & 1) * a_slot;
 #pragma unroll 1
         for (int tap = 0; tap < taps; ++tap) {
           const int step = kb * taps + tap, slot = step % kBStages;
@@ -189,6 +197,9 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
             a0 = A_addr + ((1 - (kh >> 1)) * hw + (1 - (kw >> 1))) * 16;
             d0 = tmem_acc + (((kh & 1) << 1) | (kw & 1)) * P.n_tile;
             fresh = kb == 0 && kh < 2 && kw < 2;
+          } else if (DN) {   // out[i, j] += x[2i + kh, 2j + kw] * W[kh,kw]: parity plane (kh&1, kw&1), shift (kh>>1, kw>>1)
+            a0 = A_addr + ((((kh & 1) << 1) | (kw & 1)) * (kCinBlk / 8)) * chunk_bytes + ((kh >> 1) * hw + (kw >> 1)) * 16;
+            d0 = tmem_acc, fresh = step == 0;
           } else {
             a0 = A_addr + (kh * hw + kw) * 16, d0 = tmem_acc, fresh = step == 0;
           }
@@ -217,7 +228,7 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
     const uint16_t *xcl = reinterpret_cast<const uint16_t *>(P.x);
     const size_t cstride = (size_t)P.H * P.W;
     for (int kb = 0; kb < P.kblocks; ++kb) {
-      uint8_t *A = smem + kSmA + (kb & 1) * kASlotBytes;
+      uint8_t *A = smem + kSmA + (kb & 1) * a_slot;
       float *sc = sscale + (kb & 1) * kCinBlk;
       if (kb >= 2) mbar_wait_spin(bar_afree + (kb & 1) * 8, ((kb - 2) >> 1) & 1);   // MMAs of block kb-2 are done with this buffer
       if (INCL) {
@@ -236,18 +247,20 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
       int hp = tid, chunk = 0;
       while (hp >= halo_px) hp -= halo_px, ++chunk;
 #pragma unroll 1
-      for (; chunk < 8;) {
+      for (; chunk < n_chunks;) {
         const int py = hp / hw, px = hp - py * hw;
-        const int Y = vy0 + py - P.pad, X = vx0 + px - P.pad;
+        const int Y = DN ? 2 * (vy0 + py) + (chunk >> 4) : vy0 + py - P.pad;
+        const int X = DN ? 2 * (vx0 + px) + ((chunk >> 3) & 1) : vx0 + px - P.pad;
         const bool ok = Y >= 0 && X >= 0 && Y < P.H && X < P.W;
-        const int c0 = kb * kCinBlk + chunk * 8;
+        const int cq = DN ? (chunk & 7) : chunk;      // channel chunk of the staged 64-channel block
+        const int c0 = kb * kCinBlk + cq * 8;
         uint4 u = make_uint4(0u, 0u, 0u, 0u);
         if (INCL) {
           // channels-last fp16: the 8 channels of this unit are one aligned 16-byte load; modulate as packed pairs
           if (ok && c0 < P.Cin) {
             u = __ldg(reinterpret_cast<const uint4 *>(xcl + (((size_t)b * P.H + Y) * P.W + X) * P.Cin + c0));
             if (P.in_scale != nullptr) {
-              const uint32_t *sh = reinterpret_cast<const uint32_t *>(sc) + chunk * 4;   // 4 packed pairs of this chunk
+              const uint32_t *sh = reinterpret_cast<const uint32_t *>(sc) + cq * 4;   // 4 packed pairs of this chunk
               u.x = mul2<false>(u.x, sh[0]), u.y = mul2<false>(u.y, sh[1]), u.z = mul2<false>(u.z, sh[2]), u.w = mul2<false>(u.w, sh[3]);
             }
           }
@@ -256,7 +269,7 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] = (ok && c0 + e < P.Cin) ? __ldg(xb + (size_t)(c0 + e) * cstride + (size_t)Y * P.W + X) : 0.0f;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] *= sc[chunk * 8 + e];
+          for (int e = 0; e < 8; ++e) v[e] *= sc[cq * 8 + e];
           u = make_uint4(pack2<kBF16>(v[0], v[1]), pack2<kBF16>(v[2], v[3]), pack2<kBF16>(v[4], v[5]), pack2<kBF16>(v[6], v[7]));
         }
         *reinterpret_cast<uint4 *>(A + chunk * chunk_bytes + hp * 16) = u;
@@ -282,7 +295,7 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
         bool ok;
         int oy, ox;
         if (UPP) ok = true, oy = 2 * vy + (ph >> 1), ox = 2 * vx + (ph & 1);
-        else if (P.down == 2) ok = !(vy & 1) && !(vx & 1), oy = vy >> 1, ox = vx >> 1;
+        else if (!DN && P.down == 2) ok = !(vy & 1) && !(vx & 1), oy = vy >> 1, ox = vx >> 1;   // 1x1 stride 2 only
         else ok = true, oy = vy, ox = vx;
         ok = ok && oy < P.Ho && ox < P.Wo;
         float nz = 0.0f;
@@ -405,6 +418,7 @@ extern "C" int hav_conv2d_forward(const hav_conv_args *a, void *stream) {
     P.pad = 0, vh = a->in_h - a->ksize + 1, vw = a->in_w - a->ksize + 1;                                // stride 2, pad 0
     if (vh < 1 || vw < 1) return HAV_E_SHAPE;
     P.Ho = (vh + 1) / 2, P.Wo = (vw + 1) / 2;
+    if (a->ksize == 3) vh = P.Ho, vw = P.Wo;           // polyphase: tiles run over the output positions
   } else {
     P.pad = a->ksize / 2, vh = a->in_h, vw = a->in_w, P.Ho = vh, P.Wo = vw;
   }
@@ -423,29 +437,33 @@ extern "C" int hav_conv2d_forward(const hav_conv_args *a, void *stream) {
   if (sp_tiles > 2147483647L || P.n_tiles > 65535) return HAV_E_SHAPE;
   dim3 grid((unsigned)sp_tiles, P.n_tiles);
   cudaError_t e;
+  const bool dn = a->down == 2 && a->ksize == 3;
+  const int smem_bytes = dn ? conv::kSmemBytesDN : conv::kSmemBytes;
   auto launch = [&](auto kern) -> cudaError_t {
-    cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, conv::kSmemBytes);
+    cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (er != cudaSuccess) return er;
-    kern<<<grid, conv::kThreadsV2, conv::kSmemBytes, (cudaStream_t)stream>>>(P);
+    kern<<<grid, conv::kThreadsV2, smem_bytes, (cudaStream_t)stream>>>(P);
     return cudaGetLastError();
   };
   const bool bf = a->precision == HAV_PREC_BF16;
   const int lay = (a->in_layout ? 2 : 0) | (a->out_layout ? 1 : 0);
   if (bf) {   // bf16 operands: NCHW fp32 tensors only
     if (a->up == 2) e = launch(conv::conv_tc_kernel<true, 3, true, false, false>);
+    else if (dn) e = launch(conv::conv_tc_kernel<true, 3, false, false, false, true>);
     else if (a->ksize == 3) e = launch(conv::conv_tc_kernel<true, 3, false, false, false>);
     else e = launch(conv::conv_tc_kernel<true, 1, false, false, false>);
   } else {
-#define HAV_CONV_DISPATCH(KS_, UPP_)                                                        \
-  switch (lay) {                                                                            \
-    case 0: e = launch(conv::conv_tc_kernel<false, KS_, UPP_, false, false>); break;        \
-    case 1: e = launch(conv::conv_tc_kernel<false, KS_, UPP_, false, true>); break;         \
-    case 2: e = launch(conv::conv_tc_kernel<false, KS_, UPP_, true, false>); break;         \
-    default: e = launch(conv::conv_tc_kernel<false, KS_, UPP_, true, true>); break;         \
+#define HAV_CONV_DISPATCH(KS_, UPP_, DN_)                                                        \
+  switch (lay) {                                                                                 \
+    case 0: e = launch(conv::conv_tc_kernel<false, KS_, UPP_, false, false, DN_>); break;        \
+    case 1: e = launch(conv::conv_tc_kernel<false, KS_, UPP_, false, true, DN_>); break;         \
+    case 2: e = launch(conv::conv_tc_kernel<false, KS_, UPP_, true, false, DN_>); break;         \
+    default: e = launch(conv::conv_tc_kernel<false, KS_, UPP_, true, true, DN_>); break;         \
   }
-    if (a->up == 2) { HAV_CONV_DISPATCH(3, true) }
-    else if (a->ksize == 3) { HAV_CONV_DISPATCH(3, false) }
-    else { HAV_CONV_DISPATCH(1, false) }
+    if (a->up == 2) { HAV_CONV_DISPATCH(3, true, false) }
+    else if (dn) { HAV_CONV_DISPATCH(3, false, true) }
+    else if (a->ksize == 3) { HAV_CONV_DISPATCH(3, false, false) }
+    else { HAV_CONV_DISPATCH(1, false, false) }
 #undef HAV_CONV_DISPATCH
   }
   if (e != cudaSuccess) return (int)e;
