@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
         bool ok;
         int oy, ox;
         if (UPP) ok = true, oy = 2 * vy + (ph >> 1), ox = 2 * vx + (ph & 1);
-        else if (!DN && P.down == 2) ok = !(vy & 1) && !(vx & 1), oy = vy >> 1, ox = vx >> 1;   // 1x1 stride 2 only
+        else if (!DN && P.down == 2) ok = !(vy & 1) && !(vx & 1), oy = vy >> 1, ox = vx >> 1;   // small layers, 1x1 stride 2
         else ok = true, oy = vy, ox = vx;
         ok = ok && oy < P.Ho && ox < P.Wo;
         float nz = 0.0f;
@@ -410,7 +410,8 @@ extern "C" int hav_conv2d_forward(const hav_conv_args *a, void *stream) {
   memset(&P, 0, sizeof(P));
   P.B = a->batch, P.Cin = a->cin, P.Cout = a->cout, P.H = a->in_h, P.W = a->in_w, P.k = a->ksize, P.up = a->up, P.down = a->down;
   P.act = a->act;
-  int vh, vw;   // stride-1 output positions
+  int vh, vw;   // tile grid: stride-1 output positions (output positions for the polyphase stride-2 form)
+  bool dn = false;
   if (a->up == 2) {
     P.pad = 1, vh = a->in_h + 1, vw = a->in_w + 1;      // polyphase tiles run over input positions 0..H (conv_transpose2d, stride 2, pad 0)
     P.Ho = 2 * a->in_h + 1, P.Wo = 2 * a->in_w + 1;
@@ -418,7 +419,15 @@ extern "C" int hav_conv2d_forward(const hav_conv_args *a, void *stream) {
     P.pad = 0, vh = a->in_h - a->ksize + 1, vw = a->in_w - a->ksize + 1;                                // stride 2, pad 0
     if (vh < 1 || vw < 1) return HAV_E_SHAPE;
     P.Ho = (vh + 1) / 2, P.Wo = (vw + 1) / 2;
-    if (a->ksize == 3) vh = P.Ho, vw = P.Wo;           // polyphase: tiles run over the output positions
+    // polyphase (tiles over the OUTPUT positions, 4 staged parity planes, one CTA per SM) once the grid fills the chip twice
+    // over; small layers keep the light-weight form (stride-1 tiles, even positions stored, two CTAs per SM): measured --
+    // the polyphase form is 7-27 % faster on the large layers and slower on the 8x8 ... 32x32 ones
+    if (a->ksize == 3) {
+      const long out_tiles = (long)a->batch * ((P.Wo + conv::kTileW - 1) / conv::kTileW) * ((P.Ho + conv::kTileH - 1) / conv::kTileH);
+      const int nt = (a->cout + conv_n_tile(a->cout, 1) - 1) / conv_n_tile(a->cout, 1);
+      dn = out_tiles * nt >= 2 * 148;
+      if (dn) vh = P.Ho, vw = P.Wo;
+    }
   } else {
     P.pad = a->ksize / 2, vh = a->in_h, vw = a->in_w, P.Ho = vh, P.Wo = vw;
   }
@@ -437,7 +446,6 @@ extern "C" int hav_conv2d_forward(const hav_conv_args *a, void *stream) {
   if (sp_tiles > 2147483647L || P.n_tiles > 65535) return HAV_E_SHAPE;
   dim3 grid((unsigned)sp_tiles, P.n_tiles);
   cudaError_t e;
-  const bool dn = a->down == 2 && a->ksize == 3;
   const int smem_bytes = dn ? conv::kSmemBytesDN : conv::kSmemBytes;
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
