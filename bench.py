@@ -261,8 +261,7 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings go to stderr: stdout carries exactly one JSON line
 
         dist.init_process_group("nccl", device_id=dev)
 
