@@ -65,7 +65,7 @@ class _Group:
     parameters, gradients and both moments are flat buffers and the update is the one-pass hav_adam_flat kernel
     (parallel.FlatAdam; step count and learning rate on the device, so the whole update can live inside a CUDA graph)."""
 
-    def __init__(self, modules, lr, betas=(0.9, 0.999), capturable=False):
+    def __init__(self, modules, lr, betas=(0.9, 0.999)):
         self.params = [p for m in modules for p in m.parameters()]
         self.flat = self.params[0].is_cuda and FLAT_ADAM[0]
         if self.flat:
@@ -115,8 +115,8 @@ class StageOneStep:
         mods = [self.net] + ([self.disc] if self.disc is not None else [])
         if _distributed():
             parallel.broadcast_parameters(mods)
-        self.g = _Group([self.net], lr, capturable=capturable)                                             # train_avatar.py:68-71
-        self.d = _Group([self.disc], 2e-3 * 16 / 17, betas=(0.0, 0.99 ** (16 / 17)), capturable=capturable) if self.disc is not None else None
+        self.g = _Group([self.net], lr)                                                                   # train_avatar.py:68-71
+        self.d = _Group([self.disc], 2e-3 * 16 / 17, betas=(0.0, 0.99 ** (16 / 17))) if self.disc is not None else None
         self.patch, self.it, self.lr0 = patch, 0, lr
 
     def groups(self):
@@ -191,9 +191,9 @@ class StageTwoStep:
         if _distributed():
             parallel.broadcast_parameters([self.net, self.generator, self.g_ema, self.disc])
         g_ratio, d_ratio = 4 / 5, d_reg_every / (d_reg_every + 1)                                            # :117-122
-        self.nerf = _Group([self.net], 5e-4, capturable=capturable)
-        self.g = _Group([self.generator], 2e-3 * g_ratio, betas=(0.0, 0.99 ** g_ratio), capturable=capturable)
-        self.d = _Group([self.disc], 2e-3 * d_ratio, betas=(0.0, 0.99 ** d_ratio), capturable=capturable)
+        self.nerf = _Group([self.net], 5e-4)
+        self.g = _Group([self.generator], 2e-3 * g_ratio, betas=(0.0, 0.99 ** g_ratio))
+        self.d = _Group([self.disc], 2e-3 * d_ratio, betas=(0.0, 0.99 ** d_ratio))
         self.render_size, self.gen_size, self.latent = render_size, gen_size, latent
         self.d_reg_every, self.r1, self.it = d_reg_every, r1, 0
         self.accum = 0.5 ** (32 / (10 * 1000))                                                               # :162
@@ -276,7 +276,8 @@ class Graphed:
     """A training step replayed as CUDA graphs: forward, backward, the gradient all-reduce, the Adam updates and the EMA of one
     iteration become one graph launch per graphable part (StageOneStep: one; StageTwoStep: the D step and the G step, with the
     every-16th R1 pass run eagerly between them), removing the ~1500 host-side kernel launches that bound the eager step.
-    The step must be built with capturable=True (device-side Adam state / learning rate, device RNG for sample_pdf).
+    The step must be built with capturable=True (sample_pdf's uniform draws on the device instead of the CPU generator; the
+    Adam state is device-side either way).
     `example` provides shapes; its tensors are cloned into the static input buffers every replay reads."""
 
     def __init__(self, step, example, warmup=3):
