@@ -27,6 +27,17 @@ METRIC = "rays_per_sec_512x512x64"
 CPU_CHUNK_RAYS = 4096            # one reference chunk (nerf.validation.chunksize)
 
 
+_STDOUT_FD = []
+
+
+def emit(line):
+    """Print the one JSON line on the real stdout (restoring it first if it was parked on stderr)."""
+    sys.stdout.flush()
+    if _STDOUT_FD:
+        os.dup2(_STDOUT_FD.pop(), 1)
+    print(json.dumps(line), flush=True)
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -134,7 +145,7 @@ def run_train_legs(args, torch, dist, dev, rank, world, barrier, headline):
             out = dict(headline)
             out.pop("train_note", None)
             out["train"] = {"error": "training legs did not finish within %d s; skipped" % args.train_deadline}
-            print(json.dumps(out), flush=True)
+            emit(out)
         os._exit(0)
 
     dog = threading.Timer(args.train_deadline, bail)
@@ -261,7 +272,11 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings go to stderr: stdout carries exactly one JSON line
+        # NCCL writes its version banner to the process's stdout (fd 1) whatever NCCL_DEBUG_FILE says: park fd 1 on stderr
+        # until the JSON line is due, so that stdout carries exactly one line
+        sys.stdout.flush()
+        _STDOUT_FD.append(os.dup(1))
+        os.dup2(2, 1)
 
         dist.init_process_group("nccl", device_id=dev)
 
@@ -492,7 +507,7 @@ def run_ours(args):
     note = line.pop("train_note")["note"]
     train = run_train_legs(args, torch, dist, dev, rank, world, barrier, line)
     line["train"] = dict(train, note=note)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         if "error" in train:      # a rank that failed inside a training leg leaves its peers in a collective: do not wait for them
             os._exit(0)
