@@ -128,8 +128,8 @@ __global__ void __launch_bounds__(256) upfirdn2d_kernel(float *__restrict__ out,
 // ------------------------------------------------------------------------------------------------
 // Specialised upfirdn2d for the shapes the StyleUNet actually uses (minor == 1, square up/down):
 //   <1,1,4,4> Blur, <1,2,4,4> Downsample, <2,1,4,4> Upsample, <1,2,2,2> Haar analysis, <2,1,2,2> Haar synthesis.
-// Compile-time taps (fully unrolled), compile-time window pitch (no div/mod by runtime values).  up == 1: one thread = one
-// output column x 8 rows with every window row held in registers across the output rows it overlaps; up == 2: a strip of 4
+// Compile-time taps (fully unrolled), compile-time window pitch (no div/mod by runtime values).  up == down == 1: one thread = one
+// output column x 8 rows with every window row held in registers across the output rows it overlaps; otherwise: a strip of 4
 // horizontally adjacent outputs that shares its window reads, 128-bit stores when the row pitch allows.
 // Same arithmetic as the generic kernel: out = sum over the taps that land on a real input sample.
 // ------------------------------------------------------------------------------------------------
@@ -155,14 +155,22 @@ __global__ void __launch_bounds__(256) upfirdn2d_fast_kernel(float *__restrict__
   }
   const int iy0 = ceil_div(oy0 * DOWN - p.pad_y0, UP), ix0 = ceil_div(ox0 * DOWN - p.pad_x0, UP);
   const float *xin = x + (size_t)img * p.in_h * p.in_w;
-  // window rows are dealt to the 8 warps, a lane walks its row 32 columns at a time: coalesced, no div / mod
-  for (int wy = threadIdx.x >> 5; wy < F::kWinH; wy += 8) {
-    const int iy = iy0 + wy;
-    const bool row_ok = iy >= 0 && iy < p.in_h;
-    const float *xrow = xin + (size_t)(row_ok ? iy : 0) * p.in_w;
-    for (int wx = threadIdx.x & 31; wx < F::kWinW; wx += 32) {
-      const int ix = ix0 + wx;
-      sw[wy * F::kWinW + wx] = (row_ok && ix >= 0 && ix < p.in_w) ? __ldg(xrow + ix) : 0.0f;
+  if (UP == 1 && DOWN == 1) {
+    // window rows are dealt to the 8 warps, a lane walks its row 32 columns at a time: coalesced, no div / mod
+    for (int wy = threadIdx.x >> 5; wy < F::kWinH; wy += 8) {
+      const int iy = iy0 + wy;
+      const bool row_ok = iy >= 0 && iy < p.in_h;
+      const float *xrow = xin + (size_t)(row_ok ? iy : 0) * p.in_w;
+      for (int wx = threadIdx.x & 31; wx < F::kWinW; wx += 32) {
+        const int ix = ix0 + wx;
+        sw[wy * F::kWinW + wx] = (row_ok && ix >= 0 && ix < p.in_w) ? __ldg(xrow + ix) : 0.0f;
+      }
+    }
+  } else {      // wide (stride-2) or narrow (up-sampling) windows: the flat loop keeps every thread busy -- measured faster there
+    for (int i = threadIdx.x; i < F::kWinH * F::kWinW; i += 256) {
+      const int wy = i / F::kWinW, wx = i - wy * F::kWinW;
+      const int iy = iy0 + wy, ix = ix0 + wx;
+      sw[i] = (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) ? __ldg(xin + (size_t)iy * p.in_w + ix) : 0.0f;
     }
   }
   __syncthreads();
@@ -170,7 +178,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_fast_kernel(float *__restrict__
 #pragma unroll
   for (int i = 0; i < KH * KW; ++i) kreg[i] = sk[i];
   float *oimg = out + (size_t)img * p.out_h * p.out_w;
-  if (UP == 1) {
+  if (UP == 1 && DOWN == 1) {
     // one thread = one output column x 8 rows: lanes run along x (conflict-free window reads for DOWN == 1, full-line
     // stores), and a window row loaded once into registers feeds every output row of the strip it overlaps
     constexpr int kStrip = 8, NR = (kStrip - 1) * DOWN + KH;
@@ -202,14 +210,27 @@ __global__ void __launch_bounds__(256) upfirdn2d_fast_kernel(float *__restrict__
     return;
   }
   const bool vec_ok = (p.out_w & 3) == 0;
-  // UP == 2, DOWN == 1: strips of 4 outputs, (kTileH * kTileW / 4) strips per tile, 2 per thread; tap ky contributes when
-  // (Y0 + ky) is even: KH / 2 taps per dimension
+  // strips of 4 horizontally adjacent outputs: (kTileH * kTileW / 4) strips per tile, 2 per thread
   for (int sidx = threadIdx.x; sidx < kTileH * kTileW / 4; sidx += 256) {
     const int ty = sidx / (kTileW / 4), oy = oy0 + ty, ox = ox0 + (sidx - ty * (kTileW / 4)) * 4;
     if (oy >= p.out_h || ox >= p.out_w) continue;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const int Y0 = oy * DOWN - p.pad_y0;
-    {
+    if (UP == 1) {      // DOWN == 2 (the 2x2 Haar analysis and the 4x4 downsampler): measured faster in this form
+      const int wy0 = Y0 - iy0, wx0 = ox * DOWN - p.pad_x0 - ix0;
+      constexpr int NX = 3 * DOWN + KW;   // window columns a strip touches
+#pragma unroll
+      for (int ky = 0; ky < KH; ++ky) {
+        float row[NX];
+#pragma unroll
+        for (int c = 0; c < NX; ++c) row[c] = sw[(wy0 + ky) * F::kWinW + wx0 + c];
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+          for (int kx = 0; kx < KW; ++kx) acc[o] = fmaf(row[o * DOWN + kx], kreg[ky * KW + kx], acc[o]);
+      }
+    } else {
+      // UP == 2, DOWN == 1: tap ky contributes when (Y0 + ky) is even; KH / 2 taps per dimension
       const int ky_first = Y0 & 1;                       // (-Y0) mod 2
 #pragma unroll
       for (int a = 0; a < KH / 2; ++a) {
