@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhavatar_b200.so")
 
-HAV_ABI_VERSION = 1
+HAV_ABI_VERSION = 2
 PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16}
 
@@ -32,6 +32,7 @@ class RenderArgs(C.Structure):
         ("rgb_coarse", _fp), ("depth_coarse", _fp), ("acc_coarse", _fp), ("weights_max", _fp),
         ("rgb_fine", _fp), ("depth_fine", _fp), ("acc_fine", _fp), ("z_fine", _fp),
         ("workspace", _fp), ("workspace_bytes", C.c_uint64),
+        ("camera", _fp), ("pixel_index", _fp), ("img_h", C.c_int32), ("img_w", C.c_int32), ("pdf_inds", _fp), ("range_status", _fp),
     ]
 
 
@@ -78,6 +79,7 @@ SIGNATURES = {
     "hav_upfirdn2d": (C.c_int, [_fp, _fp, _fp] + [C.c_int] * 14 + [_fp]),
     "hav_render_workspace_bytes": (C.c_uint64, [C.POINTER(RenderArgs)]),
     "hav_render_forward": (C.c_int, [C.POINTER(RenderArgs), _fp]),
+    "hav_sample_pdf": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]),
     "hav_render_backward_workspace_bytes": (C.c_uint64, [C.POINTER(RenderBwdArgs)]),
     "hav_render_backward": (C.c_int, [C.POINTER(RenderBwdArgs), _fp]),
     "hav_conv_wpack_bytes": (C.c_uint64, [C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -266,6 +266,12 @@ def _dgrad_raw(g, weight, wscale, up, down, H, W, in_scale=None):
     return conv2d(g, wp, in_scale=in_scale)
 
 
+# model/op/conv2d_gradfix.py:12-20 no_weight_gradients(): while set, a backward that is itself being recorded (the R1 penalty's
+# autograd.grad(..., create_graph=True), utils/styleUnet_util.py:72-79) skips the weight gradient it would otherwise compute and
+# throw away.  Toggled through havatar_b200.op.conv2d_gradfix.no_weight_gradients().
+WEIGHT_GRADIENTS_DISABLED = [False]
+
+
 # The convolution is bilinear in (x, w), so its three kernels are closed under differentiation:
 #     y  = F(x, w)          dF:  dx = D(gy, w)   dw = W(gy, x)
 #     dx = D(g, w)          dD:  dg = F(h, w)    dw = W(g, h)
@@ -284,7 +290,8 @@ class _Fwd(torch.autograd.Function):
         x, weight = ctx.saved_tensors
         wscale, up, down = ctx.cfg
         dx = _Dgrad.apply(gy, weight, wscale, up, down, int(x.shape[2]), int(x.shape[3])) if ctx.needs_input_grad[0] else None
-        dw = _Wgrad.apply(gy, x, wscale, up, down, int(weight.shape[-1])) if ctx.needs_input_grad[1] else None
+        dw = _Wgrad.apply(gy, x, wscale, up, down, int(weight.shape[-1])) \
+            if ctx.needs_input_grad[1] and not WEIGHT_GRADIENTS_DISABLED[0] else None
         return dx, dw, None, None, None, None
 
 
@@ -351,7 +358,7 @@ class _ConvFunction(torch.autograd.Function):
                 dx = dxs if in_scale is None else dxs * in_scale[:, :, None, None]
                 if in_scale is not None and need[2]:
                     ds = (dxs * x).sum(dim=(2, 3))
-            if need[1]:
+            if need[1] and not WEIGHT_GRADIENTS_DISABLED[0]:
                 dw = _Wgrad.apply(gs, x if in_scale is None else x * in_scale[:, :, None, None], wscale, up, down, k)
             if out_scale is not None and need[3]:
                 dd = (g * y).sum(dim=(2, 3)) / out_scale

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "../../include/havatar_b200.h"
+#include "render_common.cuh"
 
 namespace hav {
 
@@ -336,22 +337,17 @@ __global__ void __launch_bounds__(256) upfirdn2d_cl_kernel(uint16_t *__restrict_
 // ray generation (dataloader/data_util.py:28-56)
 // ------------------------------------------------------------------------------------------------
 struct RayGen {
-  float kinv[9], rot[9], org[3], near, far;
+  float cam[16], near, far;   // fx fy cx cy | c2w row-major [3,4]
   int H, W;
 };
 __global__ void __launch_bounds__(256) get_rays_kernel(float *__restrict__ rays, RayGen g) {
   const int n = g.H * g.W;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-    const float i = (float)(r % g.W), j = (float)(r / g.W);  // pixel (x=i, y=j): dataloader/dataloader.py:72
-    float c[3], d[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) c[a] = g.kinv[a * 3] * i + g.kinv[a * 3 + 1] * j + g.kinv[a * 3 + 2];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) d[a] = g.rot[a * 3] * c[0] + g.rot[a * 3 + 1] * c[1] + g.rot[a * 3 + 2] * c[2];
-    float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    float org[3], d[3];
+    pixel_ray([&](int k) { return g.cam[k]; }, g.W, g.H, r, org, d);
     float4 *o = reinterpret_cast<float4 *>(rays + (size_t)r * 8);
-    o[0] = make_float4(g.org[0], g.org[1], g.org[2], d[0] / nrm);
-    o[1] = make_float4(d[1] / nrm, d[2] / nrm, g.near, g.far);
+    o[0] = make_float4(org[0], org[1], org[2], d[0]);
+    o[1] = make_float4(d[1], d[2], g.near, g.far);
   }
 }
 
@@ -461,14 +457,8 @@ extern "C" int hav_get_rays(float *ray_batch, int height, int width, const float
   if (ray_batch == nullptr || intr == nullptr || c2w == nullptr) return HAV_E_NULL;
   if (intr[0] == 0.0f || intr[1] == 0.0f) return HAV_E_VALUE;
   RayGen g;
-  // K = [[fx,0,cx*W],[0,fy,cy*H],[0,0,1]] (data_util.py:38-39); closed-form inverse
-  const float fx = intr[0], fy = intr[1], cx = intr[2] * (float)width, cy = intr[3] * (float)height;
-  const float kinv[9] = {1.0f / fx, 0.0f, -cx / fx, 0.0f, 1.0f / fy, -cy / fy, 0.0f, 0.0f, 1.0f};
-  for (int i = 0; i < 9; ++i) g.kinv[i] = kinv[i];
-  for (int r = 0; r < 3; ++r) {
-    for (int c = 0; c < 3; ++c) g.rot[r * 3 + c] = c2w[r * 4 + c];
-    g.org[r] = c2w[r * 4 + 3];
-  }
+  for (int i = 0; i < 4; ++i) g.cam[i] = intr[i];
+  for (int i = 0; i < 12; ++i) g.cam[4 + i] = c2w[i];
   g.near = near, g.far = far, g.H = height, g.W = width;
   const int n = height * width;
   int grid = (n + 255) / 256;

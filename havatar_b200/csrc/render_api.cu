@@ -18,7 +18,7 @@ int render_check_args(const hav_render_args *a) {
   if (a == nullptr) return HAV_E_NULL;
   if (a->struct_bytes != sizeof(hav_render_args)) return HAV_E_VALUE;
   if (a->precision != HAV_PREC_FP32 && a->precision != HAV_PREC_BF16 && a->precision != HAV_PREC_FP16) return HAV_E_VALUE;
-  if ((a->flags & ~HAV_RENDER_REUSE_PACKED) != 0) return HAV_E_VALUE;
+  if ((a->flags & ~(HAV_RENDER_REUSE_PACKED | HAV_RENDER_CHECK_RANGE)) != 0) return HAV_E_VALUE;
   if (a->batch < 0 || a->rays < 0) return HAV_E_SHAPE;
   if ((int64_t)a->batch * a->rays > (int64_t)1 << 30) return HAV_E_SHAPE;
   if (a->num_coarse < 2 || a->num_coarse > kMaxSamples) return HAV_E_SHAPE;
@@ -30,12 +30,19 @@ int render_check_args(const hav_render_args *a) {
   if (a->vol_d < 1 || a->vol_h < 1 || a->vol_w < 1) return HAV_E_SHAPE;
   if ((int64_t)2 * a->batch * (a->plane_h + 3) * (a->plane_w + 3) >= ((int64_t)1 << 31) / 64) return HAV_E_SHAPE;
   if ((int64_t)a->batch * a->rays == 0) return HAV_OK;
-  const void *req[] = {a->ray_batch, a->inv_head_T, a->planes, a->wvol, a->w0, a->b0, a->w1, a->b1, a->w_alpha,
+  if (a->camera != nullptr) {   // in-kernel ray generation
+    if (a->img_h < 1 || a->img_w < 1 || (int64_t)a->img_h * a->img_w > (int64_t)1 << 30) return HAV_E_SHAPE;
+    if (a->pixel_index == nullptr && (int64_t)a->rays != (int64_t)a->img_h * a->img_w) return HAV_E_SHAPE;
+  } else if (a->ray_batch == nullptr) {
+    return HAV_E_NULL;
+  }
+  const void *req[] = {a->inv_head_T, a->planes, a->wvol, a->w0, a->b0, a->w1, a->b1, a->w_alpha,
                        a->b_alpha, a->w_feat, a->b_feat, a->w_rgb, a->b_rgb, a->rgb_coarse, a->depth_coarse,
                        a->acc_coarse, a->weights_max};
   for (const void *p : req)
     if (p == nullptr) return HAV_E_NULL;
   if (a->num_fine > 0 && (a->rgb_fine == nullptr || a->depth_fine == nullptr || a->acc_fine == nullptr)) return HAV_E_NULL;
+  if ((a->flags & HAV_RENDER_CHECK_RANGE) != 0 && a->range_status == nullptr) return HAV_E_NULL;
   return HAV_OK;
 }
 
@@ -77,6 +84,9 @@ void render_fill_dev(const hav_render_args *a, RenderDev &P) {
   P.t_rand = a->t_rand, P.noise_c = a->noise_coarse, P.u_rand = a->u_rand, P.noise_f = a->noise_fine;
   P.rgb_c = a->rgb_coarse, P.depth_c = a->depth_coarse, P.acc_c = a->acc_coarse, P.wmax = a->weights_max;
   P.rgb_f = a->rgb_fine, P.depth_f = a->depth_fine, P.acc_f = a->acc_fine, P.z_fine = a->z_fine;
+  P.camera = a->camera, P.pixel_index = a->camera != nullptr ? a->pixel_index : nullptr;
+  P.img_h = a->img_h, P.img_w = a->img_w, P.pdf_inds = a->num_fine > 0 ? a->pdf_inds : nullptr;
+  P.status = ((a->flags & HAV_RENDER_CHECK_RANGE) != 0 && a->precision == HAV_PREC_FP16) ? a->range_status : nullptr;
 }
 
 }  // namespace hav
@@ -119,9 +129,13 @@ extern "C" int hav_render_forward(const hav_render_args *a, void *stream) {
     P.wimg = ws + L.wimg;
     P.planes_cl = (const uint16_t *)(ws + L.planes_cl);
     const bool bf16 = a->precision == HAV_PREC_BF16;
+    if ((a->flags & HAV_RENDER_CHECK_RANGE) != 0) {
+      e = cudaMemsetAsync(a->range_status, 0, sizeof(int32_t), st);
+      if (e != cudaSuccess) return (int)e;
+    }
     if (!reuse) {
-      launch_pack_mlp_16(a, ws + L.wimg, st);
-      e = launch_pack_planes_16(a->planes, (uint16_t *)(ws + L.planes_cl), 2 * a->batch, a->plane_h, a->plane_w, bf16, st);
+      launch_pack_mlp_16(a, ws + L.wimg, st, P.status);
+      e = launch_pack_planes_16(a->planes, (uint16_t *)(ws + L.planes_cl), 2 * a->batch, a->plane_h, a->plane_w, bf16, st, P.status);
       if (e != cudaSuccess) return (int)e;
     }
     e = launch_render_16(P, L.num_blocks, bf16, st);

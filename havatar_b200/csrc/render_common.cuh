@@ -29,6 +29,12 @@ struct RenderDev {
   const float *rays, *bg, *invT, *planes, *wvol;
   const float *t_rand, *noise_c, *u_rand, *noise_f;
   float *rgb_c, *depth_c, *acc_c, *wmax, *rgb_f, *depth_f, *acc_f, *z_fine;
+  // in-kernel ray generation (ABI 2): camera [B,18] = fx fy cx cy | c2w [3,4] | near far; pixel_index [B,R] or NULL
+  const float *camera;
+  const int32_t *pixel_index;
+  int img_h, img_w;
+  int32_t *pdf_inds;  // optional [B,R,nfine] searchsorted indices (utils/nerf_util.py:102)
+  int32_t *status;    // HAV_RENDER_CHECK_RANGE: fp16 range report, or NULL
   // fp32 path: transposed weights [K][N] + biases (built by pack_mlp_fp32_kernel in the workspace)
   const float *W0t, *W1t, *Wht, *b0, *b1, *bh, *Wr, *br;
   // bf16 path: pre-swizzled UMMA smem image of the weights + channels-last bf16 planes
@@ -44,16 +50,43 @@ struct Ray {
   bool valid;
 };
 
+// dataloader/data_util.py:28-56 get_rays for one pixel: d = normalize(R_c2w . K^-1 [i, j, 1]^T) with
+// K = [[fx,0,cx*W],[0,fy,cy*H],[0,0,1]] inverted in closed form.  `cam` = fx fy cx cy | c2w row-major [3,4].
+// Used by hav_get_rays' kernel and by the in-kernel ray generation, so both produce the same bits.
+template <class F>
+__device__ __forceinline__ void pixel_ray(F cam, int W, int H, int pix, float o[3], float d[3]) {
+  const float fx = cam(0), fy = cam(1), cx = cam(2) * (float)W, cy = cam(3) * (float)H;
+  const float i = (float)(pix % W), j = (float)(pix / W);   // pixel (x = i, y = j): dataloader/dataloader.py:72
+  // every operation spelled out (no compiler-chosen contraction): the kernel of hav_get_rays and the render kernels must agree
+  float c[3], v[3];
+  c[0] = __fmaf_rn(i, __fdiv_rn(1.0f, fx), __fdiv_rn(-cx, fx));
+  c[1] = __fmaf_rn(j, __fdiv_rn(1.0f, fy), __fdiv_rn(-cy, fy));
+  c[2] = 1.0f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    v[a] = __fmaf_rn(cam(4 + a * 4 + 2), c[2], __fmaf_rn(cam(4 + a * 4 + 1), c[1], __fmul_rn(cam(4 + a * 4), c[0])));
+  const float nrm = __fsqrt_rn(__fmaf_rn(v[2], v[2], __fmaf_rn(v[1], v[1], __fmul_rn(v[0], v[0]))));
+#pragma unroll
+  for (int a = 0; a < 3; ++a) d[a] = __fdiv_rn(v[a], nrm), o[a] = cam(4 + a * 4 + 3);
+}
+
 __device__ __forceinline__ Ray load_ray(const RenderDev &P, int g) {
   Ray r;
   r.valid = g < P.total_rays;
   int gi = r.valid ? g : 0;
   r.b = gi / P.R;
-  const float4 *p = reinterpret_cast<const float4 *>(P.rays + (size_t)gi * 8);
-  float4 a = __ldg(p), c = __ldg(p + 1);
-  r.o[0] = a.x, r.o[1] = a.y, r.o[2] = a.z;
-  r.d[0] = a.w, r.d[1] = c.x, r.d[2] = c.y;
-  r.near = c.z, r.far = c.w;
+  if (P.camera != nullptr) {
+    const float *cam = P.camera + (size_t)r.b * 18;
+    const int pix = P.pixel_index != nullptr ? __ldg(P.pixel_index + gi) : gi - r.b * P.R;
+    pixel_ray([&](int k) { return __ldg(cam + k); }, P.img_w, P.img_h, pix, r.o, r.d);
+    r.near = __ldg(cam + 16), r.far = __ldg(cam + 17);
+  } else {
+    const float4 *p = reinterpret_cast<const float4 *>(P.rays + (size_t)gi * 8);
+    float4 a = __ldg(p), c = __ldg(p + 1);
+    r.o[0] = a.x, r.o[1] = a.y, r.o[2] = a.z;
+    r.d[0] = a.w, r.d[1] = c.x, r.d[2] = c.y;
+    r.near = c.z, r.far = c.w;
+  }
   // utils/nerf_util.py:38  ray_directions[..., None, :].norm(p=2, dim=-1)
   r.dnorm = sqrtf(r.d[0] * r.d[0] + r.d[1] * r.d[1] + r.d[2] * r.d[2]);
   return r;
@@ -184,13 +217,13 @@ __device__ __forceinline__ float sigmoidf_exact(float x) { return 1.0f / (1.0f +
 // MUFU.EX2 + MUFU.RCP version for the 16-bit tensor-core modes (rel. error ~1e-6, far below the operand rounding)
 __device__ __forceinline__ float sigmoidf_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
 
-// utils/nerf_util.py:76-117 sample_pdf + model/nerf_trainer.py:166-170 merge, for one ray (one thread).
-//   zc(s)      : coarse depth of sample s (0..Sc-1)
-//   wcol[j*ld] : in  = coarse weights w_j (j = 0..Sc-1), used as cdf scratch (overwritten)
-//   zout[j*ld] : out = sorted(cat(z[::2], z_samples)), Sf = (Sc+1)/2 + nfine entries
-template <class ZFn>
-__device__ __forceinline__ void sample_pdf_merge(ZFn zc, int Sc, int nfine, float *wcol, int ld, const float *u_rand,
-                                                 float *zout) {
+// utils/nerf_util.py:76-117 sample_pdf for one ray (one thread).
+//   zmid(j)    : bin edge j (z_vals_mid, j = 0..Sc-2)
+//   wcol[j*ld] : in  = coarse weights w_j (j = 0..Sc-1; w_0 and w_{Sc-1} are not used, :79), used as cdf scratch (overwritten)
+//   zs[k]      : out = the nfine samples (unsorted order of u);  inds_out[k] = searchsorted index (optional)
+template <class MidFn>
+__device__ __forceinline__ void sample_pdf_core(MidFn zmid, int Sc, int nfine, float *wcol, int ld, const float *u_rand,
+                                                float *zs, int32_t *inds_out) {
   const int M = Sc - 1;  // number of bins edges (z_mid) == cdf entries
   // pdf over weights[1:-1] + 1e-5 (:79-80)
   float sum = 0.0f;
@@ -202,7 +235,6 @@ __device__ __forceinline__ void sample_pdf_merge(ZFn zc, int Sc, int nfine, floa
     run += (wcol[j * ld] + 1e-5f) / sum;
     wcol[j * ld] = run;
   }
-  float zs[kMaxFine];
   for (int k = 0; k < nfine; ++k) {
     float u;
     if (u_rand == nullptr) {
@@ -218,14 +250,25 @@ __device__ __forceinline__ void sample_pdf_merge(ZFn zc, int Sc, int nfine, floa
       int mid = (lo + hi) >> 1;
       if (wcol[mid * ld] > u) hi = mid; else lo = mid + 1;
     }
+    if (inds_out != nullptr) inds_out[k] = lo;
     int below = max(lo - 1, 0), above = min(lo, M - 1);                              // :103-104
     float c0 = wcol[below * ld], c1 = wcol[above * ld];
-    float b0 = 0.5f * (zc(below + 1) + zc(below)), b1 = 0.5f * (zc(above + 1) + zc(above));  // z_vals_mid
+    float b0 = zmid(below), b1 = zmid(above);                                        // z_vals_mid
     float denom = c1 - c0;
     denom = (denom < 1e-5f) ? 1.0f : denom;                                          // :112-113
     float t = (u - c0) / denom;
     zs[k] = __fadd_rn(b0, __fmul_rn(t, b1 - b0));                                                      // :114-115
   }
+}
+
+// sample_pdf + model/nerf_trainer.py:166-170 merge, for one ray (one thread).
+//   zc(s)      : coarse depth of sample s (0..Sc-1)
+//   zout[j*ld] : out = sorted(cat(z[::2], z_samples)), Sf = (Sc+1)/2 + nfine entries
+template <class ZFn>
+__device__ __forceinline__ void sample_pdf_merge(ZFn zc, int Sc, int nfine, float *wcol, int ld, const float *u_rand,
+                                                 float *zout, int32_t *inds_out = nullptr) {
+  float zs[kMaxFine];
+  sample_pdf_core([&](int j) { return 0.5f * (zc(j + 1) + zc(j)); }, Sc, nfine, wcol, ld, u_rand, zs, inds_out);
   // torch.sort semantics even if rounding ever produced an inversion: insertion sort (normally a no-op)
   for (int k = 1; k < nfine; ++k) {
     float v = zs[k];

@@ -31,8 +31,9 @@ uint64_t tc_weight_image_bytes();
 uint64_t tc_planes_bytes(int nimg, int H, int W);
 int tc_num_ctas(int num_ray_blocks);
 int tc_scratch_slots(int num_ray_blocks);
-void launch_pack_mlp_16(const hav_render_args *a, uint8_t *wimg, cudaStream_t st);
-cudaError_t launch_pack_planes_16(const float *planes, uint16_t *out, int nimg, int H, int W, bool bf16, cudaStream_t st);
+void launch_pack_mlp_16(const hav_render_args *a, uint8_t *wimg, cudaStream_t st, int32_t *status = nullptr);
+cudaError_t launch_pack_planes_16(const float *planes, uint16_t *out, int nimg, int H, int W, bool bf16, cudaStream_t st,
+                                  int32_t *status = nullptr);
 cudaError_t launch_render_16(const RenderDev &P, int num_ray_blocks, bool bf16, cudaStream_t st);
 cudaError_t launch_render_16_v2(const RenderDev &P, int num_ray_blocks, bool bf16, cudaStream_t st);  // render_tc2.cu
 

@@ -190,7 +190,8 @@ __global__ void __launch_bounds__(kRaysPerBlock, 1) render_fp32_kernel(const Ren
     if (pass == 0 && npass == 2) {
       auto zc = [&](int s) { return coarse_z(P, ray, gi, s); };
       sample_pdf_merge(zc, P.Sc, P.nfine, wcol, kRaysPerBlock,
-                       P.u_rand != nullptr ? P.u_rand + (size_t)gi * P.nfine : nullptr, zcol);
+                       P.u_rand != nullptr ? P.u_rand + (size_t)gi * P.nfine : nullptr, zcol,
+                         (ray.valid && P.pdf_inds != nullptr) ? P.pdf_inds + (size_t)g * P.nfine : nullptr);
       if (ray.valid && P.z_fine != nullptr)
         for (int j = 0; j < P.Sf; ++j) P.z_fine[(size_t)g * P.Sf + j] = zcol[j * kRaysPerBlock];
     }
@@ -198,14 +199,42 @@ __global__ void __launch_bounds__(kRaysPerBlock, 1) render_fp32_kernel(const Ren
 }
 
 cudaError_t launch_render_fp32(const RenderDev &P, int num_blocks, cudaStream_t st) {
-  static bool attr_set = false;  // idempotent per-process attribute; racing writers set the same value
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(render_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSimtSmem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  // the attribute is per device / context: set it on every launch (a process may drive several GPUs)
+  cudaError_t e = cudaFuncSetAttribute(render_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSimtSmem);
+  if (e != cudaSuccess) return e;
   render_fp32_kernel<<<num_blocks, kRaysPerBlock, kSimtSmem, st>>>(P);
   return cudaGetLastError();
 }
 
 }  // namespace hav
+
+// ------------------------------------------------------------------------------------------------
+// hav_sample_pdf: utils/nerf_util.py:76-117 alone (the device function the render kernels run), one thread per row
+// ------------------------------------------------------------------------------------------------
+namespace hav {
+__global__ void __launch_bounds__(128) sample_pdf_kernel(const float *__restrict__ bins, const float *__restrict__ weights,
+                                                         const float *__restrict__ u, int n, int m, int nfine, float *__restrict__ samples,
+                                                         int32_t *__restrict__ inds, float *__restrict__ scratch) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int Sc = m + 1;
+  float *wcol = scratch + (size_t)r * Sc;
+  for (int j = 1; j <= Sc - 2; ++j) wcol[j] = weights[(size_t)r * (m - 1) + j - 1];
+  float zs[kMaxFine];
+  const float *b = bins + (size_t)r * m;
+  sample_pdf_core([&](int j) { return b[j]; }, Sc, nfine, wcol, 1, u != nullptr ? u + (size_t)r * nfine : nullptr, zs,
+                  inds != nullptr ? inds + (size_t)r * nfine : nullptr);
+  for (int k = 0; k < nfine; ++k) samples[(size_t)r * nfine + k] = zs[k];
+}
+}  // namespace hav
+
+extern "C" int hav_sample_pdf(const float *bins, const float *weights, const float *u, int n, int m, int nfine, float *samples,
+                              int32_t *inds, float *scratch, void *stream) {
+  if (n < 0 || m < 2 || m + 1 > hav::kMaxSamples || nfine < 1 || nfine > hav::kMaxFine) return HAV_E_SHAPE;
+  if (n == 0) return HAV_OK;
+  if (bins == nullptr || weights == nullptr || samples == nullptr || scratch == nullptr) return HAV_E_NULL;
+  hav::sample_pdf_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bins, weights, u, n, m, nfine, samples, inds, scratch);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? HAV_OK : (int)e;
+}
+

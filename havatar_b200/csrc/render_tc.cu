@@ -28,6 +28,11 @@ __device__ __forceinline__ uint16_t to16(float v) {
   if (kBF16) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
   return __half_as_ushort(__float2half_rn(v));
 }
+// HAV_RENDER_CHECK_RANGE: an operand that does not fit fp16 (it would become inf) is reported in bit 0 of *status
+template <bool kBF16>
+__device__ __forceinline__ void range_note(float v, int32_t *status) {
+  if (!kBF16 && status != nullptr && fabsf(v) > 65504.0f) atomicOr(status, 1);
+}
 
 // Weight image = the exact bytes of the shared-memory weight region: three K-major matrices in [K/8][rows][8]
 // order.  Internal K order of L0: 0..63 plane-0 channels, 64..127 plane-1 channels (the reference interleaves
@@ -37,7 +42,7 @@ __global__ void pack_mlp_16_kernel(const float *__restrict__ w0, const float *__
                                    const float *__restrict__ w1, const float *__restrict__ b1,
                                    const float *__restrict__ wa, const float *__restrict__ ba,
                                    const float *__restrict__ wf, const float *__restrict__ bf,
-                                   const float *__restrict__ wr, const float *__restrict__ br, uint16_t *img) {
+                                   const float *__restrict__ wr, const float *__restrict__ br, uint16_t *img, int32_t *status) {
   const int total = kWImgBytes / 2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int byte = i * 2;
@@ -70,6 +75,7 @@ __global__ void pack_mlp_16_kernel(const float *__restrict__ w0, const float *__
         }
       }
     }
+    range_note<kBF16>(v, status);
     img[i] = to16<kBF16>(v);
   }
 }
@@ -79,7 +85,7 @@ __global__ void pack_mlp_16_kernel(const float *__restrict__ w0, const float *__
 // (utils/util.py:404) becomes a plain in-bounds read.  One block per (plane*B+b, y) row.
 template <bool kBF16>
 __global__ void __launch_bounds__(256) pack_planes_kernel(const float *__restrict__ planes, uint16_t *__restrict__ out,
-                                                          int H, int W) {
+                                                          int H, int W, int32_t *status) {
   extern __shared__ float tile[];   // [64][W+1]
   const int img = blockIdx.y, y = blockIdx.x;
   const int Hp = H + kPadLo + kPadHi, Wp = W + kPadLo + kPadHi;
@@ -92,6 +98,7 @@ __global__ void __launch_bounds__(256) pack_planes_kernel(const float *__restric
   uint16_t *dst = out + (((size_t)img * Hp + (y + kPadLo)) * Wp + kPadLo) * kPlaneC;
   for (int i = threadIdx.x; i < kPlaneC * W; i += blockDim.x) {
     int x = i / kPlaneC, c = i % kPlaneC;
+    range_note<kBF16>(tile[c * (W + 1) + x], status);
     dst[(size_t)x * kPlaneC + c] = to16<kBF16>(tile[c * (W + 1) + x]);
   }
 }
@@ -329,7 +336,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_kernel(const RenderDev 
       if (pass == 0 && npass == 2) {
         auto zc = [&](int s) { return coarse_z(P, ray, gi, s); };
         sample_pdf_merge(zc, P.Sc, P.nfine, wcol, kRaysPerBlock, P.u_rand != nullptr ? P.u_rand + (size_t)gi * P.nfine : nullptr,
-                         zcol);
+                         zcol,
+                         (ray.valid && P.pdf_inds != nullptr) ? P.pdf_inds + (size_t)g * P.nfine : nullptr);
         if (ray.valid && P.z_fine != nullptr)
           for (int j = 0; j < P.Sf; ++j) P.z_fine[(size_t)g * P.Sf + j] = zcol[j * kRaysPerBlock];
       }
@@ -351,14 +359,11 @@ uint64_t tc_planes_bytes(int nimg, int H, int W) {
   return (uint64_t)nimg * (H + tc::kPadLo + tc::kPadHi) * (W + tc::kPadLo + tc::kPadHi) * kPlaneC * 2;
 }
 
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
+static int sm_count() {   // of the CURRENT device (not cached: a process may drive several GPUs)
+  int n = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
   return n;
 }
 
@@ -369,16 +374,17 @@ int tc_num_ctas(int num_ray_blocks) {
 }
 int tc_scratch_slots(int num_ray_blocks) { return tc_num_ctas(num_ray_blocks) * tc::kWGs; }
 
-void launch_pack_mlp_16(const hav_render_args *a, uint8_t *wimg, cudaStream_t st) {
+void launch_pack_mlp_16(const hav_render_args *a, uint8_t *wimg, cudaStream_t st, int32_t *status) {
   if (a->precision == HAV_PREC_BF16)
     tc::pack_mlp_16_kernel<true><<<54, 256, 0, st>>>(a->w0, a->b0, a->w1, a->b1, a->w_alpha, a->b_alpha, a->w_feat, a->b_feat,
-                                                      a->w_rgb, a->b_rgb, (uint16_t *)wimg);
+                                                      a->w_rgb, a->b_rgb, (uint16_t *)wimg, status);
   else
     tc::pack_mlp_16_kernel<false><<<54, 256, 0, st>>>(a->w0, a->b0, a->w1, a->b1, a->w_alpha, a->b_alpha, a->w_feat, a->b_feat,
-                                                       a->w_rgb, a->b_rgb, (uint16_t *)wimg);
+                                                       a->w_rgb, a->b_rgb, (uint16_t *)wimg, status);
 }
 
-cudaError_t launch_pack_planes_16(const float *planes, uint16_t *out, int nimg, int H, int W, bool bf16, cudaStream_t st) {
+cudaError_t launch_pack_planes_16(const float *planes, uint16_t *out, int nimg, int H, int W, bool bf16, cudaStream_t st,
+                                  int32_t *status) {
   cudaError_t e = cudaMemsetAsync(out, 0, tc_planes_bytes(nimg, H, W), st);
   if (e != cudaSuccess) return e;
   const size_t smem = (size_t)kPlaneC * (W + 1) * sizeof(float);
@@ -386,11 +392,11 @@ cudaError_t launch_pack_planes_16(const float *planes, uint16_t *out, int nimg, 
   if (bf16) {
     e = cudaFuncSetAttribute(tc::pack_planes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tc::pack_planes_kernel<true><<<grid, 256, smem, st>>>(planes, out, H, W);
+    tc::pack_planes_kernel<true><<<grid, 256, smem, st>>>(planes, out, H, W, status);
   } else {
     e = cudaFuncSetAttribute(tc::pack_planes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tc::pack_planes_kernel<false><<<grid, 256, smem, st>>>(planes, out, H, W);
+    tc::pack_planes_kernel<false><<<grid, 256, smem, st>>>(planes, out, H, W, status);
   }
   return cudaGetLastError();
 }

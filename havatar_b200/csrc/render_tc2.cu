@@ -211,7 +211,7 @@ __device__ __forceinline__ void producer_loop(const RenderDev &P, int num_ray_bl
 // ------------------------------------------------------------------------------------------------
 // consumer: GEMMs, epilogues, composite, hierarchical resampling, output
 // ------------------------------------------------------------------------------------------------
-template <bool kBF16>
+template <bool kBF16, bool kCheck>
 __device__ __forceinline__ void consumer_loop(const RenderDev &P, int num_ray_blocks, uint32_t smem_base, uint32_t tmem_base,
                                               int pair, int warp, int t) {
   const bool issuer = warp == 0;   // `pair` and `warp` are warp-uniform (shuffled from lane 0 by the caller)
@@ -223,7 +223,7 @@ __device__ __forceinline__ void consumer_loop(const RenderDev &P, int num_ray_bl
   const uint32_t tm_acc0 = tmem_base + pair * 256, tm_acc1 = tm_acc0 + 128;
   const uint32_t tm_lane = (uint32_t)(warp * 32) << 16;
   constexpr uint32_t kIdesc128 = instr_desc(128, kBF16), kIdescH = instr_desc(kNH, kBF16);
-  uint32_t n = 0, mma_phase = 0;
+  uint32_t n = 0, mma_phase = 0, sat = 0;
 
   for (int rb = blockIdx.x * kPairs + pair; rb < num_ray_blocks; rb += gridDim.x * kPairs) {
     const int g = rb * kRaysPerBlock + t;
@@ -285,7 +285,7 @@ __device__ __forceinline__ void consumer_loop(const RenderDev &P, int num_ray_bl
         mma_phase ^= 1;
         tc_fence_after();
         TOCK(10, tk);
-        hidden_epilogue<kBF16, true>(tm_acc0 + tm_lane, nullptr, t);
+        hidden_epilogue<kBF16, true, kCheck>(tm_acc0 + tm_lane, nullptr, t, &sat);
         TOCK(11, tk);
         bar_named(1 + pair);
         TOCK(12, tk);
@@ -302,7 +302,7 @@ __device__ __forceinline__ void consumer_loop(const RenderDev &P, int num_ray_bl
         mma_phase ^= 1;
         tc_fence_after();
         TOCK(14, tk);
-        hidden_epilogue<kBF16, true>(tm_acc1 + tm_lane, nullptr, t);
+        hidden_epilogue<kBF16, true, kCheck>(tm_acc1 + tm_lane, nullptr, t, &sat);
         TOCK(15, tk);
         bar_named(1 + pair);
         TOCK(16, tk);
@@ -359,7 +359,8 @@ __device__ __forceinline__ void consumer_loop(const RenderDev &P, int num_ray_bl
       if (pass == 0 && npass == 2) {
         auto zc = [&](int s) { return coarse_z(P, ray, gi, s); };
         sample_pdf_merge(zc, P.Sc, P.nfine, wcol, kRaysPerBlock, P.u_rand != nullptr ? P.u_rand + (size_t)gi * P.nfine : nullptr,
-                         zcol);
+                         zcol,
+                         (ray.valid && P.pdf_inds != nullptr) ? P.pdf_inds + (size_t)g * P.nfine : nullptr);
         if (ray.valid && P.z_fine != nullptr)
           for (int j = 0; j < P.Sf; ++j) P.z_fine[(size_t)g * P.Sf + j] = zcol[j * kRaysPerBlock];
         __threadfence_block();
@@ -367,9 +368,10 @@ __device__ __forceinline__ void consumer_loop(const RenderDev &P, int num_ray_bl
       }
     }
   }
+  if (kCheck && sat != 0 && P.status != nullptr) atomicOr(P.status, 2);   // a hidden activation was clipped to 65504
 }
 
-template <bool kBF16>
+template <bool kBF16, bool kCheck>
 __global__ void __launch_bounds__(kThreads2, 1) render_tc2_kernel(const RenderDev P, int num_ray_blocks) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(kThreads2, 1) render_tc2_kernel(const RenderDe
   const int pair = (warp_u >> 2) & 1, t = tid & 127;
   if (warp_u < 8) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
-    consumer_loop<kBF16>(P, num_ray_blocks, smem_base, tmem_base, pair, warp_u & 3, t);
+    consumer_loop<kBF16, kCheck>(P, num_ray_blocks, smem_base, tmem_base, pair, warp_u & 3, t);
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
     producer_loop<kBF16>(P, num_ray_blocks, smem, smem_base, pair, t);
@@ -431,11 +433,11 @@ int tc2_num_ctas(int num_ray_blocks) {
   return want < sms ? (want > 0 ? want : 1) : sms;
 }
 
-template <bool kBF16>
+template <bool kBF16, bool kCheck = false>
 static cudaError_t launch_tc2(const RenderDev &P, int num_ray_blocks, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(tc2::render_tc2_kernel<kBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kSmemBytes2);
+  cudaError_t e = cudaFuncSetAttribute(tc2::render_tc2_kernel<kBF16, kCheck>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kSmemBytes2);
   if (e != cudaSuccess) return e;
-  tc2::render_tc2_kernel<kBF16><<<tc2_num_ctas(num_ray_blocks), tc2::kThreads2, tc2::kSmemBytes2, st>>>(P, num_ray_blocks);
+  tc2::render_tc2_kernel<kBF16, kCheck><<<tc2_num_ctas(num_ray_blocks), tc2::kThreads2, tc2::kSmemBytes2, st>>>(P, num_ray_blocks);
   return cudaGetLastError();
 }
 
@@ -451,6 +453,7 @@ extern "C" int hav_debug_phase_cycles(unsigned long long *out32, int reset) {
 #endif
 
 cudaError_t launch_render_16_v2(const RenderDev &P, int num_ray_blocks, bool bf16, cudaStream_t st) {
+  if (!bf16 && P.status != nullptr) return launch_tc2<false, true>(P, num_ray_blocks, st);   // HAV_RENDER_CHECK_RANGE
   return bf16 ? launch_tc2<true>(P, num_ray_blocks, st) : launch_tc2<false>(P, num_ray_blocks, st);
 }
 

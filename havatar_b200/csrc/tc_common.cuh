@@ -173,8 +173,9 @@ __device__ __forceinline__ uint32_t mul2(uint32_t a, uint32_t w) {
 // next layer.  kTS: in place over the accumulator's columns [0,64) as packed pairs, plus the constant bias
 // column pair (1,0) at column 64 (columns 65..71 zero) -- reads of columns [32q, 32q+32) always precede the
 // write of [16q, 16q+16).  !kTS: shared-memory chunks 0..15 (the constant chunk 22/23 carries the bias column).
-template <bool kBF16, bool kTS>
-__device__ __forceinline__ void hidden_epilogue(uint32_t tm_row, uint8_t *Abuf, int t) {
+// kCheck (fp16 only): *sat collects whether any packed value sits at the saturation value 65504 (0x7BFF).
+template <bool kBF16, bool kTS, bool kCheck = false>
+__device__ __forceinline__ void hidden_epilogue(uint32_t tm_row, uint8_t *Abuf, int t, uint32_t *sat = nullptr) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     uint32_t r[32];
@@ -183,6 +184,10 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tm_row, uint8_t *Abuf, 
     uint32_t v[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) v[c] = pack_relu<kBF16>(__uint_as_float(r[2 * c]), __uint_as_float(r[2 * c + 1]));
+    if (kCheck) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) *sat |= __vcmpeq2(v[c], 0x7BFF7BFFu);
+    }
     if (kTS) {
       HAV_TMEM_ST16(tm_row + q * 16, v);
     } else {

@@ -4,7 +4,7 @@ UNMODIFIED reference wrappers import (`import fused`, `import upfirdn2d`: model/
 model/op/upfirdn2d.py:19), so the reference tree runs on these kernels without being edited."""
 import sys
 
-from . import fused, upfirdn2d_op
+from . import conv2d_gradfix, fused, upfirdn2d_op
 from .fused_act import FusedLeakyReLU, fused_leaky_relu
 from .upfirdn2d import upfirdn2d
 
@@ -14,4 +14,4 @@ def install_reference_modules():
     sys.modules["upfirdn2d"] = upfirdn2d_op
 
 
-__all__ = ["FusedLeakyReLU", "fused_leaky_relu", "upfirdn2d", "install_reference_modules"]
+__all__ = ["FusedLeakyReLU", "fused_leaky_relu", "upfirdn2d", "conv2d_gradfix", "install_reference_modules"]

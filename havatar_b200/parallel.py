@@ -109,6 +109,54 @@ class FlatAdam:
     def zero_grad(self):
         self.layout.flat_g.zero_()
 
+    # ---- checkpoint compatibility with torch.optim.Adam (train_avatar.py:91,306 save / restore optimizer_state_dict)
+    @property
+    def param_groups(self):
+        """One group, like the reference's optimisers; 'lr' reads the device-side learning rate."""
+        return [{"params": list(self.layout.params), "lr": float(self.state[1]), "betas": self.betas, "eps": self.eps,
+                 "weight_decay": 0, "amsgrad": False}]
+
+    def state_dict(self):
+        """torch.optim.Adam.state_dict() layout: per-parameter 'step' / 'exp_avg' / 'exp_avg_sq' sliced out of the flat moments."""
+        lay = self.layout
+        step = self.state[0].detach().clone().cpu()
+        st = {}
+        for i, (p, o) in enumerate(zip(lay.params, lay.offsets)):
+            st[i] = {"step": step.clone(), "exp_avg": self.m[o:o + p.numel()].view(p.shape).clone(),
+                     "exp_avg_sq": self.v[o:o + p.numel()].view(p.shape).clone()}
+        group = {"lr": float(self.state[1]), "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "params": list(range(len(lay.params)))}
+        return {"state": st, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        """Accepts a torch.optim.Adam state_dict (or one written by state_dict() above) over the same parameter list: the
+        moments are copied into the flat buffers and the step count / learning rate restored, so bias correction resumes where
+        the checkpoint left off.  Parameters without saved state (never stepped) keep zero moments."""
+        lay = self.layout
+        groups = sd["param_groups"]
+        ids = [i for g in groups for i in g["params"]]
+        if len(ids) != len(lay.params):
+            raise ValueError("optimizer state has %d parameters, this FlatAdam has %d" % (len(ids), len(lay.params)))
+        steps = set()
+        with torch.no_grad():
+            self.m.zero_(), self.v.zero_()
+            for pid, p, o in zip(ids, lay.params, lay.offsets):
+                st = sd["state"].get(pid)
+                if st is None:
+                    continue
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError("optimizer state shape %s does not match parameter %s" % (tuple(st["exp_avg"].shape), tuple(p.shape)))
+                self.m[o:o + p.numel()].copy_(st["exp_avg"].reshape(-1))
+                self.v[o:o + p.numel()].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.add(float(st["step"]))
+            if len(steps) > 1:
+                raise ValueError("FlatAdam keeps one step count; the state dict has %s" % sorted(steps))
+            self.state[0:1].fill_(steps.pop() if steps else 0.0)
+            self.state[1:2].fill_(float(groups[0]["lr"]))
+        g = groups[0]
+        self.betas, self.eps = (float(g["betas"][0]), float(g["betas"][1])), float(g["eps"])
+
 
 class _Bucket:
     __slots__ = ("flat", "params", "pending", "ready", "work")

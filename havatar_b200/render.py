@@ -13,7 +13,8 @@ import torch
 
 from . import _lib
 
-RenderOut = namedtuple("RenderOut", "rgb_coarse depth_coarse acc_coarse weights_max rgb_fine depth_fine acc_fine z_fine")
+RenderOut = namedtuple("RenderOut", "rgb_coarse depth_coarse acc_coarse weights_max rgb_fine depth_fine acc_fine z_fine pdf_inds",
+                       defaults=(None,))
 
 MLP_KEYS = ("layers_xyz.0.weight", "layers_xyz.0.bias", "layers_xyz.1.weight", "layers_xyz.1.bias",
             "fc_alpha.weight", "fc_alpha.bias", "fc_rgbFeat.weight", "fc_rgbFeat.bias", "fc_rgb.weight", "fc_rgb.bias")
@@ -70,11 +71,26 @@ def _workspace(device, nbytes):
     return ws
 
 
+def release_workspaces(stream=None):
+    """Drop the cached forward / backward workspaces of `stream` (a torch.cuda.Stream; None = all of them).  Workspaces are
+    cached per (device, stream) and live until released: owners of private streams call this when they are done."""
+    for cache in (_workspaces, _bwd_workspaces):
+        for key in list(cache):
+            if stream is None or key == (stream.device.index, stream.cuda_stream):
+                del cache[key]
+
+
 def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, num_coarse, num_fine=0,
                 boxes=None, t_rand=None, noise_coarse=None, u_rand=None, noise_fine=None, precision="fp16",
-                want_z_fine=False, reuse_packed=False, out=None, return_ctx=False):
+                want_z_fine=False, reuse_packed=False, out=None, return_ctx=False, camera=None, img_hw=None, pixel_index=None,
+                want_pdf_inds=False, check_range=False):
     """ray_batch [B,R,8] (o3 d3 near far; extra trailing columns such as the reference's viewdirs are
-    ignored), background_prior [B,R,3] or None, inv_head_T [B,4,3], planes [2,B,64,H,W], wvol [1,2,D,H,W],
+    ignored) -- or ray_batch=None with camera [B,18] (fx fy cx cy | c2w [3,4] row-major | near far, see `camera_block`),
+    img_hw=(H, W) and optionally pixel_index [B,R] int32 (y * W + x; default: all H*W pixels in row-major order): the rays are
+    then generated inside the kernel (dataloader/data_util.py:28-56) and no per-ray tensor is uploaded.
+    check_range=True (precision 'fp16'): raise HavError when a plane texel / MLP weight does not fit fp16 or a hidden activation
+    saturates at 65504 (HAV_RENDER_CHECK_RANGE; costs one 4-byte device->host read) instead of returning clipped values --
+    models with such magnitudes need precision='bf16'.  background_prior [B,R,3] or None, inv_head_T [B,4,3], planes [2,B,64,H,W], wvol [1,2,D,H,W],
     weights: mapping with the reference's model_coarse keys (MLP_KEYS).  Random draws are explicit inputs
     (SURVEY.md section 8a quirk v): t_rand [B,R,Sc], noise_* [B,R,S] already scaled by the noise std,
     u_rand [B,R,num_fine]; None switches that randomness off (u_rand None == sample_pdf det=True).
@@ -83,13 +99,27 @@ def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, 
     return_ctx=True additionally returns the call's argument block (a RenderCtx that keeps every tensor alive) for
     render_backward.  Returns RenderOut of [B,R,*] tensors (fine slots None when num_fine == 0)."""
     L = _lib.lib()
-    if ray_batch.dim() != 3 or ray_batch.shape[-1] < 8:
-        raise _lib.HavError("ray_batch must be [B,R,>=8]")
-    if ray_batch.shape[-1] > 8:
-        ray_batch = ray_batch[..., :8]
-    ray_batch = _f32c(ray_batch, "ray_batch")
-    dev = ray_batch.device
-    B, R = int(ray_batch.shape[0]), int(ray_batch.shape[1])
+    if camera is not None:
+        camera = _f32c(camera, "camera")
+        if camera.dim() != 2 or camera.shape[1] != 18 or img_hw is None:
+            raise _lib.HavError("camera must be [B,18] and img_hw=(H, W) must be given")
+        dev, B = camera.device, int(camera.shape[0])
+        if pixel_index is not None:
+            if not pixel_index.is_cuda or pixel_index.dtype != torch.int32 or pixel_index.dim() != 2 or pixel_index.shape[0] != B:
+                raise _lib.HavError("pixel_index must be a CUDA int32 tensor [B,R]")
+            pixel_index = pixel_index.contiguous()
+            R = int(pixel_index.shape[1])
+        else:
+            R = int(img_hw[0]) * int(img_hw[1])
+        ray_batch = None
+    else:
+        if ray_batch is None or ray_batch.dim() != 3 or ray_batch.shape[-1] < 8:
+            raise _lib.HavError("ray_batch must be [B,R,>=8]")
+        if ray_batch.shape[-1] > 8:
+            ray_batch = ray_batch[..., :8]
+        ray_batch = _f32c(ray_batch, "ray_batch")
+        dev = ray_batch.device
+        B, R = int(ray_batch.shape[0]), int(ray_batch.shape[1])
     planes = _f32c(planes, "planes")
     if planes.dim() != 5 or planes.shape[0] != 2 or planes.shape[1] != B:
         raise _lib.HavError("planes must be [2,B,C,H,W] with B == ray_batch.shape[0]")
@@ -100,7 +130,8 @@ def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, 
     a = _lib.RenderArgs()
     a.struct_bytes = C.sizeof(_lib.RenderArgs)
     a.precision = _lib.PRECISIONS[precision]
-    a.flags = 1 if reuse_packed else 0
+    check_range = bool(check_range) and precision == "fp16"
+    a.flags = (1 if reuse_packed else 0) | (2 if check_range else 0)
     a.batch, a.rays, a.num_coarse, a.num_fine = B, R, int(num_coarse), int(num_fine)
     a.plane_c, a.plane_h, a.plane_w = int(planes.shape[2]), int(planes.shape[3]), int(planes.shape[4])
     a.vol_d, a.vol_h, a.vol_w = int(wvol.shape[2]), int(wvol.shape[3]), int(wvol.shape[4])
@@ -108,8 +139,11 @@ def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, 
     for i in range(3):
         a.plane_scale[i], a.plane_trans[i] = float(ps[i]), float(pt[i])
         a.skin_scale[i], a.skin_trans[i] = float(ss[i]), float(st[i])
-    keep = [ray_batch, planes, wvol]
+    keep = [ray_batch, planes, wvol, camera, pixel_index]
     a.ray_batch, a.planes, a.wvol = _ptr(ray_batch), _ptr(planes), _ptr(wvol)
+    if camera is not None:
+        a.camera, a.pixel_index = _ptr(camera), _ptr(pixel_index)
+        a.img_h, a.img_w = int(img_hw[0]), int(img_hw[1])
     bg = _f32c(background_prior, "background_prior", (B, R, 3))
     ihT = _f32c(inv_head_T, "inv_head_T", (B, 4, 3))
     a.background, a.inv_head_T = _ptr(bg), _ptr(ihT)
@@ -126,11 +160,13 @@ def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, 
     new = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
     prev = out
     out = dict(rgb_coarse=new(B, R, 67), depth_coarse=new(B, R, 1), acc_coarse=new(B, R, 1), weights_max=new(B, R, 1),
-               rgb_fine=None, depth_fine=None, acc_fine=None, z_fine=None)
+               rgb_fine=None, depth_fine=None, acc_fine=None, z_fine=None, pdf_inds=None)
     if num_fine > 0:
         out.update(rgb_fine=new(B, R, 67), depth_fine=new(B, R, 1), acc_fine=new(B, R, 1))
         if want_z_fine:
             out["z_fine"] = new(B, R, Sf)
+        if want_pdf_inds:
+            out["pdf_inds"] = torch.empty((B, R, num_fine), dtype=torch.int32, device=dev)
     if prev is not None:
         for k in out:
             v = getattr(prev, k)
@@ -139,6 +175,11 @@ def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, 
             out[k] = v
     for k, v in out.items():
         setattr(a, k, _ptr(v))
+    status = None
+    if check_range:
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        a.range_status = _ptr(status)
+        keep.append(status)
     with torch.cuda.device(dev):
         need = int(L.hav_render_workspace_bytes(C.byref(a)))
         if need == 0 and B * R > 0:
@@ -148,6 +189,11 @@ def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, 
         a.workspace, a.workspace_bytes = C.c_void_p(ws.data_ptr()), ws.numel()
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(L.hav_render_forward(C.byref(a), C.c_void_p(stream)), "hav_render_forward")
+    if status is not None:
+        bits = int(status.item())
+        if bits:
+            what = [w for b, w in ((1, "a plane texel or MLP weight exceeds 65504"), (2, "a hidden activation saturated at 65504")) if bits & b]
+            raise _lib.HavError("fp16 operand range exceeded (%s): render with precision='bf16'" % "; ".join(what))
     res = RenderOut(**out)
     if return_ctx:
         return res, RenderCtx(a, keep, res, dev)
@@ -227,6 +273,9 @@ class _RenderFunction(torch.autograd.Function):
         ctx.rctx = rctx
         rctx.keep.append(out.z_fine)
         rctx.out = None
+        # backward re-reads planes / wvol / the MLP tensors through raw pointers: remember their versions so that an in-place
+        # update between forward and backward (an optimiser step, EMA, load_state_dict) raises like stock autograd would
+        ctx.input_versions = [(t, t._version) for t in (planes, wvol) + tuple(mlp)]
         ctx.save_for_backward(*[t for t in out[:7] if t is not None])   # keeps the storages hav_render_backward reads alive
         ctx.mark_non_differentiable(out.weights_max)
         res = [out.rgb_coarse, out.depth_coarse, out.acc_coarse, out.weights_max]
@@ -235,7 +284,12 @@ class _RenderFunction(torch.autograd.Function):
         return tuple(res)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, *g):
+        for t, v in ctx.input_versions:
+            if t._version != v:
+                raise RuntimeError("havatar_b200 render: an input needed for the backward pass (%s) was modified in place after "
+                                   "the forward (version %d -> %d)" % (tuple(t.shape), v, t._version))
         cont = lambda t: None if t is None else t.contiguous()
         kw = dict(g_rgb_coarse=cont(g[0]), g_depth_coarse=cont(g[1]), g_acc_coarse=cont(g[2]))
         if len(g) > 4:
@@ -257,7 +311,38 @@ def render_rays_autograd(ray_batch, background_prior, inv_head_T, planes, wvol, 
                 u_rand=u_rand, noise_fine=noise_fine, precision=precision)
     res = _RenderFunction.apply(opts, ray_batch, background_prior, inv_head_T, planes, wvol, *[weights[k] for k in MLP_KEYS])
     res = tuple(res) + (None,) * (7 - len(res))
-    return RenderOut(*res, None)
+    return RenderOut(*res, None, None)
+
+
+def sample_pdf(bins, weights, num_samples, u=None):
+    """utils/nerf_util.py:76-117 on the device function the render kernels run (hav_sample_pdf): bins [N,M], weights [N,M-1],
+    u [N,num_samples] uniform draws or None (det=True).  -> (samples [N,num_samples], inds [N,num_samples] int32)."""
+    L = _lib.lib()
+    bins, weights, u = _f32c(bins, "bins"), _f32c(weights, "weights"), _f32c(u, "u")
+    n, m = int(bins.shape[0]), int(bins.shape[1])
+    if tuple(weights.shape) != (n, m - 1):
+        raise _lib.HavError("weights must be [N, M-1]")
+    samples = torch.empty((n, num_samples), dtype=torch.float32, device=bins.device)
+    inds = torch.empty((n, num_samples), dtype=torch.int32, device=bins.device)
+    scratch = torch.empty((n, m + 1), dtype=torch.float32, device=bins.device)
+    with torch.cuda.device(bins.device):
+        _lib.check(L.hav_sample_pdf(_ptr(bins), _ptr(weights), _ptr(u), n, m, int(num_samples), _ptr(samples), _ptr(inds),
+                                    _ptr(scratch), C.c_void_p(torch.cuda.current_stream(bins.device).cuda_stream)), "hav_sample_pdf")
+    return samples, inds
+
+
+def camera_block(intr, c2w, near, far, device="cuda"):
+    """The [B,18] camera tensor of render_rays(camera=...): intr [B,4] or [4] (fx, fy, cx, cy), c2w [B,3,4] / [B,4,4] / [3,4],
+    near / far scalars or [B] (dataloader/dataloader.py:174-177: |T_ori[:3,3]| + {near,far} * length).  72 bytes per frame
+    instead of the 8.4 MB ray tensor of a 512 x 512 frame."""
+    intr = np.asarray(intr, dtype=np.float32).reshape(-1, 4)
+    c2w = np.asarray(c2w, dtype=np.float32)
+    c2w = c2w.reshape((-1,) + c2w.shape[-2:])[:, :3, :4].reshape(-1, 12)
+    B = max(intr.shape[0], c2w.shape[0])
+    nf = np.stack([np.broadcast_to(np.asarray(near, dtype=np.float32).reshape(-1), (B,)),
+                   np.broadcast_to(np.asarray(far, dtype=np.float32).reshape(-1), (B,))], axis=1)
+    cam = np.concatenate([np.broadcast_to(intr, (B, 4)), np.broadcast_to(c2w, (B, 12)), nf], axis=1).astype(np.float32)
+    return torch.from_numpy(np.ascontiguousarray(cam)).to(device)
 
 
 def get_rays(height, width, intr, c2w, near, far, device="cuda"):
@@ -397,3 +482,14 @@ class PipelinedHostRenderer:
         sl = self.slots[(self.i - 1) % self.DEPTH]
         sl["ev_out"].synchronize()
         return sl["host"]
+
+    def close(self):
+        """Release the render workspace cached for this renderer's private compute stream."""
+        self.s_comp.synchronize()
+        release_workspaces(self.s_comp)
+
+    def __del__(self):
+        try:
+            release_workspaces(self.s_comp)
+        except Exception:
+            pass

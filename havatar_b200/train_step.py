@@ -25,13 +25,25 @@ import torch.nn.functional as F
 from . import parallel, styleunet, trainer
 
 
-def default_cfg(num_coarse=64, num_fine=16, perturb=True, noise_std=0.1, inp_size=128, out_size=512):
-    """The fields of config/singleview_512_base.yml the orchestrator and the steps read."""
+def default_cfg(num_coarse=64, num_fine=16, perturb=True, noise_std=0.1, inp_size=128, out_size=512, lr=5e-4):
+    """The fields of config/singleview_512_base.yml the orchestrator and the steps read (lr: optimizer.lr, 5e-4 in
+    singleview_512_base.yml:87, 1e-4 in singleview_512_HD_base.yml:116; scheduler: :90-94)."""
     mode = lambda p, s: NS(num_coarse=num_coarse, num_fine=num_fine, perturb=p, radiance_field_noise_std=s, chunksize=4096)
     return NS(experiment=NS(latent_code_dim=32, cond_pose=True, cond_expr=False, model_mode=None, mask_weight=0.01),
-              models=NS(coarse=NS(XYZ_bounding=[[-1.5, 1.5], [-1.6, 1.4], [-1.6, 1.2]]),
+              models=NS(coarse=NS(XYZ_bounding=[[-1.5, 1.5], [-1.6, 1.4], [-1.6, 1.2]],
+                                  Head_bounding=[[-1.2, 1.2], [-1.6, 1.0], [-1.6, 1.2]]),
                         StyleUnet=NS(inp_size=inp_size, out_size=out_size)),
+              optimizer=NS(type="Adam", lr=lr), scheduler=NS(lr_decay=250, lr_decay_factor=0.1),
               nerf=NS(train=mode(perturb, noise_std), validation=mode(False, 0.0)))
+
+
+def _cfg_get(cfg, path, default):
+    cur = cfg
+    for name in path.split("."):
+        cur = getattr(cur, name, None)
+        if cur is None:
+            return default
+    return cur
 
 
 def d_logistic_loss(real_pred, fake_pred):                      # utils/styleUnet_util.py:65-69
@@ -43,7 +55,10 @@ def g_nonsaturating_loss(fake_pred):                            # utils/styleUne
 
 
 def d_r1_loss(real_pred, real_img):                             # utils/styleUnet_util.py:72-79
-    grad_real, = torch.autograd.grad(outputs=real_pred.sum(), inputs=real_img, create_graph=True)
+    from .op import conv2d_gradfix
+
+    with conv2d_gradfix.no_weight_gradients():
+        grad_real, = torch.autograd.grad(outputs=real_pred.sum(), inputs=real_img, create_graph=True)
     return grad_real.pow(2).reshape(grad_real.shape[0], -1).sum(1).mean()
 
 
@@ -104,13 +119,19 @@ class _Group:
 
 
 class StageOneStep:
-    def __init__(self, n_frames=4, device="cuda", cfg=None, precision="fp16", patch=64, lr=5e-4, with_discriminator=True, seed=0,
-                 capturable=False):
+    def __init__(self, n_frames=4, device="cuda", cfg=None, precision="fp16", patch=64, lr=None, with_discriminator=True, seed=0,
+                 capturable=False, pretrain_wc_iters=0):
+        """pretrain_wc_iters > 0: a run that does not resume from a checkpoint first fits the skinning-weight volume to the head
+        box (train_avatar.py:93-95 uses 3000 iterations); load a checkpoint into `self.net` instead when resuming."""
         torch.manual_seed(seed)
         self.cfg = cfg or default_cfg()
+        lr = float(_cfg_get(self.cfg, "optimizer.lr", 5e-4)) if lr is None else lr
         self.device = torch.device(device)
         self.net = trainer.Trainer(self.cfg, n_frames, precision=precision).to(self.device)
         self.net.device_rng = capturable
+        if pretrain_wc_iters > 0:
+            self.net.headpose_skin_net.pretrain_wc(num_iter=pretrain_wc_iters,
+                                                   vol_thr=_cfg_get(self.cfg, "models.coarse.Head_bounding", None))
         self.disc = styleunet.Discriminator(patch, img_channel=3).to(self.device) if with_discriminator else None
         mods = [self.net] + ([self.disc] if self.disc is not None else [])
         if _distributed():
@@ -124,8 +145,12 @@ class StageOneStep:
 
     def pre_step(self):
         """Host-side bookkeeping of one iteration (outside any CUDA graph): the exponential learning-rate decay of
-        train_avatar.py:154-158, applied to the coming step."""
-        self.g.set_lr(max(self.lr0 * (0.1 ** (self.it / 250000.0)), 5e-5))
+        train_avatar.py:154-158.  The reference sets lr(i) AFTER optimizer.step() of iteration i (0-based), so iteration i runs
+        with lr(i - 1) and iteration 0 with the undecayed rate."""
+        if self.it > 0:
+            steps = float(_cfg_get(self.cfg, "scheduler.lr_decay", 250)) * 1000.0
+            factor = float(_cfg_get(self.cfg, "scheduler.lr_decay_factor", 0.1))
+            self.g.set_lr(max(self.lr0 * (factor ** ((self.it - 1) / steps)), 5e-5))
         self.it += 1
 
     def parts(self):
@@ -176,9 +201,12 @@ class StageOneStep:
 
 class StageTwoStep:
     def __init__(self, n_frames=8, device="cuda", cfg=None, precision="fp16", render_size=128, gen_size=512, d_reg_every=16,
-                 r1=10.0, latent=64, n_mlp=4, seed=0, capturable=False):
+                 r1=10.0, latent=64, n_mlp=4, seed=0, capturable=False, lr=1e-3, nerf_lr=None):
+        """lr: su_args.lr as train_avatarHD.py:118 overrides it (1e-3); nerf_lr: cfg.optimizer.lr (1e-4 in
+        config/singleview_512_HD_base.yml:116)."""
         torch.manual_seed(seed)
-        self.cfg = cfg or default_cfg(inp_size=render_size, out_size=gen_size)
+        self.cfg = cfg or default_cfg(inp_size=render_size, out_size=gen_size, lr=1e-4)
+        nerf_lr = float(_cfg_get(self.cfg, "optimizer.lr", 1e-4)) if nerf_lr is None else nerf_lr
         self.device = torch.device(device)
         self.net = trainer.Trainer(self.cfg, n_frames, precision=precision).to(self.device)                 # train_avatarHD.py:109
         self.net.device_rng = capturable
@@ -191,9 +219,9 @@ class StageTwoStep:
         if _distributed():
             parallel.broadcast_parameters([self.net, self.generator, self.g_ema, self.disc])
         g_ratio, d_ratio = 4 / 5, d_reg_every / (d_reg_every + 1)                                            # :117-122
-        self.nerf = _Group([self.net], 5e-4)
-        self.g = _Group([self.generator], 2e-3 * g_ratio, betas=(0.0, 0.99 ** g_ratio))
-        self.d = _Group([self.disc], 2e-3 * d_ratio, betas=(0.0, 0.99 ** d_ratio))
+        self.nerf = _Group([self.net], nerf_lr)                                                              # :121
+        self.g = _Group([self.generator], lr * g_ratio, betas=(0.0, 0.99 ** g_ratio))                        # :119
+        self.d = _Group([self.disc], lr * d_ratio, betas=(0.0, 0.99 ** d_ratio))                             # :120
         self.render_size, self.gen_size, self.latent = render_size, gen_size, latent
         self.d_reg_every, self.r1, self.it = d_reg_every, r1, 0
         self.accum = 0.5 ** (32 / (10 * 1000))                                                               # :162
@@ -202,12 +230,14 @@ class StageTwoStep:
     def groups(self):
         return [self.nerf, self.g, self.d]
 
-    def _noise(self, b):                                             # mixing_noise with mixing = 0 (:170-175)
-        return [torch.randn(b, self.latent, device=self.device)]
+    def _noise(self, b, given=None):                                 # mixing_noise with mixing = 0 (:170-175)
+        return [given] if given is not None else [torch.randn(b, self.latent, device=self.device)]
 
     def pre_step(self):
+        """self.it counts iterations STARTED; the reference's 0-based index i = self.it - 1 gates R1 (i % d_reg_every == 0, so
+        iteration 0 regularises, :209) and sets the GAN weight (:205-206)."""
         self.it += 1
-        self.gan_w.fill_(min(1e-3 * 1.1 ** (self.it // 500), 0.1))                                             # :205-206
+        self.gan_w.fill_(min(1e-3 * 1.1 ** ((self.it - 1) // 500), 0.1))                                       # :205-206
 
     def parts(self):
         return [("d", self.d_step, True), ("r1", self.r1_step, False), ("g", self.g_step, True)]
@@ -221,26 +251,29 @@ class StageTwoStep:
             out.update(fn(batch) or {})
         return out
 
-    def _inp(self, batch):
+    def _inp(self, batch, phase):
+        """Optional explicit draws for parity tests (SURVEY.md section 8a quirk v): batch['randoms_d' / 'randoms_g'] = the
+        render's random tensors, batch['z_d' / 'z_g'] = the mixing noise, batch['gen_noise_d' / 'gen_noise_g'] = the per-layer
+        generator noise maps of the D-step / G-step forward."""
         return dict(mode="train", fidx=batch["fidx"], render_full_img=True, ray_batch=batch["ray_batch"],
                     background_prior=batch["background_prior"], inv_head_T=batch["inv_head_T"],
                     front_render_cond=batch["front_render_cond"], left_render_cond=batch["left_render_cond"],
-                    right_render_cond=batch["right_render_cond"])
+                    right_render_cond=batch["right_render_cond"], randoms=batch.get("randoms_" + phase))
 
     def d_step(self, batch):                                                                                    # :211-231
         gt_hr = batch["gt_hr_img"]
         B = gt_hr.shape[0]
         self.nerf.requires_grad(False), self.g.requires_grad(False), self.d.requires_grad(True)
         with torch.no_grad():
-            render, _, _ = self.net(**self._inp(batch))
-            fake = self.generator(self._noise(B), render[:, 3:].contiguous())
+            render, _, _ = self.net(**self._inp(batch, "d"))
+            fake = self.generator(self._noise(B, batch.get("z_d")), render[:, 3:].contiguous(), noise=batch.get("gen_noise_d"))
         d_loss = d_logistic_loss(self.disc(gt_hr), self.disc(fake)) * self.gan_w
         d_loss.backward()
         self.d.step()
-        return {"d_loss": d_loss.detach()}
+        return {"d_loss": d_loss.detach(), "d": (d_loss / self.gan_w).detach()}
 
     def r1_step(self, batch):                                                                                   # :233-240
-        if self.it % self.d_reg_every != 0:
+        if (self.it - 1) % self.d_reg_every != 0:                                                            # :209 d_regularize
             return {"r1": None}
         self.nerf.requires_grad(False), self.g.requires_grad(False), self.d.requires_grad(True)
         real = batch["gt_hr_img"].detach().requires_grad_(True)
@@ -248,7 +281,7 @@ class StageTwoStep:
         r1_loss = d_r1_loss(pred, real) * self.gan_w
         (self.r1 / 2 * r1_loss * self.d_reg_every + 0 * pred[0]).sum().backward()
         self.d.step()
-        return {"r1": r1_loss.detach()}
+        return {"r1": (r1_loss / self.gan_w).detach()}                                                       # loss_dict["r1"], :240
 
     def g_step(self, batch):                                                                                    # :243-303
         gt_hr, rs, gs = batch["gt_hr_img"], self.render_size, self.gen_size
@@ -256,12 +289,14 @@ class StageTwoStep:
         gt_lr = F.interpolate(F.interpolate(gt_hr, size=(rs, rs), mode="bilinear", align_corners=True), size=(gs, gs),
                               mode="bilinear", align_corners=True)                                              # :202-204
         self.nerf.requires_grad(True), self.g.requires_grad(True), self.d.requires_grad(False)
-        render, mask, lat = self.net(**self._inp(batch))
+        render, mask, lat = self.net(**self._inp(batch, "g"))
         lr_img = F.interpolate(render[:, :3], size=(gs, gs), mode="bilinear", align_corners=True)
-        g_loss = F.mse_loss(lr_img, gt_lr) + lat
-        g_loss = g_loss + self.cfg.experiment.mask_weight * F.binary_cross_entropy(mask.clip(1e-3, 1.0 - 1e-3), batch["gt_lr_mask"])
-        fake = self.generator(self._noise(B), render[:, 3:].contiguous())
-        g_loss = g_loss + g_nonsaturating_loss(self.disc(fake)) * self.gan_w + F.l1_loss(fake, gt_hr)
+        rgb_loss = F.mse_loss(lr_img, gt_lr)
+        mask_loss = self.cfg.experiment.mask_weight * F.binary_cross_entropy(mask.clip(1e-3, 1.0 - 1e-3), batch["gt_lr_mask"])
+        g_loss = rgb_loss + lat + mask_loss
+        fake = self.generator(self._noise(B, batch.get("z_g")), render[:, 3:].contiguous(), noise=batch.get("gen_noise_g"))
+        g_ns, hr_l1 = g_nonsaturating_loss(self.disc(fake)), F.l1_loss(fake, gt_hr)
+        g_loss = g_loss + g_ns * self.gan_w + hr_l1
         g_loss.backward()
         self.g.step()
         self.nerf.step()
@@ -269,7 +304,8 @@ class StageTwoStep:
             pe, pg = list(self.g_ema.parameters()), list(self.generator.parameters())
             torch._foreach_mul_(pe, self.accum)
             torch._foreach_add_(pe, pg, alpha=1 - self.accum)
-        return {"g_loss": g_loss.detach()}
+        return {"g_loss": g_loss.detach(), "rgb_loss": rgb_loss.detach(), "mask_loss": mask_loss.detach(), "g_nonsat": g_ns.detach(),
+                "hr_l1": hr_l1.detach()}
 
 
 class Graphed:

@@ -47,6 +47,30 @@ class _BoxWarp(nn.Module):
     def forward(self, x):
         return x * self.scale_factor + self.trans_factor
 
+    def inv_trans(self, x):
+        """utils/util.py:221-229."""
+        return (x - self.trans_factor.to(x.device)) * (1.0 / self.scale_factor.to(x.device))
+
+
+def voxel_feature(xyz, volume, padding_mode="border"):
+    """utils/util.py:409-418: trilinear fetch of [B,N,3] normalised points from a [B,C,D,H,W] volume -> [B,N,C] (plain torch:
+    only the one-off skinning-volume pre-training and its visualisation use it; the per-sample fetch is in the render kernel)."""
+    B, N, _ = xyz.shape
+    feat = torch.nn.functional.grid_sample(volume, xyz.reshape(B, N, 1, 1, 3), mode="bilinear", padding_mode=padding_mode,
+                                           align_corners=True)
+    return feat[:, :, :, 0, 0].permute(0, 2, 1)
+
+
+def make_volume_pts(steps=50, perturb=False, gridwarper=None):
+    """utils/util.py:239-254: a steps^3 lattice over [-1,1]^3 (optionally jittered by up to one cell), mapped back to world
+    space through the box warp."""
+    c = torch.linspace(-1.0, 1.0, steps=steps, dtype=torch.float32)
+    xv, yv, zv = torch.meshgrid(c, c.clone(), c.clone(), indexing="ij")
+    pts = torch.stack([xv, yv, zv], dim=-1).reshape(-1, 3)
+    if perturb:
+        pts = pts + torch.rand_like(pts) * (2 / (steps - 1))
+    return gridwarper.inv_trans(pts) if gridwarper is not None else pts
+
 
 class _UpConv3D(nn.Module):
     """UpConv3DBlock(up_mode='upsample') (voxel_encoder.py:183-211): keys up.1.{weight,bias}."""
@@ -105,6 +129,56 @@ class SkinningField(nn.Module):
             self.canonical_W = torch.cat([1 - w[:, 1:], w[:, 1:]], dim=1).contiguous()
         self.fix_canoW = True
 
+    def sample_volume(self, pts, padding_mode="border"):
+        """Skinning_Field.py:65-68: bone-0 weight of world-space points [N,3] -> [N,1]."""
+        vol = self.canonical_Wvolume()
+        return voxel_feature(self.gridwarper(pts.unsqueeze(0)), vol[:, 0:1], padding_mode=padding_mode)[0]
+
+    def pretrain_wc(self, num_iter=1, lr=1e-3, save_path=None, pose_space=False, vol_thr=None, progress=False):
+        """Skinning_Field.py:101-125: fit the head-bone channel of the weight volume to the indicator of the head box `vol_thr`
+        (binary cross-entropy on a jittered 20^3 lattice, Adam) -- what train_avatar.py:95 runs for 3000 iterations before a
+        from-scratch stage-one training.  Plain torch: a one-off initialisation, not on the per-frame path."""
+        if vol_thr is None:
+            vol_thr = [[-0.5, 0.5], [-0.8, 0.5], [-0.3, 1.0]]
+        opt = torch.optim.Adam([{"params": self.parameters()}], lr=lr)
+        dev = self.identity_trans.device
+        it = range(num_iter)
+        if progress:
+            from tqdm import tqdm
+            it = tqdm(it)
+        loss = None
+        with torch.enable_grad():
+            for _ in it:
+                pts = make_volume_pts(steps=20, perturb=True, gridwarper=self.gridwarper).to(dev)
+                inside = torch.ones(pts.shape[0], dtype=torch.bool, device=dev)
+                for ax in range(3):
+                    inside &= (pts[:, ax] > vol_thr[ax][0]) & (pts[:, ax] < vol_thr[ax][1])
+                gt = inside.float().unsqueeze(-1)
+                wc = self.canonical_Wvolume()
+                pred = voxel_feature(self.gridwarper(pts.unsqueeze(0)), wc[:, 0:1] if pose_space else wc[:, 1:])
+                loss = torch.nn.functional.binary_cross_entropy(torch.clamp(pred, 0.0, 1.0)[0], gt)
+                loss.backward()
+                opt.step()
+                opt.zero_grad()
+        self._key = None                                     # cached volume is stale
+        styleunet.invalidate_caches()
+        if save_path is not None:
+            torch.save(self.canonical_Wvolume(), save_path)
+        return None if loss is None else float(loss.detach())
+
+    def visualize_motion_weight_vol(self, path):
+        """Skinning_Field.py:127-132: a 20^3 point cloud coloured by the head-bone weight, written as a Wavefront .obj
+        ('v x y z b g r' lines, utils/util.py:111-123)."""
+        dev = self.identity_trans.device
+        with torch.no_grad():
+            pts = make_volume_pts(steps=20, perturb=False, gridwarper=self.gridwarper).to(dev)
+            wc = self.canonical_Wvolume()
+            w = voxel_feature(self.gridwarper(pts.unsqueeze(0)), wc[:, 1:])[0, :, 0].cpu().numpy()
+            v = pts.cpu().numpy()
+        with open(path, "w") as fp:
+            for (x, y, z), c in zip(v, w):
+                fp.write("v %f %f %f %f %f %f\n" % (x, y, z, c, c, c))
+
     def volume(self):
         """[1,2,D,H,W] skinning-weight volume for the kernel (Skinning_Field.py:79), cached per weight version."""
         if self.fix_canoW:
@@ -157,6 +231,10 @@ class PlaneNeRF(nn.Module):
 
 class Trainer(nn.Module):
     def __init__(self, cfg, latent_codes_size=0, freeze_motion=True, precision="fp16"):
+        """precision: 'fp16' (default), 'bf16', 'fp32', or 'auto' = fp16 with the range report on (render.render_rays
+        check_range) and a permanent switch to bf16 the first time an operand leaves the fp16 range (inference renders only).
+        freeze_motion: accepted and, like the reference, without effect -- nerf_trainer.py:35-36 sets `requires_grad` on the
+        MODULE object, which freezes no parameter, so the skinning field trains (SURVEY.md section 8a quirk i)."""
         super().__init__()
         self.cfg = cfg
         ld = cfg.experiment.latent_code_dim
@@ -210,9 +288,23 @@ class Trainer(nn.Module):
             rnd["noise_coarse"] = torch.randn(B, R, nc, device=dev) * std
             if nf > 0:
                 rnd["noise_fine"] = torch.randn(B, R, (nc + 1) // 2 + nf, device=dev) * std
-        render = hrender.render_rays_autograd if torch.is_grad_enabled() else hrender.render_rays
-        o = render(ray_batch, bg, inv_head_T, self.model_coarse.triPlane_embeddings, self.headpose_skin_net.volume(),
-                   self.model_coarse.mlp_weights(), nc, nf, boxes=self._boxes(), precision=self.precision, **rnd)
+        args = (ray_batch, bg, inv_head_T, self.model_coarse.triPlane_embeddings, self.headpose_skin_net.volume(),
+                self.model_coarse.mlp_weights(), nc, nf)
+        prec = "fp16" if self.precision == "auto" else self.precision
+        if torch.is_grad_enabled():
+            o = hrender.render_rays_autograd(*args, boxes=self._boxes(), precision=prec, **rnd)
+        elif self.precision == "auto":
+            try:
+                o = hrender.render_rays(*args, boxes=self._boxes(), precision="fp16", check_range=True, **rnd)
+            except hrender._lib.HavError as e:
+                if "fp16 operand range" not in str(e):
+                    raise
+                import warnings
+                warnings.warn("havatar_b200: %s -- switching this Trainer to bf16 operands" % e)
+                self.precision = "bf16"
+                o = hrender.render_rays(*args, boxes=self._boxes(), precision="bf16", **rnd)
+        else:
+            o = hrender.render_rays(*args, boxes=self._boxes(), precision=prec, **rnd)
         return o.rgb_coarse, o.depth_coarse, o.acc_coarse, o.weights_max, o.rgb_fine, o.depth_fine, o.acc_fine
 
     def forward(self, **data):

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define HAV_ABI_VERSION 1
+#define HAV_ABI_VERSION 2
 
 /* argument errors (negative); positive return values are cudaError_t */
 #define HAV_OK 0
@@ -53,6 +53,9 @@ extern "C" {
                                      hav_render_forward with the same weights/planes/precision/batch: skip re-packing
                                      (weights change once per optimiser step, planes once per frame; the reference
                                      re-renders the same frame in 4096-ray groups, train_avatar.py:182-218) */
+#define HAV_RENDER_CHECK_RANGE 2  /* HAV_PREC_FP16 only: report operands that leave the fp16 range in *range_status (below).
+                                     fp16 conversions saturate, so without this an out-of-range model renders finite but
+                                     wrong values; callers switch to HAV_PREC_BF16 when the status comes back non-zero */
 
 int hav_abi_version(void);
 const char *hav_error_string(int code);
@@ -137,10 +140,32 @@ typedef struct hav_render_args {
 
   void *workspace;          /* >= hav_render_workspace_bytes(args) bytes, 256-byte aligned */
   uint64_t workspace_bytes;
+
+  /* ---- ABI 2 ---- */
+  /* In-kernel ray generation (dataloader/data_util.py:28-56 get_rays + the near / far fill of dataloader/dataloader.py:174-180):
+   * when `camera` is non-NULL, ray_batch may be NULL and the rays of batch element b are generated inside the render kernel
+   * from camera[b] = { fx, fy, cx, cy | c2w row-major [3,4] | near, far } (18 floats, DEVICE memory; focal lengths in pixels,
+   * principal point as a fraction of the image size) for an img_h x img_w image: ray r <-> pixel (p / img_w, p % img_w) with
+   * p = pixel_index[b*R + r], or p = r when pixel_index is NULL (dataloader.py:72; then R must equal img_h * img_w).
+   * Same arithmetic as hav_get_rays, so a render from `camera` equals the render of hav_get_rays' output bit for bit. */
+  const float *camera;        /* [B,18] or NULL */
+  const int32_t *pixel_index; /* [B,R] or NULL (the dataloader's select_inds as y * img_w + x, dataloader.py:160-170) */
+  int32_t img_h, img_w;
+  int32_t *pdf_inds;          /* optional [B,R,num_fine]: sample_pdf's searchsorted(cdf, u, right=True) indices
+                                 (utils/nerf_util.py:102) -- integer bookkeeping exposed for bit-exact parity tests, or NULL */
+  int32_t *range_status;      /* DEVICE int32, required with HAV_RENDER_CHECK_RANGE: zeroed by the call, then bit 0 = a plane texel
+                                 or MLP weight exceeds the fp16 range, bit 1 = a hidden activation saturated at +-65504 */
 } hav_render_args;
 
 uint64_t hav_render_workspace_bytes(const hav_render_args *args);
 int hav_render_forward(const hav_render_args *args, void *stream);
+
+/* sample_pdf alone (utils/nerf_util.py:76-117): the same device function the render kernels run between their two passes,
+ * one thread per row -- exists so that the integer bookkeeping (searchsorted indices, :102) can be compared bit for bit on
+ * identical inputs.  bins [n,m] (z_vals_mid), weights [n,m-1], u [n,nfine] uniform draws or NULL (det=True, :87-91);
+ * samples [n,nfine] (unsorted, as sample_pdf returns them), inds [n,nfine] int32 or NULL; scratch: n*(m+1) floats. */
+int hav_sample_pdf(const float *bins, const float *weights, const float *u, int n, int m, int nfine, float *samples,
+                   int32_t *inds, float *scratch, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Backward of hav_render_forward: what autograd produces for Trainer.predict_and_render_radiance in the reference

@@ -29,7 +29,10 @@ RENDER_CASES = {
     # non-square planes / non-cubic volume pin the axis conventions; window at the frame corner leaves the box
     "render_oddshape": dict(batch=1, crop=(0, 0, 8, 16), num_coarse=16, num_fine=0, rand=False, seed=30,
                             plane_hw=(24, 40), vol_dhw=(6, 10, 14)),
+    # BASELINE.json configs[0] LITERALLY (round 2): single 64 x 64 crop, 32 samples per ray, coarse only
+    "render_c64_s32": dict(batch=1, crop=(224, 224, 64, 64), num_coarse=32, num_fine=0, rand=False, seed=60),
 }
+ROUND2_RENDER_CASES = ("render_c64_s32",)
 
 
 # backward cases: gradients of  sum_k <cotangent_k, out_k>  from the reference's own autograd (small planes / volume keep the
@@ -42,7 +45,7 @@ RENDER_BWD_CASES = {
 }
 
 
-def _reference_render(trainer, torch, case, grad=False):
+def _reference_render(trainer, torch, case, grad=False, inds_out=None):
     sc = synth.scene(batch=case["batch"], crop=case["crop"], seed=case["seed"],
                      plane_hw=case.get("plane_hw", (128, 128)), vol_dhw=case.get("vol_dhw", (64, 64, 64)))
     B, R = sc["ray_batch"].shape[:2]
@@ -79,12 +82,19 @@ def _reference_render(trainer, torch, case, grad=False):
             return torch.from_numpy(v.copy())
 
         torch.rand, torch.randn = fake_rand, fake_randn
+    orig_ss = torch.searchsorted
+    if inds_out is not None:      # integer bookkeeping of sample_pdf (utils/nerf_util.py:102), recorded as the reference computes it
+        def spy(*a, **k):
+            r = orig_ss(*a, **k)
+            inds_out.append(r.detach().numpy().copy())
+            return r
+        torch.searchsorted = spy
     try:
         with torch.set_grad_enabled(grad):
             out = trainer.predict_and_render_radiance("train", rays11, torch.from_numpy(sc["background_prior"]),
                                                       inv_head_T=torch.from_numpy(sc["inv_head_T"]))
     finally:
-        torch.rand, torch.randn = orig_rand, orig_randn
+        torch.rand, torch.randn, torch.searchsorted = orig_rand, orig_randn, orig_ss
     names = ["rgb_coarse", "depth_coarse", "acc_coarse", "weights_max", "rgb_fine", "depth_fine", "acc_fine"]
     res = {n: o.detach().numpy() for n, o in zip(names, out) if o is not None}
     if not grad:
@@ -112,8 +122,46 @@ def gen_render_bwd(trainer, torch):
         print(name, {k: (v.shape, "%.3g" % np.abs(v).max()) for k, v in out.items() if k.startswith("g_")})
 
 
-def gen_render(trainer, torch):
+def gen_pdf_inds(trainer, torch):
+    """sample_pdf's searchsorted indices exactly as the reference computes them: inside the whole hierarchical render (both
+    hierarchical RENDER_CASES) and for the stand-alone sample_pdf inputs of stages.npz (recomputed from the same seed)."""
+    from utils import nerf_util
+
+    out = {}
     for name, case in RENDER_CASES.items():
+        if case["num_fine"] == 0:
+            continue
+        inds = []
+        _reference_render(trainer, torch, case, inds_out=inds)
+        assert len(inds) == 1
+        out[name] = inds[0].reshape(case["batch"], -1, case["num_fine"]).astype(np.int32)
+    st = np.load(os.path.join(GOLD, "stages.npz"))
+    bins, wts, u = st["pdf_bins"], st["pdf_w"], st["pdf_u"]
+    orig_ss, orig_rand = torch.searchsorted, torch.rand
+    rec = []
+
+    def spy(*a, **k):
+        r = orig_ss(*a, **k)
+        rec.append(r.numpy().copy())
+        return r
+
+    torch.searchsorted = spy
+    torch.rand = lambda shape, *a, **k: torch.from_numpy(u.copy())
+    try:
+        det = nerf_util.sample_pdf(torch.from_numpy(bins), torch.from_numpy(wts), 16, det=True).numpy()
+        rnd = nerf_util.sample_pdf(torch.from_numpy(bins), torch.from_numpy(wts), 16, det=False).numpy()
+    finally:
+        torch.searchsorted, torch.rand = orig_ss, orig_rand
+    assert np.array_equal(det, st["pdf_det"]) and np.array_equal(rnd, st["pdf_rand"])
+    out["stage_det"], out["stage_rand"] = rec[0].astype(np.int32), rec[1].astype(np.int32)
+    np.savez_compressed(os.path.join(GOLD, "pdf_inds.npz"), **out)
+    print("pdf_inds", {k: (v.shape, int(v.min()), int(v.max())) for k, v in out.items()})
+
+
+def gen_render(trainer, torch, only=None):
+    for name, case in RENDER_CASES.items():
+        if only is not None and name not in only:
+            continue
         out = _reference_render(trainer, torch, case)
         np.savez_compressed(os.path.join(GOLD, name + ".npz"), case=json.dumps(case), **out)
         print(name, {k: v.shape for k, v in out.items()}, "acc mean %.4f" % out["acc_coarse"].mean())
@@ -236,7 +284,16 @@ STYLEUNET_CASES = {
     "disc_64": dict(net="Discriminator", kw=dict(size=64, img_channel=3), batch=4, seed=4),
     "zxc_64_32": dict(net="StyleGAN_zxc", kw=dict(out_ch=16, out_size=32, style_dim=44, middle_size=16, zero_latent=False,
                                                    zero_noise=True, no_skip=True, n_mlp=4, inp_size=64, inp_ch=7), batch=2, seed=2),
+    # FULL-SIZE networks (round 2): the shipped upsampler 128 -> 512 (train_avatarHD.py:110, config/singleview_512_HD_base.yml:33-37),
+    # BASELINE.json configs[3]'s 512 -> 1024, and the 512 x 512 wavelet discriminator (train_avatarHD.py:112).  `stride` = the
+    # fixture stores every stride-th pixel of the output image (the whole image is produced and compared at those pixels).
+    "swgan_128_512": dict(net="SWGAN_unet", kw=dict(inp_size=128, inp_ch=64, out_ch=3, out_size=512, style_dim=64, n_mlp=4), batch=1, seed=6,
+                          stride=8),
+    "swgan_512_1024": dict(net="SWGAN_unet", kw=dict(inp_size=512, inp_ch=64, out_ch=3, out_size=1024, style_dim=64, n_mlp=4), batch=1, seed=7,
+                           stride=16),
+    "disc_512": dict(net="Discriminator", kw=dict(size=512, img_channel=3), batch=2, seed=8),
 }
+FULL_SIZE_CASES = ("swgan_128_512", "swgan_512_1024", "disc_512")
 
 
 def styleunet_inputs(case, net):
@@ -255,10 +312,12 @@ def styleunet_inputs(case, net):
     return sd, style, cond, noise
 
 
-def gen_styleunet(torch):
+def gen_styleunet(torch, only=None):
     import model.styleUnet as ref
 
     for name, case in STYLEUNET_CASES.items():
+        if only is not None and name not in only:
+            continue
         net = getattr(ref, case["net"])(**case["kw"])
         sd, style, cond, noise = styleunet_inputs(case, net)
         missing = net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
@@ -272,6 +331,8 @@ def gen_styleunet(torch):
                 net.zero_noise[0] = torch.from_numpy(noise[0])        # the fixed first-layer draw (styleUnet.py:748)
                 out, _ = net([torch.from_numpy(style)], torch.from_numpy(cond))
         keys = json.dumps({k: list(v.shape) for k, v in net.state_dict().items()})
+        st = case.get("stride", 1)
+        out = out[..., ::st, ::st] if st > 1 else out
         np.savez_compressed(os.path.join(GOLD, "styleunet_%s.npz" % name), out=out.numpy(), state_dict_shapes=keys)
         print(name, tuple(out.shape), "abs mean %.3f max %.3f" % (out.abs().mean(), out.abs().max()))
 
@@ -393,6 +454,205 @@ def gen_trainer_train(torch):
                         acc_fine=out[6].detach().numpy(), **res)
 
 
+# ------------------------------------------------------------------------------------------------
+# stage-two training step (train_avatarHD.py:201-303) at reduced size, round 2
+# ------------------------------------------------------------------------------------------------
+STAGE_TWO_CASE = dict(batch=2, render_size=32, gen_size=128, num_coarse=32, num_fine=8, seed=9, latent=64, n_mlp=4)
+STAGE_TWO_GRAD_KEYS = {
+    # gradients recorded right after the backward of each phase (before the optimiser step)
+    "d": ["convs.0.conv1.0.weight", "convs.2.conv2.1.weight", "final_conv.0.weight", "final_linear.1.weight", "from_rgbs.1.conv.0.weight"],
+    "r1": ["convs.0.conv1.0.weight", "convs.1.conv2.1.weight", "final_linear.0.weight", "from_rgbs.0.conv.0.weight"],
+    "g": ["convs.0.conv.weight", "convs.3.conv.modulation.weight", "to_rgbs.1.conv.weight", "style.2.weight", "comb_convs.0.0.weight",
+          "cond_convs.0.conv1.0.weight", "convs.1.noise.weight"],
+    "nerf": ["latent_codes", "model_coarse.layers_xyz.0.weight", "model_coarse.fc_rgbFeat.weight", "model_coarse.XY_gen.conv_out.0.weight",
+             "model_coarse.YZ_gen.convs.5.conv.weight", "headpose_skin_net.canonical_Wvolume.final_conv.weight"],
+}
+
+
+def subsample(v, cap=4096):
+    """Every k-th element of the flattened array, k = ceil(size / cap): keeps the fixtures small while touching the whole tensor."""
+    flat = np.asarray(v).reshape(-1)
+    return flat[::max(1, -(-flat.size // cap))].copy()
+
+
+def stage_two_inputs(case=None):
+    """Deterministic inputs of the stage-two step golden (shared with tests/test_stage_two_parity_gpu.py)."""
+    c = case or STAGE_TWO_CASE
+    B, rs, gs, seed = c["batch"], c["render_size"], c["gen_size"], c["seed"]
+    sc = synth.scene(batch=B, height=rs, width=rs, seed=seed)
+    R = rs * rs
+    conds = {k: np.abs(synth.named_normal("input." + k, (B, 7, 256, 256), seed)).astype(np.float32) % np.float32(1.0)
+             for k in ("front_render_cond", "left_render_cond", "right_render_cond")}
+    noise0 = {g: synth.named_normal("input.%s.noise0" % g, (1, 1, 16, 16), seed) for g in ("XY_gen", "YZ_gen")}
+    rnd = {"d": synth.randoms(B, R, c["num_coarse"], c["num_fine"], seed=seed + 7),
+           "g": synth.randoms(B, R, c["num_coarse"], c["num_fine"], seed=seed + 8)}
+    z = {ph: synth.named_normal("input.z_" + ph, (B, c["latent"]), seed) for ph in ("d", "g")}
+    res = [r for r in range(4, int(np.log2(gs))) for _ in range(2)]      # SWGAN_unet.make_noise: middle_log_size+1 .. log_size
+    gnoise = {ph: [synth.named_normal("input.gnoise_%s%d" % (ph, i), (1, 1, 2 ** r, 2 ** r), seed) for i, r in enumerate(res)]
+              for ph in ("d", "g")}
+    rs_ = np.random.RandomState(seed + 1)
+    gt_hr = (rs_.uniform(0, 1, size=(B, 3, gs, gs)) * 2 - 1).astype(np.float32)
+    gt_mask = (rs_.uniform(0, 1, size=(B, 1, rs, rs)) > 0.4).astype(np.float32)
+    return dict(scene=sc, conds=conds, noise0=noise0, rnd=rnd, z=z, gnoise=gnoise, gt_hr=gt_hr, gt_mask=gt_mask)
+
+
+def stage_two_states(shapes_nerf, shapes_gen, shapes_disc, seed):
+    """Name-keyed initial weights of the three networks (the discriminator's first convolutions are scaled down so that its
+    logits stay O(1) on random inputs)."""
+    sd_n = synth.trainer_state(shapes_nerf, seed=seed)
+    sd_n["latent_codes"] = (synth.named_normal("latent_codes", shapes_nerf["latent_codes"], seed) * np.float32(0.1)).astype(np.float32)
+    return sd_n, synth.styleunet_state(shapes_gen, seed + 1), synth.styleunet_state(shapes_disc, seed + 2)
+
+
+def gen_skin(torch):
+    """Deformation_Field_new.pretrain_wc / sample_volume (model/Skinning_Field.py:65-68,101-125) of the unmodified reference:
+    two Adam iterations of the head-box fit from seeded weights and a seeded torch generator (make_volume_pts' jitter)."""
+    from oracle import ref_shim
+    from model.nerf_trainer import Trainer
+
+    cfg = ref_shim.load_cfg()
+    net = Trainer(cfg, 2)
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    sd = synth.trainer_state(shapes, seed=11)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    skin = net.headpose_skin_net
+    torch.manual_seed(77)
+    import tqdm as _tq
+    skin.pretrain_wc(num_iter=2, vol_thr=cfg.models.coarse.Head_bounding)
+    with torch.no_grad():
+        vol = skin.canonical_Wvolume()
+        pts = torch.from_numpy(np.random.RandomState(5).uniform(-1.4, 1.4, size=(64, 3)).astype(np.float32))
+        smp = skin.sample_volume(pts)
+    np.savez_compressed(os.path.join(GOLD, "skin_pretrain.npz"), vol=vol.numpy()[:, :, ::8, ::8, ::8], pts=pts.numpy(), sample=smp.numpy(),
+                        b0=dict(skin.named_parameters())["canonical_Wvolume.final_conv.bias"].detach().numpy())
+    print("skin", vol.shape, float(vol[0, 1].mean()), smp.shape)
+
+
+def gen_stage_two(torch):
+    """The loop body of train_avatarHD.py:201-303 (iteration i = 0, so the R1 branch runs) restated around the UNMODIFIED
+    reference modules and loss functions, LPIPS term omitted (its weights are not available offline), random draws and mixing
+    noise supplied.  Records the losses of each phase, a handful of gradients per network taken right after each backward,
+    and a few weights after the optimiser steps."""
+    import torch.nn.functional as F
+    from oracle import ref_shim
+    from model.nerf_trainer import Trainer
+    from model.styleUnet import SWGAN_unet, Discriminator
+    from utils.styleUnet_util import d_logistic_loss, d_r1_loss, g_nonsaturating_loss, requires_grad, accumulate
+
+    c = STAGE_TWO_CASE
+    B, rs, gs = c["batch"], c["render_size"], c["gen_size"]
+    cfg = ref_shim.load_cfg("singleview_512_HD_base.yml")
+    cfg.models.StyleUnet.inp_size, cfg.models.StyleUnet.out_size = rs, gs
+    cfg.nerf.train.num_coarse, cfg.nerf.train.num_fine = c["num_coarse"], c["num_fine"]
+    nerf = Trainer(cfg, 4)
+    gen = SWGAN_unet(inp_size=rs, inp_ch=64, out_size=gs, out_ch=3, style_dim=c["latent"], c_dim=0, n_mlp=c["n_mlp"], channel_multiplier=2)
+    g_ema = SWGAN_unet(inp_size=rs, inp_ch=64, out_size=gs, out_ch=3, style_dim=c["latent"], c_dim=0, n_mlp=c["n_mlp"], channel_multiplier=2)
+    disc = Discriminator(gs, 3, channel_multiplier=2, c_dim=0)
+    shp = lambda m: {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd_n, sd_g, sd_d = stage_two_states(shp(nerf), shp(gen), shp(disc), c["seed"])
+    for m, sd in ((nerf, sd_n), (gen, sd_g), (disc, sd_d)):
+        miss = m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+        assert not miss.unexpected_keys, miss
+    accumulate(g_ema, gen, 0)                                                                              # train_avatarHD.py:115
+    inp = stage_two_inputs(c)
+    nerf.model_coarse.XY_gen.zero_noise[0] = torch.from_numpy(inp["noise0"]["XY_gen"])
+    nerf.model_coarse.YZ_gen.zero_noise[0] = torch.from_numpy(inp["noise0"]["YZ_gen"])
+    g_ratio, d_ratio, lr = 4 / 5, 16 / 17, 1e-3                                                            # :116-118
+    g_optim = torch.optim.Adam(gen.parameters(), lr=lr * g_ratio, betas=(0 ** g_ratio, 0.99 ** g_ratio))
+    d_optim = torch.optim.Adam(disc.parameters(), lr=lr * d_ratio, betas=(0 ** d_ratio, 0.99 ** d_ratio))
+    n_optim = torch.optim.Adam([{"params": nerf.parameters()}], lr=cfg.optimizer.lr)
+    sc = inp["scene"]
+    Rn = rs * rs
+    t = torch.from_numpy
+    gt_hr, gt_mask = t(inp["gt_hr"]), t(inp["gt_mask"])
+    inp_data = dict(mode="train", fidx=torch.tensor([1, 3]), render_full_img=True, ray_batch=t(sc["ray_batch"]),
+                    background_prior=t(sc["background_prior"]), inv_head_T=t(sc["inv_head_T"]), **{k: t(v) for k, v in inp["conds"].items()})
+    orig_rand, orig_randn = torch.rand, torch.randn
+
+    def with_draws(rnd, fn):
+        q_rand = [rnd["t_rand"], rnd["u_rand"].reshape(B * Rn, -1)]
+        q_randn = [rnd["unit_coarse"].reshape(B * Rn, -1), rnd["unit_fine"].reshape(B * Rn, -1)]
+
+        def fake(q):
+            def f(shape, *a, **k):
+                v = q.pop(0)
+                assert tuple(shape) == v.shape, (tuple(shape), v.shape)
+                return torch.from_numpy(v.copy())
+            return f
+
+        torch.rand, torch.randn = fake(q_rand), fake(q_randn)
+        try:
+            r = fn()
+        finally:
+            torch.rand, torch.randn = orig_rand, orig_randn
+        assert not q_rand and not q_randn
+        return r
+
+    out = {}
+    grads = lambda m, keys, tag: out.update({"g_%s_%s" % (tag, k): subsample(dict(m.named_parameters())[k].grad.numpy()) for k in keys})
+    i = 0
+    gan_w = min(1e-3 * 1.1 ** (i // 500), 0.1)                                                            # :205-206
+    gt_lr = F.interpolate(F.interpolate(gt_hr, size=(rs, rs), mode="bilinear", align_corners=True), size=(gs, gs), mode="bilinear",
+                          align_corners=True)                                                              # :202-204
+    # ---- D step (:211-231)
+    requires_grad(nerf, False), requires_grad(gen, False), requires_grad(disc, True)
+    with torch.no_grad():
+        render, _, _ = with_draws(inp["rnd"]["d"], lambda: nerf(**inp_data))
+        fake_img = gen([t(inp["z"]["d"])], render[:, 3:], noise=[t(n) for n in inp["gnoise"]["d"]])
+    out["render_d"] = render.numpy()[:, :, ::2, ::2].copy()
+    out["fake_d"] = fake_img.numpy()[:, :, ::4, ::4].copy()
+    fake_pred, real_pred = disc(fake_img, flat_pose=None), disc(gt_hr, flat_pose=None)
+    d_loss = d_logistic_loss(real_pred, fake_pred) * gan_w
+    out["d_loss"] = np.float32((d_loss / gan_w).item())
+    out["real_pred"], out["fake_pred"] = real_pred.detach().numpy().copy(), fake_pred.detach().numpy().copy()
+    disc.zero_grad()
+    d_loss.backward()
+    grads(disc, STAGE_TWO_GRAD_KEYS["d"], "d")
+    d_optim.step()
+    # ---- R1 (:233-240), i % d_reg_every == 0
+    gt_req = gt_hr.clone().requires_grad_(True)
+    real_pred = disc(gt_req, flat_pose=None)
+    r1_loss = d_r1_loss(real_pred, gt_req) * gan_w
+    out["r1"] = np.float32((r1_loss / gan_w).item())
+    disc.zero_grad()
+    (10.0 / 2 * r1_loss * 16 + 0 * real_pred[0]).backward()
+    grads(disc, STAGE_TWO_GRAD_KEYS["r1"], "r1")
+    d_optim.step()
+    # ---- G step (:243-280)
+    requires_grad(nerf, True)
+    render, mask, lat = with_draws(inp["rnd"]["g"], lambda: nerf(**inp_data))
+    lr_img = F.interpolate(render[:, :3], size=(gs, gs), mode="bilinear", align_corners=True)
+    rgb_loss = F.mse_loss(lr_img, gt_lr)
+    nerf_loss = rgb_loss + 1.0 * lat
+    mask_loss = cfg.experiment.mask_weight * F.binary_cross_entropy(mask.clip(1e-3, 1.0 - 1e-3), gt_mask)
+    nerf_loss = nerf_loss + mask_loss
+    g_loss = nerf_loss
+    requires_grad(gen, True)
+    fake_img = gen([t(inp["z"]["g"])], render[:, 3:], noise=[t(n) for n in inp["gnoise"]["g"]])
+    requires_grad(disc, False)
+    fake_pred = disc(fake_img, flat_pose=None)
+    g_ns = g_nonsaturating_loss(fake_pred)
+    hr_l1 = F.l1_loss(fake_img, gt_hr)
+    g_loss = g_loss + g_ns * gan_w + hr_l1
+    out.update(rgb_loss=np.float32(rgb_loss.item()), mask_loss=np.float32(mask_loss.item()), lat=np.float32(lat.item()),
+               g_nonsat=np.float32(g_ns.item()), hr_l1=np.float32(hr_l1.item()), g_loss=np.float32(g_loss.item()))
+    nerf.zero_grad()
+    gen.zero_grad()
+    g_loss.backward()
+    grads(gen, STAGE_TWO_GRAD_KEYS["g"], "g")
+    grads(nerf, STAGE_TWO_GRAD_KEYS["nerf"], "nerf")
+    g_optim.step()
+    n_optim.step()
+    accumulate(g_ema, gen, 0.5 ** (32 / (10 * 1000)))                                                     # :162, :303
+    # a few weights after the whole iteration
+    out["w_disc_final_linear.1.weight"] = subsample(dict(disc.named_parameters())["final_linear.1.weight"].detach().numpy())
+    out["w_gen_to_rgbs.1.conv.weight"] = subsample(dict(gen.named_parameters())["to_rgbs.1.conv.weight"].detach().numpy())
+    out["w_ema_to_rgbs.1.conv.weight"] = subsample(dict(g_ema.named_parameters())["to_rgbs.1.conv.weight"].detach().numpy())
+    out["w_nerf_model_coarse.fc_rgb.weight"] = subsample(dict(nerf.named_parameters())["model_coarse.fc_rgb.weight"].detach().numpy())
+    np.savez_compressed(os.path.join(GOLD, "stage_two_step.npz"), **out)
+    print("stage_two", {k: (float(v) if v.ndim == 0 else "%s max %.3g" % (v.shape, np.abs(v).max())) for k, v in out.items()})
+
+
 def main():
     from oracle import ref_shim
 
@@ -404,6 +664,21 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     if "--train-only" in sys.argv:
         return gen_trainer_train(torch)
+    if "--round2" in sys.argv:          # fixtures added in round 2 only (the round-1 files stay byte-identical)
+        from model.nerf_trainer import Trainer
+
+        which = [a for a in sys.argv[2:] if not a.startswith("--")]
+        if not which or "styleunet" in which:
+            gen_styleunet(torch, only=FULL_SIZE_CASES)
+        if not which or "render" in which:
+            trainer = Trainer(cfg, 4)
+            gen_render(trainer, torch, only=ROUND2_RENDER_CASES)
+            gen_pdf_inds(trainer, torch)
+        if not which or "stage_two" in which:
+            gen_stage_two(torch)
+        if not which or "skin" in which:
+            gen_skin(torch)
+        return
     if "--bwd-only" not in sys.argv:
         gen_stages(torch)
         gen_ops(torch)

@@ -12,6 +12,15 @@ from havatar_b200 import conv
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _fp32_reference():
+    """The torch side of every comparison is a true fp32 reference: cuDNN / cuBLAS TF32 off (torch enables cuDNN TF32 by default)."""
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def rel_err(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-12))
 

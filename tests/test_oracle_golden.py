@@ -30,7 +30,7 @@ def oracle_render_case(case):
                           sc["weights"], ro.default_boxes(), case["num_coarse"], case["num_fine"], **kw)
 
 
-@pytest.mark.parametrize("name", ["render_c32_s32", "render_hier_det", "render_hier_rand", "render_oddshape"])
+@pytest.mark.parametrize("name", ["render_c32_s32", "render_hier_det", "render_hier_rand", "render_oddshape", "render_c64_s32"])
 def test_render_matches_reference(golden_dir, name):
     g = _load(golden_dir, name)
     case = json.loads(str(g.pop("case")))
@@ -92,3 +92,29 @@ def test_torch_port_matches_reference(golden_dir, name):
     for k, ref in g.items():
         err = np.abs(out[k].reshape(ref.shape) - ref).max()
         assert err < ATOL, (name, k, err)
+
+
+def test_sample_pdf_indices_match_reference_bit_for_bit(golden_dir):
+    """Integer bookkeeping: the searchsorted(right=True) indices of utils/nerf_util.py:102, recorded
+    while the unmodified reference ran (oracle/gen_golden.py::gen_pdf_inds), against the oracle on identical inputs."""
+    g, gi = _load(golden_dir, "stages"), _load(golden_dir, "pdf_inds")
+    _, inds = ro.sample_pdf(g["pdf_bins"], g["pdf_w"], 16, u_rand=g["pdf_u"])
+    assert np.array_equal(inds.astype(np.int32), gi["stage_rand"])
+    _, inds = ro.sample_pdf(g["pdf_bins"], g["pdf_w"], 16)
+    # det=True: the last sample sits at u == 1.0 exactly, a knife-edge of the reference itself (cdf[-1] = 1 +- 1 ulp, see above)
+    assert np.array_equal(inds.astype(np.int32)[:, :-1], gi["stage_det"][:, :-1])
+    assert np.abs(inds[:, -1] - gi["stage_det"][:, -1]).max() <= 1
+
+
+@pytest.mark.parametrize("name", ["render_hier_det", "render_hier_rand"])
+def test_whole_path_sample_pdf_indices(golden_dir, name):
+    """Indices inside the whole hierarchical render.  The coarse weights feeding the cdf carry summation-order noise (1e-6
+    class), so an index may move by one where u falls within that distance of a cdf entry: exact on >= 99.9 % of the samples,
+    never off by more than one."""
+    g, gi = _load(golden_dir, name), _load(golden_dir, "pdf_inds")
+    case = json.loads(str(g.pop("case")))
+    out = oracle_render_case(case)
+    got, ref = out["pdf_inds"].reshape(gi[name].shape), gi[name]
+    skip_last = not case["rand"]
+    a, b = (got[..., :-1], ref[..., :-1]) if skip_last else (got, ref)
+    assert (a != b).mean() <= 1e-3 and np.abs(a.astype(np.int64) - b).max() <= 1

@@ -17,7 +17,8 @@ TOL_FP32 = dict(rgb=1e-4, depth=2e-4, acc=1e-4, wmax=1e-4)
 # 16-bit tensor-core operands, fp32 accumulate.  SURVEY.md section 8d allows 2e-2 abs; fp16 measures ~1e-4 on these scenes
 # (bench.py reports 83 dB PSNR against the fp32 mode on the full frame), so the gate is 10x tighter than the allowance
 TOL_TC = dict(rgb=2e-3, depth=4e-3, acc=2e-3, wmax=2e-3)
-CASES = ["render_c32_s32", "render_hier_det", "render_hier_rand", "render_oddshape"]
+# render_c64_s32 = BASELINE.json configs[0] literally: one 64 x 64 crop, 32 samples per ray, coarse only
+CASES = ["render_c32_s32", "render_hier_det", "render_hier_rand", "render_oddshape", "render_c64_s32"]
 
 
 def _dev(a):
@@ -169,3 +170,112 @@ def test_bad_arguments_raise():
     with pytest.raises(RuntimeError):
         render.render_rays(torch.zeros(1, 4, 8), None, torch.zeros(1, 4, 3), torch.zeros(2, 1, 64, 8, 8),
                            torch.zeros(1, 2, 4, 4, 4), {}, 8)  # CPU tensors
+
+
+def test_sample_pdf_indices_are_bit_exact(golden_dir):
+    """SURVEY.md section 8 a9 "int indices bit-exact": hav_sample_pdf runs the device function the render kernels use between
+    their two passes on the stage fixture's inputs; its searchsorted indices must equal the ones the unmodified reference
+    computed (tests/golden/pdf_inds.npz, recorded by wrapping torch.searchsorted at utils/nerf_util.py:102) and the oracle's."""
+    g, gi = np.load(os.path.join(golden_dir, "stages.npz")), np.load(os.path.join(golden_dir, "pdf_inds.npz"))
+    bins, w, u = _dev(g["pdf_bins"]), _dev(g["pdf_w"]), _dev(g["pdf_u"])
+    smp, inds = render.sample_pdf(bins, w, 16, u)
+    torch.cuda.synchronize()
+    assert np.array_equal(inds.cpu().numpy(), gi["stage_rand"])
+    assert np.array_equal(inds.cpu().numpy(), ro.sample_pdf(g["pdf_bins"], g["pdf_w"], 16, u_rand=g["pdf_u"])[1].astype(np.int32))
+    assert np.abs(smp.cpu().numpy() - g["pdf_rand"]).max() < 1e-4
+    smp, inds = render.sample_pdf(bins, w, 16, None)
+    torch.cuda.synchronize()
+    # det=True: u[-1] == 1.0 exactly against cdf[-1] == 1 +- 1 ulp is a knife-edge of the reference itself (its CPU and CUDA
+    # cumsum kernels disagree there); every other column is exact
+    assert np.array_equal(inds.cpu().numpy()[:, :-1], gi["stage_det"][:, :-1])
+    assert np.abs(inds.cpu().numpy()[:, -1] - gi["stage_det"][:, -1]).max() <= 1
+    assert np.abs(smp.cpu().numpy() - g["pdf_det"])[:, :-1].max() < 1e-5
+
+
+@pytest.mark.parametrize("name", ["render_hier_det", "render_hier_rand"])
+def test_whole_path_sample_pdf_indices(golden_dir, name):
+    """The same indices exported from inside the fused render (hav_render_args.pdf_inds, fp32 mode) against the reference's.
+    The cdf is built from the coarse weights, which carry 1e-6-class summation-order noise, so an index may move by one where u
+    falls within that distance of a cdf entry: exact on >= 99.9 % of the samples, never off by more than one."""
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    gi = np.load(os.path.join(golden_dir, "pdf_inds.npz"))[name]
+    case = json.loads(str(z["case"]))
+    sc, rnd = case_scene(case)
+    kw = {} if rnd is None else {k: _dev(rnd[k]) for k in ("t_rand", "noise_coarse", "u_rand", "noise_fine")}
+    w = {k: _dev(v) for k, v in sc["weights"].items()}
+    out = render.render_rays(_dev(sc["ray_batch"]), _dev(sc["background_prior"]), _dev(sc["inv_head_T"]), _dev(sc["planes"]),
+                             _dev(sc["wvol"]), w, case["num_coarse"], case["num_fine"], precision="fp32", want_pdf_inds=True, **kw)
+    torch.cuda.synchronize()
+    got = out.pdf_inds.cpu().numpy()
+    assert got.shape == gi.shape and got.dtype == np.int32
+    a, b = (got, gi) if case["rand"] else (got[..., :-1], gi[..., :-1])
+    assert (a != b).mean() <= 1e-3 and np.abs(a.astype(np.int64) - b).max() <= 1
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_in_kernel_ray_generation_equals_uploaded_rays(golden_dir, precision):
+    """rays generated inside the render kernel from an 18-float camera block (hav_render_args.camera)
+    give the render of hav_get_rays' ray tensor bit for bit -- full frame, and a patch of pixels through pixel_index
+    (the dataloader's select_inds, dataloader/dataloader.py:160-170)."""
+    g = np.load(os.path.join(golden_dir, "stages.npz"))
+    H, W = 48, 40
+    sc = synth.scene(batch=2, height=H, width=W, seed=70)
+    intr = np.stack([g["ray_intr"] * np.float32([0.1, 0.1, 1, 1]), g["ray_intr"] * np.float32([0.12, 0.11, 1.02, 0.97])])
+    c2w = np.stack([g["ray_c2w"], g["ray_c2w"]])
+    c2w[1, :, 3] += np.float32([0.1, -0.05, 0.2])
+    near, far = np.float32([2.3, 2.5]), np.float32([4.9, 5.1])
+    rays = torch.stack([render.get_rays(H, W, intr[b], c2w[b], float(near[b]), float(far[b])) for b in range(2)])
+    cam = render.camera_block(intr, c2w, near, far)
+    w = {k: _dev(v) for k, v in sc["weights"].items()}
+    common = (_dev(sc["inv_head_T"]), _dev(sc["planes"]), _dev(sc["wvol"]), w, 16, 4)
+    a = render.render_rays(rays, _dev(sc["background_prior"]), *common, precision=precision)
+    b = render.render_rays(None, _dev(sc["background_prior"]), *common, precision=precision, camera=cam, img_hw=(H, W))
+    torch.cuda.synchronize()
+    for k in ("rgb_coarse", "depth_coarse", "acc_coarse", "weights_max", "rgb_fine", "depth_fine", "acc_fine"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    rs = np.random.RandomState(3)
+    pix = np.stack([np.sort(rs.choice(H * W, size=131, replace=False)) for _ in range(2)]).astype(np.int32)
+    sub = torch.stack([rays[i, torch.from_numpy(pix[i]).long().cuda()] for i in range(2)])
+    bg = _dev(sc["background_prior"][:, :131])
+    a = render.render_rays(sub, bg, *common, precision=precision)
+    b = render.render_rays(None, bg, *common, precision=precision, camera=cam, img_hw=(H, W), pixel_index=_dev(pix))
+    torch.cuda.synchronize()
+    for k in ("rgb_coarse", "acc_coarse", "rgb_fine", "depth_fine"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+
+
+def test_trained_magnitude_inputs_saturate_loudly_in_fp16_and_render_in_bf16():
+    """Range stress (round-1 VERDICT weak #1).  (a) planes and both hidden layers' weights x16 (trained-like magnitudes, hidden
+    activations in the thousands): fp16 must still track the fp32 mode and report a clean range status.  (b) x128: hidden
+    activations pass 65504; fp16 conversions saturate (cvt.rn.satfinite), i.e. the render would be finite but WRONG --
+    render_rays(check_range=True) must raise instead of returning it, and bf16 (fp32 exponent range) must still render."""
+    def scaled(f, head_div=1.0):
+        sc = synth.scene(batch=1, crop=(240, 240, 16, 16), seed=5)
+        sc["planes"] = (sc["planes"] * np.float32(f)).astype(np.float32)
+        for k in ("layers_xyz.0.weight", "layers_xyz.1.weight"):
+            sc["weights"][k] = (sc["weights"][k] * np.float32(f)).astype(np.float32)
+        # keep the outputs O(1)-O(10) so that absolute tolerances mean something: undo (most of) the f^3 gain in the linear heads
+        for k in ("fc_alpha.weight", "fc_rgbFeat.weight"):
+            sc["weights"][k] = (sc["weights"][k] / np.float32(head_div)).astype(np.float32)
+        w = {k: _dev(v) for k, v in sc["weights"].items()}
+        return (_dev(sc["ray_batch"]), _dev(sc["background_prior"]), _dev(sc["inv_head_T"]), _dev(sc["planes"]), _dev(sc["wvol"]), w, 24, 0)
+
+    args = scaled(16.0, 256.0)        # head weights stay fp16-normal (3e-4); hidden activations reach ~1e3
+    ref = render.render_rays(*args, precision="fp32")
+    h = render.render_rays(*args, precision="fp16", check_range=True)          # must not raise
+    torch.cuda.synchronize()
+    assert float((h.rgb_coarse - ref.rgb_coarse).abs().max()) < 5e-3
+    assert float((h.acc_coarse - ref.acc_coarse).abs().max()) < 5e-3
+    args = scaled(128.0, 128.0 ** 3)  # hidden activations ~1e5 > 65504
+    ref = render.render_rays(*args, precision="fp32")
+    with pytest.raises(RuntimeError, match="fp16 operand range"):
+        render.render_rays(*args, precision="fp16", check_range=True)
+    b = render.render_rays(*args, precision="bf16", check_range=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(b.rgb_coarse).all()
+    assert float((b.rgb_coarse - ref.rgb_coarse).abs().max()) < 1e-1           # 8-bit mantissa operands, no clipping
+    # texels beyond 65504 are reported too (bit 0)
+    big = list(scaled(1.0))
+    big[3] = big[3] * 2.0e5
+    with pytest.raises(RuntimeError, match="fp16 operand range"):
+        render.render_rays(*big, precision="fp16", check_range=True)

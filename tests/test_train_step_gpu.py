@@ -18,6 +18,17 @@ def _moved(before, mods):
     return sum(int(not torch.equal(a, b)) for a, b in zip(before, after)), len(after)
 
 
+def _unmoved_names(before, mods):
+    named = [(n, p) for m in mods for n, p in m.named_parameters()]
+    return {n for (n, p), b in zip(named, before) if torch.equal(p, b)}
+
+
+# What the REFERENCE itself leaves without a gradient in a plane generator (listed by running the unmodified Trainer's training
+# step on CPU): the first comb conv is never reached by StyleGAN_zxc.forward's indexing (styleUnet.py:858-866), and with
+# zero_noise=True every noise map except the first is zero, so those NoiseInjection weights get an exactly-zero gradient.
+GEN_UNUSED = {"comb_convs.0.0.weight", "comb_convs.0.1.bias"} | {"convs.%d.noise.weight" % i for i in range(6)}
+
+
 def test_stage_one_step_runs_and_updates_every_subnetwork():
     cfg = train_step.default_cfg(num_coarse=32, num_fine=8)
     step = train_step.StageOneStep(n_frames=4, cfg=cfg, patch=64, seed=0)
@@ -31,8 +42,8 @@ def test_stage_one_step_runs_and_updates_every_subnetwork():
     torch.cuda.synchronize()
     assert all(torch.isfinite(l["loss"]) and torch.isfinite(l["d_loss"]) for l in losses)
     for k, v in groups.items():
-        moved, total = _moved(before[k], v)
-        assert moved >= 0.8 * total, (k, moved, total)      # a few generator tensors are unused by the no_skip configuration
+        unmoved = _unmoved_names(before[k], v)
+        assert unmoved == (GEN_UNUSED if k in ("xy", "yz") else set()), (k, sorted(unmoved))
     assert not torch.equal(lat0, net.latent_codes)
     assert all(torch.isfinite(p).all() for p in net.parameters())
 
@@ -45,11 +56,13 @@ def test_stage_two_step_runs_with_r1():
     ema0 = _snap([step.g_ema])
     outs = [step(batch) for _ in range(2)]
     torch.cuda.synchronize()
-    assert outs[0]["r1"] is None and outs[1]["r1"] is not None and torch.isfinite(outs[1]["r1"])
+    # the R1 gate uses the 0-based iteration index: iteration 0 regularises (train_avatarHD.py:209)
+    assert outs[0]["r1"] is not None and torch.isfinite(outs[0]["r1"]) and outs[1]["r1"] is None
     assert all(torch.isfinite(o["g_loss"]) and torch.isfinite(o["d_loss"]) for o in outs)
     for k, v in mods.items():
-        moved, total = _moved(before[k], v)
-        assert moved >= 0.8 * total, (k, moved, total)      # a few generator tensors are unused by the no_skip configuration
+        unmoved = _unmoved_names(before[k], v)
+        allowed = {"%s.%s" % (g, n) for g in ("XY_gen", "YZ_gen") for n in GEN_UNUSED} if k == "nerf" else set()
+        assert unmoved <= allowed, (k, sorted(unmoved - allowed))
     assert _moved(ema0, [step.g_ema])[0] > 0
 
 
@@ -87,4 +100,4 @@ def test_graphed_stage_two_step_with_eager_r1():
     assert all(torch.isfinite(o["g_loss"]) and torch.isfinite(o["d_loss"]) for o in outs)
     assert any(o["r1"] is not None for o in outs)
     moved, total = _moved(g0, [step.generator])
-    assert moved >= 0.8 * total
+    assert moved >= 0.9 * total
