@@ -89,6 +89,7 @@ SIGNATURES = {
     "hav_conv2d_wgrad": (C.c_int, [C.POINTER(ConvWgradArgs), _fp]),
     "hav_rowscale_dot": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int64, _fp]),
     "hav_adam_flat": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _fp]),
+    "hav_make_render_cond": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, _fp]),
     "hav_get_rays": (C.c_int, [_fp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
                                C.c_float, _fp]),
 }

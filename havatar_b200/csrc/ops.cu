@@ -351,9 +351,44 @@ __global__ void __launch_bounds__(256) get_rays_kernel(float *__restrict__ rays,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// condition renderings: dataloader/dataloader.py:218-229 make_render_cond_ on the device
+// ------------------------------------------------------------------------------------------------
+// render / normal: [n, px, 3] uint8 RGB as decoded from the ortho_*_256_baseGama.png pair; out: [n, 7, px] float32 =
+// render / 255 | normal / 255 | (|normal| > 0) -- channels first, i.e. already permuted the way the entry scripts feed the
+// plane generators (train_avatar.py:121-123 .permute(0, 3, 1, 2)).  One thread per pixel, 6 byte loads, 7 coalesced stores.
+__global__ void __launch_bounds__(256) render_cond_kernel(float *__restrict__ out, const uint8_t *__restrict__ render,
+                                                          const uint8_t *__restrict__ normal, int n, int px) {
+  const long total = (long)n * px;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int img = (int)(i / px), p = (int)(i % px);
+    const uint8_t *r = render + i * 3, *m = normal + i * 3;
+    float *o = out + (size_t)img * 7 * px + p;
+    const uint8_t n0 = m[0], n1 = m[1], n2 = m[2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[(size_t)c * px] = __fdiv_rn((float)r[c], 255.0f);
+    o[(size_t)3 * px] = __fdiv_rn((float)n0, 255.0f);
+    o[(size_t)4 * px] = __fdiv_rn((float)n1, 255.0f);
+    o[(size_t)5 * px] = __fdiv_rn((float)n2, 255.0f);
+    o[(size_t)6 * px] = (n0 | n1 | n2) ? 1.0f : 0.0f;   // np.linalg.norm(normal, axis=-1) > 0
+  }
+}
+
 }  // namespace hav
 
 using namespace hav;
+
+extern "C" int hav_make_render_cond(float *out, const uint8_t *render, const uint8_t *normal, int n, int pixels, void *stream) {
+  if (n < 0 || pixels < 1) return HAV_E_SHAPE;
+  if (n == 0) return HAV_OK;
+  if (out == nullptr || render == nullptr || normal == nullptr) return HAV_E_NULL;
+  const long total = (long)n * pixels;
+  long want = (total + 255) / 256;
+  const int grid = (int)(want < (long)kSMs * 16 ? want : (long)kSMs * 16);
+  render_cond_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, render, normal, n, pixels);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? HAV_OK : (int)e;
+}
 
 extern "C" int hav_fused_bias_act(float *out, const float *x, const float *bias, const float *ref, int64_t numel,
                                   int64_t step_b, int64_t size_b, int act, int grad, float alpha, float scale,

@@ -301,14 +301,15 @@ class _RenderFunction(torch.autograd.Function):
 
 
 def render_rays_autograd(ray_batch, background_prior, inv_head_T, planes, wvol, weights, num_coarse, num_fine=0, boxes=None,
-                         t_rand=None, noise_coarse=None, u_rand=None, noise_fine=None, precision="fp16"):
+                         t_rand=None, noise_coarse=None, u_rand=None, noise_fine=None, precision="fp16", camera=None, img_hw=None,
+                         pixel_index=None):
     """render_rays as a differentiable torch op: gradients flow to `planes`, `wvol` and the MLP tensors in `weights`
     (the learnable inputs of predict_and_render_radiance); rays, poses and random draws are constants.
     Returns RenderOut (z_fine slot None)."""
     if precision == "fp32":
         raise _lib.HavError("the differentiable render runs on the tensor-core path: precision 'fp16' or 'bf16'")
     opts = dict(num_coarse=num_coarse, num_fine=num_fine, boxes=boxes, t_rand=t_rand, noise_coarse=noise_coarse,
-                u_rand=u_rand, noise_fine=noise_fine, precision=precision)
+                u_rand=u_rand, noise_fine=noise_fine, precision=precision, camera=camera, img_hw=img_hw, pixel_index=pixel_index)
     res = _RenderFunction.apply(opts, ray_batch, background_prior, inv_head_T, planes, wvol, *[weights[k] for k in MLP_KEYS])
     res = tuple(res) + (None,) * (7 - len(res))
     return RenderOut(*res, None, None)

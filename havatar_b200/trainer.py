@@ -268,9 +268,16 @@ class Trainer(nn.Module):
         self.model_coarse.set_conditional_embedding(inputs["front_render_cond"], inputs["left_render_cond"],
                                                     inputs["right_render_cond"], inputs["latent_code"],
                                                     inv_head_T.reshape(inv_head_T.shape[0], -1))
-        ray_batch, bg = inputs["ray_batch"], inputs["background_prior"]
-        B, R = ray_batch.shape[:2]
-        dev = ray_batch.device
+        ray_batch, bg = inputs.get("ray_batch"), inputs["background_prior"]
+        cam = {}
+        if ray_batch is None:       # rays generated inside the kernel from the 18-float camera block (havatar_b200/data.py)
+            cam = dict(camera=inputs["camera"], img_hw=inputs["img_hw"], pixel_index=inputs.get("pixel_index"))
+            B = cam["camera"].shape[0]
+            R = cam["pixel_index"].shape[1] if cam["pixel_index"] is not None else int(cam["img_hw"][0]) * int(cam["img_hw"][1])
+            dev = cam["camera"].device
+        else:
+            B, R = ray_batch.shape[:2]
+            dev = ray_batch.device
         nc, nf = int(opt.num_coarse), int(opt.num_fine)
         rnd = {}
         given = inputs.get("randoms")       # tests: the reference's draws as explicit tensors (SURVEY.md section 8a quirk v)
@@ -292,31 +299,32 @@ class Trainer(nn.Module):
                 self.model_coarse.mlp_weights(), nc, nf)
         prec = "fp16" if self.precision == "auto" else self.precision
         if torch.is_grad_enabled():
-            o = hrender.render_rays_autograd(*args, boxes=self._boxes(), precision=prec, **rnd)
+            o = hrender.render_rays_autograd(*args, boxes=self._boxes(), precision=prec, **cam, **rnd)
         elif self.precision == "auto":
             try:
-                o = hrender.render_rays(*args, boxes=self._boxes(), precision="fp16", check_range=True, **rnd)
+                o = hrender.render_rays(*args, boxes=self._boxes(), precision="fp16", check_range=True, **cam, **rnd)
             except hrender._lib.HavError as e:
                 if "fp16 operand range" not in str(e):
                     raise
                 import warnings
                 warnings.warn("havatar_b200: %s -- switching this Trainer to bf16 operands" % e)
                 self.precision = "bf16"
-                o = hrender.render_rays(*args, boxes=self._boxes(), precision="bf16", **rnd)
+                o = hrender.render_rays(*args, boxes=self._boxes(), precision="bf16", **cam, **rnd)
         else:
-            o = hrender.render_rays(*args, boxes=self._boxes(), precision=prec, **rnd)
+            o = hrender.render_rays(*args, boxes=self._boxes(), precision=prec, **cam, **rnd)
         return o.rgb_coarse, o.depth_coarse, o.acc_coarse, o.weights_max, o.rgb_fine, o.depth_fine, o.acc_fine
 
     def forward(self, **data):
         """model/nerf_trainer.py:94-118 (including its quirk ii: slots 1 and 5 of the long tuple are both depth_fine)."""
-        ray_batch = data["ray_batch"]
-        B = ray_batch.shape[0]
+        ray_batch = data.get("ray_batch")
+        B = (ray_batch if ray_batch is not None else data["camera"]).shape[0]
         latent_code = self.latent_codes[data["fidx"]] if data["mode"] == "train" else self.latent_codes[0:1]
         latent_code_loss = torch.square(latent_code - self.latent_codes.mean(dim=0, keepdims=True).detach()).mean()
         rgb_c, _, acc_c, weights, rgb_f, depth_f, acc_f = self.nerf_forward(
             ray_batch=ray_batch, background_prior=data["background_prior"], latent_code=latent_code, inv_head_T=data["inv_head_T"],
             front_render_cond=data["front_render_cond"], left_render_cond=data["left_render_cond"],
-            right_render_cond=data["right_render_cond"], mode=data["mode"], randoms=data.get("randoms"))
+            right_render_cond=data["right_render_cond"], mode=data["mode"], randoms=data.get("randoms"), camera=data.get("camera"),
+            img_hw=data.get("img_hw"), pixel_index=data.get("pixel_index"))
         if data["render_full_img"]:
             render = rgb_f if rgb_f is not None else rgb_c
             mask = acc_f if acc_f is not None else acc_c

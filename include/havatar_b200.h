@@ -16,6 +16,8 @@
  *                            reference has no native boundary here -- it is ~140 ATen launches per chunk)
  *   hav_render_backward  <- loss.backward() through model/nerf_trainer.py:120-201 (train_avatar.py:149; ATen autograd)
  *   hav_get_rays         <- dataloader/data_util.py:28-56 + dataloader/dataloader.py:174-180
+ *   hav_make_render_cond <- dataloader/dataloader.py:218-229 (make_render_cond_)
+ *   hav_sample_pdf       <- utils/nerf_util.py:76-117 (sample_pdf)
  *   hav_conv2d_forward   <- model/styleUnet.py:222-297 (ModulatedConv2d.forward) and :108-118 (EqualConv2d.forward): the
  *                            reference calls cuDNN grouped conv2d / conv_transpose2d through model/op/conv2d_gradfix.py:22-75
  *   hav_pack_planes      <- model/nerf_model.py:85 (plane stacking; layout change for the bf16 path)
@@ -203,6 +205,14 @@ int hav_render_backward(const hav_render_bwd_args *args, void *stream);
  */
 int hav_get_rays(float *ray_batch, int height, int width, const float intr[4], const float c2w[12],
                  float near, float far, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Condition renderings (dataloader/dataloader.py:218-229 make_render_cond_): render / normal are the decoded
+ * ortho_{front,left,right}_{render,normal}_256_baseGama.png pairs as [n, pixels, 3] uint8 RGB in DEVICE memory; out is
+ * [n, 7, pixels] float32 = render / 255 | normal / 255 | (normal != 0) -- channels first, the layout the plane generators take
+ * (train_avatar.py:121-123).  Uploading uint8 and converting here moves 7x fewer bytes than the reference's float32 [H,W,7].
+ */
+int hav_make_render_cond(float *out, const uint8_t *render, const uint8_t *normal, int n, int pixels, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core convolution of the StyleUNet blocks: ModulatedConv2d (model/styleUnet.py:165-297) in the shared-weight

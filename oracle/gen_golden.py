@@ -528,6 +528,84 @@ def gen_skin(torch):
     print("skin", vol.shape, float(vol[0, 1].mean()), smp.shape)
 
 
+def make_fixture_dataset(dst):
+    """A tiny dataset in the reference's on-disk formats (data_preprocessing/fit_video.py:336-339,353-418): split JSON, two
+    frames x two views (one of them view_name '8', which the loader skips), 16 x 16 images / masks, 32 x 32 condition PNGs."""
+    import cv2
+
+    rs = np.random.RandomState(300)
+    os.makedirs(dst, exist_ok=True)
+    frames = []
+    for f, fidx in enumerate((7, 3)):
+        inst = "inst_%d" % fidx
+        os.makedirs(os.path.join(dst, inst), exist_ok=True)
+        for v in ("front", "left", "right"):
+            yy, xx = np.mgrid[0:32, 0:32]
+            normal = np.stack([(xx * 7 + f * 13) % 256, (yy * 5 + 31) % 256, (xx + yy) * 3 % 256], -1).astype(np.uint8)
+            normal[(xx - 16) ** 2 + (yy - 16) ** 2 > 150 + 20 * f] = 0                     # outside the head: |normal| == 0
+            render = rs.randint(0, 256, size=(32, 32, 3)).astype(np.uint8)
+            cv2.imwrite(os.path.join(dst, inst, "ortho_%s_normal_256_baseGama.png" % v), cv2.cvtColor(normal, cv2.COLOR_RGB2BGR))
+            cv2.imwrite(os.path.join(dst, inst, "ortho_%s_render_256_baseGama.png" % v), cv2.cvtColor(render, cv2.COLOR_RGB2BGR))
+        views = []
+        for vi, name in enumerate(("0", "8", "2")):
+            ang = 0.2 * vi + 0.1 * f
+            c, s_ = np.cos(ang), np.sin(ang)
+            pose = np.eye(4)
+            pose[:3, :3] = np.array([[c, 0, s_], [0, -1, 0], [s_, 0, -c]])
+            pose[:3, 3] = [0.1 * vi, -0.05 * f, 4.0 + 0.1 * vi]
+            ori = pose.copy()
+            ori[:3, 3] += [0.01, 0.02, -0.03]
+            img = rs.randint(0, 256, size=(16, 16, 3)).astype(np.uint8)
+            mask = (rs.uniform(size=(16, 16)) > 0.5).astype(np.uint8) * 255
+            ip, mp = "%s/img_%s.png" % (inst, name), "%s/mask_%s.png" % (inst, name)
+            cv2.imwrite(os.path.join(dst, ip), img)
+            cv2.imwrite(os.path.join(dst, mp), np.repeat(mask[..., None], 3, -1))
+            views.append({"view_name": name, "transform_matrix": pose.tolist(), "transform_matrix_ori": ori.tolist(), "file_path": ip,
+                          "mask_path": mp})
+        ht = np.eye(4)
+        a = 0.15 + 0.1 * f
+        ht[:3, :3] = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+        ht[:3, 3] = [0.02, -0.01 * f, 0.03]
+        frames.append({"fidx": fidx, "inst_dir": inst, "head_transformation": ht.tolist(), "mutiview_info_ls": views})
+    meta = {"img_res": 16, "mutiview_intr_ls": [[24.0, 23.0, 0.5, 0.48], [25.0, 25.0, 0.51, 0.5], [22.0, 24.0, 0.49, 0.52]], "frames": frames}
+    with open(os.path.join(dst, "sv_v31_all.json"), "w") as fjs:
+        json.dump(meta, fjs)
+
+
+def gen_dataset(torch):
+    """The unmodified reference MultiView_ImgDataset (dataloader/dataloader.py:38-230, mode 'val') on the fixture dataset:
+    every item's ray tensor, colours, condition tensors and inv_head_T."""
+    from oracle import ref_shim
+
+    dst = os.path.join(GOLD, "dataset")
+    make_fixture_dataset(dst)
+    cfg = ref_shim.load_cfg()
+    cfg.dataset.cond_render_res = 32
+    from dataloader.dataloader import MultiView_ImgDataset
+
+    out = {}
+    cwd = os.getcwd()
+    os.chdir(dst)                       # the reference opens the JSON's paths as they are
+    try:
+        for tag, res in (("r32", 32), ("r24", 24)):          # 24: the cv2.INTER_LINEAR resize branch (dataloader.py:220-225)
+            cfg.dataset.cond_render_res = res
+            ds = MultiView_ImgDataset("sv_v31_all.json", "val", cfg, down_sample=1.0, white_bg=True)
+            out["len"] = np.int32(len(ds))
+            for i in range(len(ds)):
+                idx, d = ds[i]
+                if tag == "r32":
+                    out["item%d_mv_rays" % i] = d["mv_rays"].numpy()
+                    out["item%d_gt" % i] = d["mv_rays_gt_color"].numpy()
+                    out["item%d_inv_head_T" % i] = d["inv_head_T"].numpy()
+                    out["item%d_fidx" % i] = np.int32(ds.frames[i]["fidx"])
+                for v in ("front", "left", "right"):
+                    out["item%d_%s_%s" % (i, v, tag)] = d["%s_render_cond" % v].numpy()
+    finally:
+        os.chdir(cwd)
+    np.savez_compressed(os.path.join(GOLD, "dataset_items.npz"), **out)
+    print("dataset", int(out["len"]), sorted(k for k in out if k.startswith("item0")))
+
+
 def gen_stage_two(torch):
     """The loop body of train_avatarHD.py:201-303 (iteration i = 0, so the R1 branch runs) restated around the UNMODIFIED
     reference modules and loss functions, LPIPS term omitted (its weights are not available offline), random draws and mixing
@@ -678,6 +756,8 @@ def main():
             gen_stage_two(torch)
         if not which or "skin" in which:
             gen_skin(torch)
+        if not which or "dataset" in which:
+            gen_dataset(torch)
         return
     if "--bwd-only" not in sys.argv:
         gen_stages(torch)
