@@ -10,8 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhavatar_b200.so")
 
 HAV_ABI_VERSION = 2
-PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16}
+PREC_FP32, PREC_BF16, PREC_FP16, PREC_FP16X3 = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16, "fp16x3": PREC_FP16X3}
 
 _fp = C.c_void_p  # device pointers travel as integers
 

@@ -1,5 +1,6 @@
 // C-ABI entry points of the fused render (include/havatar_b200.h): argument checks, workspace
 // carving, weight/plane packing and kernel dispatch.  No allocation, no synchronisation.
+#include <stdlib.h>
 #include <string.h>
 
 #include "render_common.cuh"
@@ -17,8 +18,10 @@ struct WsLayout {
 int render_check_args(const hav_render_args *a) {
   if (a == nullptr) return HAV_E_NULL;
   if (a->struct_bytes != sizeof(hav_render_args)) return HAV_E_VALUE;
-  if (a->precision != HAV_PREC_FP32 && a->precision != HAV_PREC_BF16 && a->precision != HAV_PREC_FP16) return HAV_E_VALUE;
-  if ((a->flags & ~(HAV_RENDER_REUSE_PACKED | HAV_RENDER_CHECK_RANGE)) != 0) return HAV_E_VALUE;
+  if (a->precision != HAV_PREC_FP32 && a->precision != HAV_PREC_BF16 && a->precision != HAV_PREC_FP16 &&
+      a->precision != HAV_PREC_FP16X3)
+    return HAV_E_VALUE;
+  if ((a->flags & ~(HAV_RENDER_REUSE_PACKED | HAV_RENDER_CHECK_RANGE | HAV_RENDER_CTA_PAIRS)) != 0) return HAV_E_VALUE;
   if (a->batch < 0 || a->rays < 0) return HAV_E_SHAPE;
   if ((int64_t)a->batch * a->rays > (int64_t)1 << 30) return HAV_E_SHAPE;
   if (a->num_coarse < 2 || a->num_coarse > kMaxSamples) return HAV_E_SHAPE;
@@ -55,9 +58,11 @@ static WsLayout layout(const hav_render_args *a) {
   uint64_t off = 0;
   L.pack_f32 = off, off = align_up(off + (uint64_t)kPackF32Floats * 4, 256);
   if (a->precision != HAV_PREC_FP32) {
-    L.wimg = off, off = align_up(off + tc_weight_image_bytes(), 256);
-    L.planes_cl = off, off = align_up(off + tc_planes_bytes(2 * a->batch, a->plane_h, a->plane_w), 256);
-    L.scratch_blocks = tc_scratch_slots(L.num_blocks);
+    const int x3 = a->precision == HAV_PREC_FP16X3 ? 2 : 1;   // split mode: hi + lo weight images, fp32 channels-last planes
+    L.wimg = off, off = align_up(off + x3 * tc_weight_image_bytes(), 256);
+    L.planes_cl = off, off = align_up(off + x3 * tc_planes_bytes(2 * a->batch, a->plane_h, a->plane_w), 256);
+    const int s2 = tc_scratch_slots(L.num_blocks), s3 = tc3_scratch_slots(L.num_blocks);
+    L.scratch_blocks = s2 > s3 ? s2 : s3;
   } else {
     L.scratch_blocks = L.num_blocks;
   }
@@ -129,6 +134,18 @@ extern "C" int hav_render_forward(const hav_render_args *a, void *stream) {
     P.wimg = ws + L.wimg;
     P.planes_cl = (const uint16_t *)(ws + L.planes_cl);
     const bool bf16 = a->precision == HAV_PREC_BF16;
+    if (a->precision == HAV_PREC_FP16X3) {
+      if (!reuse) {
+        hav_render_args h = *a;
+        h.precision = HAV_PREC_FP16;
+        launch_pack_mlp_16(&h, ws + L.wimg, st, nullptr);
+        launch_pack_mlp_16_lo(&h, ws + L.wimg + tc_weight_image_bytes(), st);
+        e = launch_pack_planes_f32(a->planes, (float *)(ws + L.planes_cl), 2 * a->batch, a->plane_h, a->plane_w, st);
+        if (e != cudaSuccess) return (int)e;
+      }
+      e = launch_render_16_v3(P, L.num_blocks, 2, st);
+      return e == cudaSuccess ? HAV_OK : (int)e;
+    }
     if ((a->flags & HAV_RENDER_CHECK_RANGE) != 0) {
       e = cudaMemsetAsync(a->range_status, 0, sizeof(int32_t), st);
       if (e != cudaSuccess) return (int)e;
@@ -138,7 +155,8 @@ extern "C" int hav_render_forward(const hav_render_args *a, void *stream) {
       e = launch_pack_planes_16(a->planes, (uint16_t *)(ws + L.planes_cl), 2 * a->batch, a->plane_h, a->plane_w, bf16, st, P.status);
       if (e != cudaSuccess) return (int)e;
     }
-    e = launch_render_16(P, L.num_blocks, bf16, st);
+    const bool v3 = (a->flags & HAV_RENDER_CTA_PAIRS) != 0 || getenv("HAV_TC3") != nullptr;   // CTA-pair kernel (render_tc3.cu)
+    e = v3 ? launch_render_16_v3(P, L.num_blocks, bf16 ? 1 : 0, st) : launch_render_16(P, L.num_blocks, bf16, st);
   }
   return e == cudaSuccess ? HAV_OK : (int)e;
 }

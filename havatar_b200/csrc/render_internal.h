@@ -36,5 +36,10 @@ cudaError_t launch_pack_planes_16(const float *planes, uint16_t *out, int nimg, 
                                   int32_t *status = nullptr);
 cudaError_t launch_render_16(const RenderDev &P, int num_ray_blocks, bool bf16, cudaStream_t st);
 cudaError_t launch_render_16_v2(const RenderDev &P, int num_ray_blocks, bool bf16, cudaStream_t st);  // render_tc2.cu
+// render_tc3.cu: CTA pairs (cta_group::2); mode 0 fp16, 1 bf16, 2 fp16 hi + lo split
+cudaError_t launch_render_16_v3(const RenderDev &P, int num_ray_blocks, int mode, cudaStream_t st);
+int tc3_scratch_slots(int num_ray_blocks);
+void launch_pack_mlp_16_lo(const hav_render_args *a, uint8_t *wimg_lo, cudaStream_t st);   // fp16(w - fp16(w)) image
+cudaError_t launch_pack_planes_f32(const float *planes, float *out, int nimg, int H, int W, cudaStream_t st);
 
 }  // namespace hav

@@ -37,7 +37,7 @@ __device__ __forceinline__ void range_note(float v, int32_t *status) {
 // Weight image = the exact bytes of the shared-memory weight region: three K-major matrices in [K/8][rows][8]
 // order.  Internal K order of L0: 0..63 plane-0 channels, 64..127 plane-1 channels (the reference interleaves
 // them as 2c+plane, model/nerf_model.py:99), 128..175 PE, 176 bias.
-template <bool kBF16>
+template <bool kBF16, bool kLo = false>
 __global__ void pack_mlp_16_kernel(const float *__restrict__ w0, const float *__restrict__ b0,
                                    const float *__restrict__ w1, const float *__restrict__ b1,
                                    const float *__restrict__ wa, const float *__restrict__ ba,
@@ -76,6 +76,7 @@ __global__ void pack_mlp_16_kernel(const float *__restrict__ w0, const float *__
       }
     }
     range_note<kBF16>(v, status);
+    if (kLo) v = v - __half2float(__float2half_rn(v));   // split precision: the residual of the fp16 rounding (fp16 mode only)
     img[i] = to16<kBF16>(v);
   }
 }
@@ -381,6 +382,41 @@ void launch_pack_mlp_16(const hav_render_args *a, uint8_t *wimg, cudaStream_t st
   else
     tc::pack_mlp_16_kernel<false><<<54, 256, 0, st>>>(a->w0, a->b0, a->w1, a->b1, a->w_alpha, a->b_alpha, a->w_feat, a->b_feat,
                                                        a->w_rgb, a->b_rgb, (uint16_t *)wimg, status);
+}
+
+void launch_pack_mlp_16_lo(const hav_render_args *a, uint8_t *wimg_lo, cudaStream_t st) {
+  tc::pack_mlp_16_kernel<false, true><<<54, 256, 0, st>>>(a->w0, a->b0, a->w1, a->b1, a->w_alpha, a->b_alpha, a->w_feat, a->b_feat,
+                                                           a->w_rgb, a->b_rgb, (uint16_t *)wimg_lo, nullptr);
+}
+
+namespace tc {
+// planes [2,B,64,H,W] fp32 -> [2B][H+3][W+3][64] fp32 channels-last with the same zero border as the 16-bit layout (split mode)
+__global__ void __launch_bounds__(256) pack_planes_f32_kernel(const float *__restrict__ planes, float *__restrict__ out, int H, int W) {
+  extern __shared__ float tile[];   // [64][W+1]
+  const int img = blockIdx.y, y = blockIdx.x;
+  const int Hp = H + kPadLo + kPadHi, Wp = W + kPadLo + kPadHi;
+  const float *src = planes + (size_t)img * kPlaneC * H * W + (size_t)y * W;
+  for (int i = threadIdx.x; i < kPlaneC * W; i += blockDim.x) {
+    int c = i / W, x = i % W;
+    tile[c * (W + 1) + x] = __ldg(src + (size_t)c * H * W + x);
+  }
+  __syncthreads();
+  float *dst = out + (((size_t)img * Hp + (y + kPadLo)) * Wp + kPadLo) * kPlaneC;
+  for (int i = threadIdx.x; i < kPlaneC * W; i += blockDim.x) {
+    int x = i / kPlaneC, c = i % kPlaneC;
+    dst[(size_t)x * kPlaneC + c] = tile[c * (W + 1) + x];
+  }
+}
+}  // namespace tc
+
+cudaError_t launch_pack_planes_f32(const float *planes, float *out, int nimg, int H, int W, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(out, 0, 2 * tc_planes_bytes(nimg, H, W), st);
+  if (e != cudaSuccess) return e;
+  const size_t smem = (size_t)kPlaneC * (W + 1) * sizeof(float);
+  e = cudaFuncSetAttribute(tc::pack_planes_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  tc::pack_planes_f32_kernel<<<dim3(H, nimg), 256, smem, st>>>(planes, out, H, W);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_pack_planes_16(const float *planes, uint16_t *out, int nimg, int H, int W, bool bf16, cudaStream_t st,

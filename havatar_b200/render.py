@@ -83,14 +83,15 @@ def release_workspaces(stream=None):
 def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, num_coarse, num_fine=0,
                 boxes=None, t_rand=None, noise_coarse=None, u_rand=None, noise_fine=None, precision="fp16",
                 want_z_fine=False, reuse_packed=False, out=None, return_ctx=False, camera=None, img_hw=None, pixel_index=None,
-                want_pdf_inds=False, check_range=False):
+                want_pdf_inds=False, check_range=False, cta_pairs=False):
     """ray_batch [B,R,8] (o3 d3 near far; extra trailing columns such as the reference's viewdirs are
     ignored) -- or ray_batch=None with camera [B,18] (fx fy cx cy | c2w [3,4] row-major | near far, see `camera_block`),
     img_hw=(H, W) and optionally pixel_index [B,R] int32 (y * W + x; default: all H*W pixels in row-major order): the rays are
     then generated inside the kernel (dataloader/data_util.py:28-56) and no per-ray tensor is uploaded.
     check_range=True (precision 'fp16'): raise HavError when a plane texel / MLP weight does not fit fp16 or a hidden activation
     saturates at 65504 (HAV_RENDER_CHECK_RANGE; costs one 4-byte device->host read) instead of returning clipped values --
-    models with such magnitudes need precision='bf16'.  background_prior [B,R,3] or None, inv_head_T [B,4,3], planes [2,B,64,H,W], wvol [1,2,D,H,W],
+    models with such magnitudes need precision='bf16'.  precision 'fp16x3' = split-precision tensor-core mode (fp32-class
+    results, HAV_PREC_FP16X3); cta_pairs=True runs the 16-bit modes on the CTA-pair kernel (HAV_RENDER_CTA_PAIRS).  background_prior [B,R,3] or None, inv_head_T [B,4,3], planes [2,B,64,H,W], wvol [1,2,D,H,W],
     weights: mapping with the reference's model_coarse keys (MLP_KEYS).  Random draws are explicit inputs
     (SURVEY.md section 8a quirk v): t_rand [B,R,Sc], noise_* [B,R,S] already scaled by the noise std,
     u_rand [B,R,num_fine]; None switches that randomness off (u_rand None == sample_pdf det=True).
@@ -131,7 +132,7 @@ def render_rays(ray_batch, background_prior, inv_head_T, planes, wvol, weights, 
     a.struct_bytes = C.sizeof(_lib.RenderArgs)
     a.precision = _lib.PRECISIONS[precision]
     check_range = bool(check_range) and precision == "fp16"
-    a.flags = (1 if reuse_packed else 0) | (2 if check_range else 0)
+    a.flags = (1 if reuse_packed else 0) | (2 if check_range else 0) | (4 if cta_pairs and precision in ('fp16', 'bf16') else 0)
     a.batch, a.rays, a.num_coarse, a.num_fine = B, R, int(num_coarse), int(num_fine)
     a.plane_c, a.plane_h, a.plane_w = int(planes.shape[2]), int(planes.shape[3]), int(planes.shape[4])
     a.vol_d, a.vol_h, a.vol_w = int(wvol.shape[2]), int(wvol.shape[3]), int(wvol.shape[4])

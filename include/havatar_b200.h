@@ -49,6 +49,9 @@ extern "C" {
 #define HAV_PREC_FP32 0 /* CUDA-core fp32 everywhere: reference-exact mode (1e-5 class parity) */
 #define HAV_PREC_BF16 1 /* tcgen05 bf16 operands, fp32 accumulate in TMEM (fast path, fp32 exponent range) */
 #define HAV_PREC_FP16 2 /* tcgen05 fp16 operands (saturating converts), fp32 accumulate: fast path, 8x finer rounding */
+#define HAV_PREC_FP16X3 3 /* tcgen05 split precision: activations and weights as fp16 hi + lo pairs, three MMAs per product
+                             (hi*hi + lo*hi + hi*lo, fp32 accumulate), fp32 planes / blends / positional encoding / composite:
+                             fp32-class results (1e-5 class parity) at tensor-core speed.  Operand range is fp16's. */
 
 /* hav_render_args.flags */
 #define HAV_RENDER_REUSE_PACKED 1 /* the workspace still holds the packed MLP weights and planes written by a previous
@@ -58,6 +61,9 @@ extern "C" {
 #define HAV_RENDER_CHECK_RANGE 2  /* HAV_PREC_FP16 only: report operands that leave the fp16 range in *range_status (below).
                                      fp16 conversions saturate, so without this an out-of-range model renders finite but
                                      wrong values; callers switch to HAV_PREC_BF16 when the status comes back non-zero */
+
+#define HAV_RENDER_CTA_PAIRS 4    /* 16-bit modes: run the CTA-pair kernel (tcgen05 cta_group::2, render_tc3.cu) instead of the
+                                     single-CTA kernel (render_tc2.cu); HAV_PREC_FP16X3 always runs on CTA pairs */
 
 int hav_abi_version(void);
 const char *hav_error_string(int code);

@@ -86,7 +86,7 @@ def test_stage_two_iteration_matches_the_reference(golden_dir):
         l2 = float(np.linalg.norm(v - ref) / (np.linalg.norm(ref) + 1e-30))
         cos = float((v * ref).sum() / (np.linalg.norm(v) * np.linalg.norm(ref) + 1e-30))
         table.append("%-64s relL2 %.4f  cos %.5f  max-rel %.4f" % (k, l2, cos, _rel(v, g[k])))
-        lim_l2, lim_cos = (0.5, 0.88) if k.startswith("g_r1_") else (0.25, 0.97)
+        lim_l2, lim_cos = (0.25, 0.99) if k.startswith("g_r1_") else (0.12, 0.995)      # measured: 0.12 / 0.997 and 0.08 / 0.9994
         if l2 > lim_l2 or cos < lim_cos:
             bad[k] = (l2, cos)
     print("\n".join(table))
