@@ -3,6 +3,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/havatar_b200.h"
 #include "render_common.cuh"
@@ -259,6 +260,189 @@ __global__ void __launch_bounds__(256) upfirdn2d_fast_kernel(float *__restrict__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Streaming 4x4 FIR (up == down == 1, minor == 1: the Blur after every transposed / before every stride-2 convolution,
+// model/styleUnet.py:69-87).  No shared memory and no tile-wide synchronisation: a thread owns 4 adjacent output columns and
+// marches down kBlurRows output rows, keeping the last three rows of horizontal sums in registers.  Each input row is read
+// with three 16-byte loads from 16-byte aligned addresses (the row pitch is 2^k + 1 floats here, so the alignment of a row
+// shifts by one element per row: the shift is uniform across the warp and selects one of four statically indexed code paths).
+// The 4x4 tap matrix is factorised in the kernel: rank one ([1,3,3,1] x [1,3,3,1], every tap set the StyleUNet uses) takes
+// the separable path (4 + 4 FMAs per output instead of 16); anything else the general path.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBlurRows = 32;
+
+template <int S, bool kSep>
+__device__ __forceinline__ void blur_row(const float (&c)[12], const float (&kx)[4], const float (&k2)[16], float (&h)[4],
+                                         float (&part)[4][4]) {
+  if (kSep) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) h[o] = fmaf(c[S + o + 3], kx[3], fmaf(c[S + o + 2], kx[2], fmaf(c[S + o + 1], kx[1], c[S + o] * kx[0])));
+  } else {
+    // general taps: this input row is tap row i of the output row that is i rows above it; part[i] collects that output row
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) part[i][o] = fmaf(c[S + o + j], k2[i * 4 + j], part[i][o]);
+  }
+}
+
+// kFast: every 16-byte chunk the strip touches lies inside the tensor's allocation (no pointer guards; rows above / below the
+// image are a CTA-uniform branch, and only the first / last thread of a row masks its out-of-row columns).  False only at the
+// two ends of the whole tensor.  Rows are processed four at a time so that the window rotates by renaming.
+template <bool kSep, bool kFast>
+__device__ __forceinline__ void blur_march(float *__restrict__ oimg, const float *__restrict__ ximg, const float *__restrict__ xlo,
+                                           const float *__restrict__ xhi, const UfdParams &p, int ox, int oy0, int rows,
+                                           const float (&kx)[4], const float (&ky)[4], const float (&k2)[16]) {
+  // sliding state: separable -> the horizontal sums of the last three input rows; general -> partially summed output rows
+  float H[4][4], part[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int o = 0; o < 4; ++o) H[i][o] = 0.0f, part[i][o] = 0.0f;
+  const int ix0 = ox - p.pad_x0;                       // input column of tap 0 of output ox
+  const bool edge = ix0 < 0 || ix0 + 7 > p.in_w;       // some of the 7 columns this thread reads lie outside the row
+  const bool pair_ok = (p.out_w & 1) == 0 && ox + 3 < p.out_w;   // 8-byte aligned output pairs on every row
+  const float *rowp_base = ximg + (long)(oy0 - p.pad_y0) * p.in_w + ix0;   // first element this thread needs on input row r = 0
+  const int total = rows + 3;
+  float *op = oimg + (size_t)oy0 * p.out_w + ox - (size_t)3 * p.out_w;   // output row r - 3
+
+  // the three 16-byte chunks of input row r (zeros when the row is above / below the image), loaded one row AHEAD of their use
+  auto load_row = [&](int r, float4 (&dst)[3], int &sh_out) {
+    const float *rp = rowp_base + (long)r * p.in_w;
+    const int sh = (int)(((uintptr_t)rp >> 2) & 3);
+    sh_out = sh;
+    const float4 *a0 = reinterpret_cast<const float4 *>(rp - sh);
+    const int iy = oy0 + r - p.pad_y0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < p.in_h) {          // uniform across the CTA: rows above / below the image are zero padding
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        if (kFast) {
+          dst[q] = __ldg(a0 + q);
+        } else {
+          const float *ap = reinterpret_cast<const float *>(a0 + q);
+          if (ap >= xlo && ap + 4 <= xhi) dst[q] = __ldg(a0 + q);             // inside the tensor's allocation (16-byte aligned)
+          else {
+            if (ap + 0 >= xlo && ap + 0 < xhi) dst[q].x = __ldg(ap + 0);
+            if (ap + 1 >= xlo && ap + 1 < xhi) dst[q].y = __ldg(ap + 1);
+            if (ap + 2 >= xlo && ap + 2 < xhi) dst[q].z = __ldg(ap + 2);
+            if (ap + 3 >= xlo && ap + 3 < xhi) dst[q].w = __ldg(ap + 3);
+          }
+        }
+      }
+    }
+  };
+  float4 nxt[3];
+  int sh_nxt;
+  load_row(0, nxt, sh_nxt);
+  auto one_row = [&](int r, float (&Hm3)[4], float (&Hm2)[4], float (&Hm1)[4], float (&Hnew)[4]) {
+    float c[12];
+    const int sh = sh_nxt;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) c[4 * q] = nxt[q].x, c[4 * q + 1] = nxt[q].y, c[4 * q + 2] = nxt[q].z, c[4 * q + 3] = nxt[q].w;
+    if (r + 1 < total) load_row(r + 1, nxt, sh_nxt);      // in flight while this row is filtered
+    if (edge) {   // first / last thread of a row only: zero padding left / right of the row (a short divergent block)
+#pragma unroll
+      for (int e = 0; e < 12; ++e) {
+        const int ix = ix0 - sh + e;
+        if (ix < 0 || ix >= p.in_w) c[e] = 0.0f;
+      }
+    }
+    switch (sh) {        // warp-uniform (every lane's first element is 4 lanes * 16 bytes further along the same row)
+      case 0: blur_row<0, kSep>(c, kx, k2, Hnew, part); break;
+      case 1: blur_row<1, kSep>(c, kx, k2, Hnew, part); break;
+      case 2: blur_row<2, kSep>(c, kx, k2, Hnew, part); break;
+      default: blur_row<3, kSep>(c, kx, k2, Hnew, part); break;
+    }
+    float o4[4];
+    if (kSep) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) o4[o] = fmaf(Hnew[o], ky[3], fmaf(Hm1[o], ky[2], fmaf(Hm2[o], ky[1], Hm3[o] * ky[0])));
+    } else {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        o4[o] = part[3][o];                                   // the output row whose LAST tap row this input row is
+        part[3][o] = part[2][o], part[2][o] = part[1][o], part[1][o] = part[0][o], part[0][o] = 0.0f;
+      }
+    }
+    if (r >= 3) {
+      if (pair_ok) {
+        *reinterpret_cast<float2 *>(op) = make_float2(o4[0], o4[1]);
+        *reinterpret_cast<float2 *>(op + 2) = make_float2(o4[2], o4[3]);
+      } else {
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+          if (ox + o < p.out_w) op[o] = o4[o];
+      }
+    }
+    op += p.out_w;
+  };
+  for (int r = 0; r < total; r += 4) {      // the window rotates through H[0..3] by renaming
+    one_row(r, H[1], H[2], H[3], H[0]);
+    if (r + 1 < total) one_row(r + 1, H[2], H[3], H[0], H[1]);
+    if (r + 2 < total) one_row(r + 2, H[3], H[0], H[1], H[2]);
+    if (r + 3 < total) one_row(r + 3, H[0], H[1], H[2], H[3]);
+  }
+}
+
+__global__ void __launch_bounds__(128, 6) blur4x4_stream_kernel(float *__restrict__ out, const float *__restrict__ x,
+                                                             const float *__restrict__ kernel, UfdParams p, int bands_x, long n_img) {
+  // flipped taps (upfirdn2d correlates with the flipped kernel) and their rank-one factorisation k2[i][j] = ky[i] * kx[j]
+  float k2[16], kx[4], ky[4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) k2[i] = __ldg(kernel + 15 - i);
+  int best = 0;
+#pragma unroll
+  for (int i = 1; i < 16; ++i)
+    if (fabsf(k2[i]) > fabsf(k2[best])) best = i;
+  const int r0 = best >> 2, c0 = best & 3;
+  const float piv = k2[best];
+  bool sep = piv != 0.0f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) kx[j] = k2[r0 * 4 + j];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ky[i] = sep ? k2[i * 4 + c0] / piv : 0.0f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sep = sep && fabsf(k2[i] - ky[i >> 2] * kx[i & 3]) <= 1e-6f * fabsf(piv);
+  const int band = blockIdx.x % bands_x, strip = blockIdx.x / bands_x;
+  const int ox = (band * blockDim.x + threadIdx.x) * 4, oy0 = strip * kBlurRows;
+  if (ox >= p.out_w) return;
+  const float *xhi = x + (size_t)n_img * p.in_h * p.in_w;
+  for (long img = blockIdx.y; img < n_img; img += gridDim.y) {
+    float *oimg = out + (size_t)img * p.out_h * p.out_w;
+    const float *ximg = x + (size_t)img * p.in_h * p.in_w;
+    const int rows = min(kBlurRows, p.out_h - oy0);
+    // fast path: all rows of the strip exist, the thread's 7 columns lie inside the row, and the aligned 16-byte chunks around
+    // them stay inside the allocation (they may spill into the neighbouring rows of the same tensor, which is harmless)
+    const int iy_first = oy0 - p.pad_y0, ix0 = ox - p.pad_x0;
+    const int iy_lo = max(iy_first, 0), iy_hi = min(iy_first + rows + 2, p.in_h - 1);       // rows that are actually read
+    const float *first = ximg + (long)iy_lo * p.in_w + ix0, *last = ximg + (long)iy_hi * p.in_w + ix0;
+    const bool fast = first - 3 >= x && last + 12 <= xhi;
+    if (sep) {
+      if (fast) blur_march<true, true>(oimg, ximg, x, xhi, p, ox, oy0, rows, kx, ky, k2);
+      else blur_march<true, false>(oimg, ximg, x, xhi, p, ox, oy0, rows, kx, ky, k2);
+    } else {
+      blur_march<false, false>(oimg, ximg, x, xhi, p, ox, oy0, rows, kx, ky, k2);
+    }
+  }
+}
+
+static cudaError_t launch_blur4x4_stream(float *out, const float *x, const float *kernel, const UfdParams &p, int64_t imgs,
+                                         cudaStream_t st) {
+  // a thread owns 4 output columns: as many warps per CTA as a row needs (at most 4), so that narrow images do not park idle
+  // warps on the SM
+  const int warps = (p.out_w + 127) / 128;
+  const int threads = 32 * (warps < 4 ? warps : 4);
+  const int bands_x = (p.out_w + threads * 4 - 1) / (threads * 4), strips = (p.out_h + kBlurRows - 1) / kBlurRows;
+  const int gy = (int)(imgs < 65535 ? imgs : 65535);
+  blur4x4_stream_kernel<<<dim3(bands_x * strips, gy), threads, 0, st>>>(out, x, kernel, p, bands_x, (long)imgs);
+  return cudaGetLastError();
+}
+
 template <int UP, int DOWN, int KH, int KW>
 static cudaError_t launch_ufd_fast(float *out, const float *x, const float *kernel, const UfdParams &p, int64_t imgs, cudaStream_t st) {
   const int tiles_x = (p.out_w + kTileW - 1) / kTileW, tiles_y = (p.out_h + kTileH - 1) / kTileH;
@@ -439,7 +623,10 @@ extern "C" int hav_upfirdn2d(float *out, const float *x, const float *kernel, in
     // the StyleUNet's own shapes (model/styleUnet.py:29-87, 371-422) take the specialised kernels
     cudaError_t fe = cudaErrorInvalidValue;
     const int64_t n_img = (int64_t)major;
-    if (up_x == 1 && down_x == 1 && kh == 4) fe = launch_ufd_fast<1, 1, 4, 4>(out, x, kernel, p, n_img, (cudaStream_t)stream);
+    static const bool old_blur = getenv("HAV_BLUR_TILED") != nullptr;   // A/B aid: the shared-memory tile kernel of round 1
+    if (up_x == 1 && down_x == 1 && kh == 4 && !old_blur && ((uintptr_t)x & 15) == 0)
+      fe = launch_blur4x4_stream(out, x, kernel, p, n_img, (cudaStream_t)stream);
+    else if (up_x == 1 && down_x == 1 && kh == 4) fe = launch_ufd_fast<1, 1, 4, 4>(out, x, kernel, p, n_img, (cudaStream_t)stream);
     else if (up_x == 1 && down_x == 2 && kh == 4) fe = launch_ufd_fast<1, 2, 4, 4>(out, x, kernel, p, n_img, (cudaStream_t)stream);
     else if (up_x == 2 && down_x == 1 && kh == 4) fe = launch_ufd_fast<2, 1, 4, 4>(out, x, kernel, p, n_img, (cudaStream_t)stream);
     else if (up_x == 1 && down_x == 2 && kh == 2) fe = launch_ufd_fast<1, 2, 2, 2>(out, x, kernel, p, n_img, (cudaStream_t)stream);

@@ -8,8 +8,9 @@
 //     each CTA contributes its own 128-row A tile (X in its shared memory, or the hidden activations in its TMEM) and HALF of
 //     the weight rows (B operand: N/2 rows per CTA), so the B-operand shared-memory reads per row tile and the per-CTA weight
 //     footprint are halved (109 KB -> 55.5 KB);
-//   * cross-CTA hand-shakes are mbarriers in the leader's shared memory with 256 arrivals (128 threads of each CTA, remote
-//     arrive through mapa / shared::cluster), completions come back through tcgen05.commit ... multicast::cluster.
+//   * cross-CTA hand-shakes: each CTA synchronises its own 128 threads locally (named barrier / local mbarrier), then ONE
+//     thread of the non-leader CTA relays the event to an mbarrier in the leader's shared memory (mapa / shared::cluster remote
+//     arrive: one message per event instead of 128); completions come back through tcgen05.commit ... multicast::cluster.
 //
 // The halved weight footprint is what makes the split-precision mode fit (HAV_PREC_FP16X3): A = A_hi + A_lo and
 // W = W_hi + W_lo as fp16 pairs, D = A_hi W_hi + A_lo W_hi + A_hi W_lo accumulated in fp32 TMEM (the dropped A_lo W_lo term
@@ -38,7 +39,7 @@ constexpr int kConstBytes = 2 * kChunkA;
 constexpr int kStageRow = 48;
 constexpr int kStageBytes3 = 128 * kStageRow;
 // barrier slots per pair (8 bytes each)
-constexpr int kBarXFull = 0, kBarXFree = 1, kBarMma = 2, kBarZFine = 3, kBarReady = 4, kBarsPerPair = 5;
+constexpr int kBarXFull = 0, kBarXFree = 1, kBarMma = 2, kBarZFine = 3, kBarReady = 4, kBarPeerFull = 5, kBarsPerPair = 6;
 constexpr int kHCols = 136;                               // split mode: hidden activations hi [0,72) | lo [72,136) (TMEM columns)
 
 enum { kModeF16 = 0, kModeBF16 = 1, kModeSplit = 2 };
@@ -182,7 +183,7 @@ __device__ __forceinline__ void producer_loop(const RenderDev &P, int num_ray_bl
   uint8_t *X = smem + C::smX + pair * C::sets * kXBytes;          // split: X_hi, then X_lo at + kXBytes
   uint8_t *stage_base = smem + C::smStage + pair * 2 * kStageBytes3;
   const uint32_t bars = smem_base + C::smBar + pair * kBarsPerPair * 8;
-  const uint32_t bar_full_leader = map_to_cta(bars + kBarXFull * 8, 0);
+  const uint32_t bar_full = bars + kBarXFull * 8;
   const uint32_t bar_free = bars + kBarXFree * 8, bar_zfine = bars + kBarZFine * 8;
   const int Wp = P.PW + kPadLo + kPadHi;
   uint32_t n = 0, zfine_phase = 0;
@@ -363,7 +364,7 @@ __device__ __forceinline__ void producer_loop(const RenderDev &P, int num_ray_bl
           }
         }
         fence_async_all();                  // X (this CTA's shared memory) is read by the async proxy of an MMA the LEADER issues
-        mbar_arrive_cluster(bar_full_leader);
+        mbar_arrive_local(bar_full);        // the non-leader's consumer warp 0 relays the completed barrier to the leader
       }
     }
   }
@@ -402,7 +403,9 @@ __device__ __forceinline__ void consumer_loop(const RenderDev &P, int num_ray_bl
   const uint32_t bars = smem_base + C::smBar + pair * kBarsPerPair * 8;
   const uint32_t bar_full = bars + kBarXFull * 8, bar_free = bars + kBarXFree * 8, bar_mma = bars + kBarMma * 8,
                  bar_zfine = bars + kBarZFine * 8, bar_ready = bars + kBarReady * 8;
-  const uint32_t bar_ready_leader = map_to_cta(bar_ready, 0);
+  const uint32_t bar_peer_full = bars + kBarPeerFull * 8;
+  const uint32_t bar_ready_leader = map_to_cta(bar_ready, 0), bar_peer_full_leader = map_to_cta(bar_peer_full, 0);
+  const bool relay = warp == 0 && !leader;
   const uint32_t X_addr = smem_base + C::smX + pair * C::sets * kXBytes, C_addr = smem_base + C::smConst;
   const uint32_t W_addr = smem_base + C::smW;
   const uint32_t tm_acc0 = tmem_base + pair * 256, tm_acc1 = tm_acc0 + 128;
@@ -441,8 +444,15 @@ __device__ __forceinline__ void consumer_loop(const RenderDev &P, int num_ray_bl
       }
     }
   };
-  // every consumer thread of both CTAs has finished its TMEM accesses of this phase -> the leader may issue
-  auto arrive_ready = [&]() { mbar_arrive_cluster(bar_ready_leader); };
+  // every consumer thread of both CTAs has finished its TMEM accesses of this phase -> the leader may issue.  Local: the 128
+  // threads of this CTA's consumer group meet at a named barrier; the non-leader's warp 0 then sends ONE remote arrive.
+  auto arrive_ready = [&]() {
+    bar_named(1 + pair);
+    if (relay) {
+      if (elect_one()) mbar_arrive_cluster(bar_ready_leader);
+      __syncwarp();
+    }
+  };
   auto wait_ready = [&]() {
     mbar_wait_cluster(bar_ready, ready_phase & 1);
     ++ready_phase;
@@ -477,13 +487,19 @@ __device__ __forceinline__ void consumer_loop(const RenderDev &P, int num_ray_bl
       for (int s = 0; s < S; ++s, ++n) {
         if (issuer) {
           if (n > 0) wait_ready();                       // both CTAs have read the previous head accumulator (acc0 is free)
-          mbar_wait_cluster(bar_full, n & 1);            // both CTAs' X tiles are in place
+          mbar_wait(bar_full, n & 1);                    // this CTA's X tile is in place ...
+          mbar_wait_cluster(bar_peer_full, n & 1);       // ... and the peer's (relayed)
           tc_fence_after();
           if (elect_one()) {
             issue_l0();
             umma_commit2(bar_free);
             umma_commit2(bar_mma);
           }
+          __syncwarp();
+        }
+        if (relay) {                                      // non-leader: forward "my X tile is full" to the leader
+          mbar_wait(bar_full, n & 1);
+          if (elect_one()) mbar_arrive_cluster(bar_peer_full_leader);
           __syncwarp();
         }
         float z_next = 0.0f, dist;
@@ -588,20 +604,21 @@ __global__ void __launch_bounds__(kThreads3, 1) render_tc3_kernel(const RenderDe
   const int tid = threadIdx.x;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t rank = cluster_ctarank();
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + C::smBar + 96);
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + C::smBar + 112);
 
   if (tid < 32) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + C::smBar + 96), "r"(kTmemCols));
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + C::smBar + 112), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
   if (tid == 32) {
     for (int p = 0; p < C::pairs; ++p) {
       const uint32_t b = smem_base + C::smBar + p * kBarsPerPair * 8;
-      mbar_init(b + kBarXFull * 8, 256);   // 128 producer threads of EACH CTA (only the leader's copy is used)
+      mbar_init(b + kBarXFull * 8, 128);   // local: the 128 producer threads of this CTA
+      mbar_init(b + kBarPeerFull * 8, 1);  // leader's copy: the peer's relay thread ("the peer's X tile is full")
       mbar_init(b + kBarXFree * 8, 1);     // tcgen05.commit, multicast
       mbar_init(b + kBarMma * 8, 1);       // tcgen05.commit, multicast
       mbar_init(b + kBarZFine * 8, 128);   // local: consumer -> producer, fine depths written
-      mbar_init(b + kBarReady * 8, 256);   // 128 consumer threads of EACH CTA (only the leader's copy is used)
+      mbar_init(b + kBarReady * 8, 1);     // leader's copy: the peer's relay thread ("the peer's consumers passed this phase")
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }

@@ -103,3 +103,26 @@ def test_reference_module_names_are_installable():
     op.install_reference_modules()
     assert sys.modules["fused"].fused_bias_act is fused_mod.fused_bias_act
     assert sys.modules["upfirdn2d"].upfirdn2d is upfirdn2d_op.upfirdn2d
+
+
+@pytest.mark.parametrize("shape,pad", [((3, 2, 33, 70), (1, 2, 2, 1)), ((2, 3, 257, 257), (1, 1, 1, 1)), ((1, 1, 5, 3), (2, 2, 2, 2)),
+                                       ((1, 2, 64, 1025), (2, 1, 2, 1)), ((70000, 1, 4, 4), (1, 1, 1, 1))])
+@pytest.mark.parametrize("taps", ["blur", "random"])
+def test_streaming_4x4_fir_matches_oracle(shape, pad, taps):
+    """up == down == 1, 4x4 taps -> blur4x4_stream_kernel: separable path ([1,3,3,1] outer product) and general path (random
+    taps), odd row pitches (every row has a different 16-byte alignment), edge / narrow / > 65535-image cases; and the round-1
+    shared-memory kernel must agree with it."""
+    rs = np.random.RandomState(sum(shape))
+    if shape[0] > 1000:
+        x = rs.standard_normal((shape[0], 1, 1, 1)).astype(np.float32) * np.ones(shape, np.float32) + rs.standard_normal(shape[1:]).astype(np.float32)
+    else:
+        x = rs.standard_normal(shape).astype(np.float32)
+    k = ufd_kernel(np, [1, 3, 3, 1], 4.0) if taps == "blur" else rs.standard_normal((4, 4)).astype(np.float32)
+    y = op.upfirdn2d(_t(x), _t(k), pad=pad).cpu().numpy()
+    n = min(shape[0], 64)
+    ref = oo.upfirdn2d(x[:n], k, 1, 1, 1, 1, *pad)
+    assert y.shape[1:] == ref.shape[1:] and y.shape[0] == shape[0]
+    assert np.abs(y[:n] - ref).max() < 4e-6 * max(1.0, float(np.abs(ref).max()))
+    if shape[0] > 1000:
+        ref_last = oo.upfirdn2d(x[-2:], k, 1, 1, 1, 1, *pad)
+        assert np.abs(y[-2:] - ref_last).max() < 4e-6 * max(1.0, float(np.abs(ref_last).max()))
