@@ -405,6 +405,40 @@ def run_ours(args):
                 "max_abs_err_acc": float((out.acc_coarse[:, lo:hi] - ref32.acc_coarse).abs().max())}
         del ref32
 
+    # ---- the reference-precision mode on the tensor cores (HAV_PREC_FP16X3: fp16 hi + lo split operands, fp32 everything else),
+    #      same frame, same timing discipline (whole step: packing + render; L2 flushed between steps)
+    x3 = None
+    if rank == 0:
+        try:
+            o3 = None
+            for _ in range(3):
+                o3 = render.render_rays(d["ray_batch"], d["background_prior"], d["inv_head_T"], d["planes"], wvol, wts, S, 0,
+                                        precision="fp16x3", out=o3)
+            torch.cuda.synchronize()
+            n3 = max(3, min(args.steps, 10))
+            ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n3)]
+            for a3, b3 in ev3:
+                flush.zero_()
+                a3.record()
+                o3 = render.render_rays(d["ray_batch"], d["background_prior"], d["inv_head_T"], d["planes"], wvol, wts, S, 0,
+                                        precision="fp16x3", out=o3)
+                b3.record()
+            torch.cuda.synchronize()
+            ms3 = sum(a3.elapsed_time(b3) for a3, b3 in ev3) / n3
+            lo, hi = (H // 2 - 8) * W, (H // 2 + 8) * W
+            sub = lambda t: t[:, lo:hi].contiguous()
+            r32 = render.render_rays(sub(d["ray_batch"]), sub(d["background_prior"]), d["inv_head_T"], d["planes"], wvol, wts, S, 0,
+                                     precision="fp32")
+            x3 = {"value": R / (ms3 * 1e-3), "unit": "rays/s", "ms_per_step": ms3, "dtype": "fp16 hi+lo split operands (3 MMAs per product), fp32 accumulate / planes / encoding / composite",
+                  "kernel": "tc3::render_tc3_kernel<2> (CTA pairs, tcgen05 cta_group::2)",
+                  "max_abs_err_67ch_vs_fp32_mode": float((o3.rgb_coarse[:, lo:hi] - r32.rgb_coarse).abs().max()),
+                  "max_abs_err_acc_vs_fp32_mode": float((o3.acc_coarse[:, lo:hi] - r32.acc_coarse).abs().max()),
+                  "tensor_tflops_3x_count": 3 * R * S * FLOP_PER_SAMPLE / (ms3 * 1e-3) / 1e12}
+            x3_rgb = o3.rgb_coarse.reshape(-1, 67)[::61].cpu().numpy()
+            del o3, r32
+        except Exception as exc:
+            x3 = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     # ---- timed region 2: end to end through the host-buffer API: every step uploads its inputs from pinned host
     #      memory and downloads rendered maps to pinned host memory; copies of neighbouring frames overlap the
     #      render (PipelinedHostRenderer: H2D / compute / D2H streams, two buffer sets).  Two variants: ALL maps (the
@@ -522,6 +556,9 @@ def run_ours(args):
             ref_real["max_abs_diff_vs_ours_67ch"] = float(np.abs(mine - z_["rgb"]).max())
             ref_real["max_abs_diff_vs_ours_acc"] = float(np.abs(out.acc_coarse.reshape(-1)[::61].cpu().numpy() - z_["acc"]).max())
             ref_real["rays_compared"] = int(z_["rgb"].shape[0])
+            if x3 is not None and "error" not in x3:
+                x3["max_abs_diff_vs_reference_gpu_67ch"] = float(np.abs(x3_rgb - z_["rgb"]).max())
+                x3["speedup_vs_reference_gpu"] = x3["value"] / ref_real["rays_per_sec"]
             ref_real["value"], ref_real["unit"] = ref_real["rays_per_sec"], "rays/s"
             os.remove(tmp)
         except Exception as exc:
@@ -581,6 +618,7 @@ def run_ours(args):
                      "hbm_gbs_algorithmic": R * BYTES_PER_RAY / (kern_ms * 1e-3) / 1e9},
         "cpu_baseline": {"value": cpu_rate, "unit": "rays/s", "cores": threads, "kind": cpu_kind, "sample": cpu_sample,
                          "seconds": cpu_s},
+        "reference_precision_mode": x3,
         "reference_gpu": ref_real,
         "reference_gpu_port": ref_gpu,
         "clocks": clocks,

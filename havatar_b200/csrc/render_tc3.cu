@@ -179,7 +179,13 @@ __device__ __forceinline__ void producer_loop(const RenderDev &P, int num_ray_bl
                                               int pair, int t) {
   using C = Cfg<kMode>;
   constexpr bool kBF16 = C::bf16, kSplit = C::split;
-  const int warp = t >> 5, lane = t & 31;
+  // split mode: EIGHT producer warps serve the single pair -- two threads per row (tp = 0..255: row t = tp & 127, half = tp >> 7;
+  // half 0 builds the tap descriptors and the positional encoding of frequencies 0..3, half 1 frequencies 4..7) and each warp
+  // gathers 16 rows instead of 32: the fp32 gather + 48 exact sines per row made the 4-warp producer the bottleneck
+  const int tp = t, half = kSplit ? (tp >> 7) : 0;
+  t = tp & 127;
+  const int warp = tp >> 5, lane = tp & 31;
+  constexpr int kRowsPerWarp = kSplit ? 16 : 32;
   uint8_t *X = smem + C::smX + pair * C::sets * kXBytes;          // split: X_hi, then X_lo at + kXBytes
   uint8_t *stage_base = smem + C::smStage + pair * 2 * kStageBytes3;
   const uint32_t bars = smem_base + C::smBar + pair * kBarsPerPair * 8;
@@ -218,12 +224,14 @@ __device__ __forceinline__ void producer_loop(const RenderDev &P, int num_ray_bl
           int off0, off1;
           uint4 *sr = reinterpret_cast<uint4 *>(stage + t * kStageRow);
           if constexpr (kSplit) {
-            float w0[4], w1[4];
-            plane_taps_f32(qx, qy, P.PH, P.PW, ray.b, off0, w0);
-            plane_taps_f32(qz, qy, P.PH, P.PW, P.B + ray.b, off1, w1);
-            sr[0] = make_uint4(off0, off1, 0u, 0u);
-            sr[1] = make_uint4(__float_as_uint(w0[0]), __float_as_uint(w0[1]), __float_as_uint(w0[2]), __float_as_uint(w0[3]));
-            sr[2] = make_uint4(__float_as_uint(w1[0]), __float_as_uint(w1[1]), __float_as_uint(w1[2]), __float_as_uint(w1[3]));
+            if (half == 0) {
+              float w0[4], w1[4];
+              plane_taps_f32(qx, qy, P.PH, P.PW, ray.b, off0, w0);
+              plane_taps_f32(qz, qy, P.PH, P.PW, P.B + ray.b, off1, w1);
+              sr[0] = make_uint4(off0, off1, 0u, 0u);
+              sr[1] = make_uint4(__float_as_uint(w0[0]), __float_as_uint(w0[1]), __float_as_uint(w0[2]), __float_as_uint(w0[3]));
+              sr[2] = make_uint4(__float_as_uint(w1[0]), __float_as_uint(w1[1]), __float_as_uint(w1[2]), __float_as_uint(w1[3]));
+            }
           } else {
             uint32_t w0[4], w1[4];
             plane_taps_packed<kBF16>(qx, qy, P.PH, P.PW, ray.b, off0, w0);
@@ -234,11 +242,12 @@ __device__ __forceinline__ void producer_loop(const RenderDev &P, int num_ray_bl
           }
         }
         // positional encoding, order [f][sin|cos][xyz] (model/network/embedder.py:32-61)
-        uint32_t pk[24], pl[kSplit ? 24 : 1];
-        if constexpr (kSplit) {   // exact: sin(a), sin(a + pi/2) per frequency, like the reference
+        uint32_t pk[kSplit ? 12 : 24], pl[kSplit ? 12 : 1];
+        if constexpr (kSplit) {   // exact: sin(a), sin(a + pi/2) per frequency, like the reference; this thread's 4 frequencies
+          const float f0 = half == 0 ? 1.0f : 16.0f;
 #pragma unroll
-          for (int f = 0; f < kFreqs; ++f) {
-            const float fr = (float)(1 << f);
+          for (int f = 0; f < kFreqs / 2; ++f) {
+            const float fr = f0 * (float)(1 << f);
             float sn[3], cn[3];
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
@@ -265,13 +274,20 @@ __device__ __forceinline__ void producer_loop(const RenderDev &P, int num_ray_bl
             }
           }
         }
-        bar_named(3 + pair);                                  // tap descriptors of all 128 rows are visible
+        if constexpr (kSplit) asm volatile("bar.sync 3, 256;" ::: "memory");   // tap descriptors of all 128 rows are visible
+        else bar_named(3 + pair);
         if (n > 0) mbar_wait(bar_free, (n - 1) & 1);          // L0 of the previous tile has finished reading X (both CTAs)
+        if constexpr (kSplit) {      // 24 of the 48 encoding values = 3 chunks: half 0 -> chunks 16..18, half 1 -> 19..21
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          *reinterpret_cast<uint4 *>(X + (16 + c) * kChunkA + t * 16) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
-          if constexpr (kSplit)
-            *reinterpret_cast<uint4 *>(X + kXBytes + (16 + c) * kChunkA + t * 16) = make_uint4(pl[c * 4], pl[c * 4 + 1], pl[c * 4 + 2], pl[c * 4 + 3]);
+          for (int c = 0; c < 3; ++c) {
+            uint8_t *dst = X + (16 + 3 * half + c) * kChunkA + t * 16;
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+            *reinterpret_cast<uint4 *>(dst + kXBytes) = make_uint4(pl[c * 4], pl[c * 4 + 1], pl[c * 4 + 2], pl[c * 4 + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 6; ++c)
+            *reinterpret_cast<uint4 *>(X + (16 + c) * kChunkA + t * 16) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
         }
         if constexpr (!kSplit) {
           // cooperative gather, 16-bit planes: one step = 4 consecutive rows x 1 plane x 8 channel octets (see render_tc2.cu)
@@ -320,8 +336,8 @@ __device__ __forceinline__ void producer_loop(const RenderDev &P, int num_ray_bl
           // 16 lanes x 16 B); fp32 blend in ATen's order (nw, ne, sw, se), then hi / lo split into X_hi / X_lo
           const float4 *planes = reinterpret_cast<const float4 *>(P.planes_cl);
           const int quad = lane & 15, rsub = lane >> 4;
-          const uint8_t *sp0 = stage + (warp * 32 + rsub) * kStageRow;
-          uint8_t *xrow = X + (quad >> 1) * kChunkA + (warp * 32 + rsub) * 16 + (quad & 1) * 8;
+          const uint8_t *sp0 = stage + (warp * kRowsPerWarp + rsub) * kStageRow;
+          uint8_t *xrow = X + (quad >> 1) * kChunkA + (warp * kRowsPerWarp + rsub) * 16 + (quad & 1) * 8;
           const size_t row_pitch = (size_t)Wp * 16;
           float4 ta[4], tb[4], wa, wb;
           int offn;
@@ -348,13 +364,14 @@ __device__ __forceinline__ void producer_loop(const RenderDev &P, int num_ray_bl
           };
           issue(load_desc(0, wa), ta);
           offn = load_desc(1, wb);
+          constexpr int kSteps = kRowsPerWarp;        // 2 rows x 1 plane per step
 #pragma unroll 1
-          for (int i = 0; i < 32; i += 2) {
+          for (int i = 0; i < kSteps; i += 2) {
             issue(offn, tb);
             float4 wn;
-            if (i + 2 < 32) offn = load_desc(i + 2, wn);
+            if (i + 2 < kSteps) offn = load_desc(i + 2, wn);
             blend(ta, wa, i);
-            if (i + 2 < 32) {
+            if (i + 2 < kSteps) {
               issue(offn, ta);
               wa = wn;
               offn = load_desc(i + 3, wn);
@@ -613,7 +630,7 @@ __global__ void __launch_bounds__(kThreads3, 1) render_tc3_kernel(const RenderDe
   if (tid == 32) {
     for (int p = 0; p < C::pairs; ++p) {
       const uint32_t b = smem_base + C::smBar + p * kBarsPerPair * 8;
-      mbar_init(b + kBarXFull * 8, 128);   // local: the 128 producer threads of this CTA
+      mbar_init(b + kBarXFull * 8, C::split ? 256 : 128);   // local: the producer threads of this CTA
       mbar_init(b + kBarPeerFull * 8, 1);  // leader's copy: the peer's relay thread ("the peer's X tile is full")
       mbar_init(b + kBarXFree * 8, 1);     // tcgen05.commit, multicast
       mbar_init(b + kBarMma * 8, 1);       // tcgen05.commit, multicast
@@ -658,14 +675,15 @@ __global__ void __launch_bounds__(kThreads3, 1) render_tc3_kernel(const RenderDe
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int t = tid & 127;
   // 16-bit modes: warps 0-3 / 4-7 = consumers of pair 0 / 1, warps 8-11 / 12-15 = producers of pair 0 / 1.
-  // split mode (one pair): warps 0-3 consumers, warps 8-11 producers, the rest idle.
+  // split mode (one pair): warps 0-3 consumers (4-7 idle), warps 8-15 producers (two threads per row).
   const int pair = (warp_u >> 2) & 1;
   if (warp_u < 8) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
     if (pair < C::pairs) consumer_loop<kMode, kCheck>(P, num_ray_blocks, iters, smem_base, tmem_base, pair, warp_u & 3, t, rank == 0);
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
-    if (pair < C::pairs) producer_loop<kMode>(P, num_ray_blocks, iters, smem, smem_base, pair, t);
+    if (C::split) producer_loop<kMode>(P, num_ray_blocks, iters, smem, smem_base, 0, tid - 256);      // all eight warps, one pair
+    else producer_loop<kMode>(P, num_ray_blocks, iters, smem, smem_base, pair, t);
   }
   tc_fence_before();
   __syncthreads();
