@@ -13,6 +13,31 @@ for prec in ("fp32", "fp16"):
                            u_rand=dev(rnd["u_rand"]), noise_fine=dev(rnd["noise_fine"]), want_z_fine=True)
     torch.cuda.synchronize()
     print(prec, float(o.acc_fine.mean()))
+# round 2: CTA-pair kernel (16-bit and split precision; 4 ray blocks = an odd share per cluster -> dummy blocks), in-kernel ray
+# generation with a pixel selection, the range report, sample_pdf alone, the condition-image kernel, the streaming blur
+args = (dev(sc["background_prior"]), dev(sc["inv_head_T"]), dev(sc["planes"]), dev(sc["wvol"]), w, 16, 6)
+rk = dict(t_rand=dev(rnd["t_rand"]), noise_coarse=dev(rnd["noise_coarse"]), u_rand=dev(rnd["u_rand"]), noise_fine=dev(rnd["noise_fine"]))
+for kw in (dict(precision="fp16", cta_pairs=True), dict(precision="bf16", cta_pairs=True), dict(precision="fp16x3"),
+           dict(precision="fp16", check_range=True)):
+    o = render.render_rays(dev(sc["ray_batch"]), *args, want_pdf_inds=True, **kw, **rk)
+    torch.cuda.synchronize()
+    print(kw, float(o.acc_fine.mean()), int(o.pdf_inds.max()))
+cam = render.camera_block(np.array([700., 690., 0.5, 0.5], np.float32), np.stack([np.eye(4)[:3]] * 2).astype(np.float32), 2.4, 5.0)
+pix = torch.randint(0, 48 * 40, (2, 200), device="cuda", dtype=torch.int32)
+o = render.render_rays(None, *args, precision="fp16", camera=cam, img_hw=(48, 40), pixel_index=pix)
+torch.cuda.synchronize()
+print("camera", float(o.acc_coarse.mean()))
+smp, inds = render.sample_pdf(torch.rand(37, 63, device="cuda").sort(-1).values, torch.rand(37, 62, device="cuda"), 16, torch.rand(37, 16, device="cuda"))
+from havatar_b200 import data as hdata
+c = hdata.make_render_cond(torch.randint(0, 256, (3, 24, 24, 3), dtype=torch.uint8), torch.randint(0, 256, (3, 24, 24, 3), dtype=torch.uint8))
+torch.cuda.synchronize()
+print("pdf / cond", tuple(smp.shape), tuple(c.shape))
+kb = torch.tensor([1., 3., 3., 1.], device="cuda"); kb = kb[None] * kb[:, None]
+for shp, pad in (((2, 3, 33, 70), (1, 2, 2, 1)), ((1, 2, 5, 3), (2, 2)), ((3, 1, 257, 257), (1, 1))):
+    for kk in (kb, torch.randn(4, 4, device="cuda")):
+        y = op.upfirdn2d(torch.randn(*shp, device="cuda"), kk, pad=pad)
+torch.cuda.synchronize()
+print("blur ok")
 x = torch.randn(2, 72, 20, 12, device="cuda")
 wt = torch.randn(40, 72, 3, 3, device="cuda")
 for up, down in ((1, 1), (2, 1), (1, 2)):
