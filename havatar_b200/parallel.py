@@ -243,6 +243,15 @@ class GradSync:
 
     def _issue(self, b):
         if self.world > 1:
+            if b.flat.is_cuda:
+                # backward may run on more than one stream (the two plane generators, pipeline.two_stream_planes): everything
+                # enqueued so far on any of them precedes this collective
+                from .pipeline import forked_streams
+
+                cur = torch.cuda.current_stream(b.flat.device)
+                for s in forked_streams(b.flat.device):
+                    if s != cur:
+                        cur.wait_stream(s)
             op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
             b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
             self.collectives += 1

@@ -13,6 +13,41 @@ from . import styleunet
 from .graph import GraphedForward
 
 
+_SIDE = {}
+_FORK = {}      # device index -> (main, side) streams of the most recent two-stream plane generation
+
+
+def forked_streams(device):
+    """Streams that may hold gradient work of the plane generators' backward on `device` (parallel.GradSync orders its
+    collectives after all of them)."""
+    return _FORK.get(device.index if device.index is not None else torch.cuda.current_device(), ())
+
+
+def two_stream_planes(owner, lat, front, sides):
+    """The two plane generators are independent (model/nerf_model.py:73-84 runs them back to back): run YZ_gen on a side stream
+    while XY_gen runs on the current one.  Most of their layers (16^2 .. 64^2 maps) are latency-bound at batch 1, so the two
+    streams fill each other's gaps; under CUDA-graph capture the fork / join becomes two parallel branches of the graph."""
+    import os
+
+    if os.environ.get("HAV_PLANES_ONE_STREAM"):          # A/B aid
+        xy, _ = owner.XY_gen(lat, front.contiguous())
+        yz, _ = owner.YZ_gen(lat, sides.contiguous())
+        return torch.stack([xy, yz], dim=0)
+    main = torch.cuda.current_stream(front.device)
+    side = _SIDE.get(front.device.index)
+    if side is None:
+        side = _SIDE[front.device.index] = torch.cuda.Stream(front.device)
+    sides = sides.contiguous()
+    _FORK[front.device.index] = (main, side)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        yz, _ = owner.YZ_gen(lat, sides)
+    xy, _ = owner.XY_gen(lat, front.contiguous())
+    main.wait_stream(side)
+    yz.record_stream(main)
+    return torch.stack([xy, yz], dim=0)
+
+
 class AvatarHD(torch.nn.Module):
     def __init__(self, mlp_weights, wvol, render_size=128, out_size=512, plane_res=128, cond_size=256, feat_dim=64, latent_dim=32,
                  num_coarse=64, num_fine=0, precision="fp16", boxes=None):
@@ -37,9 +72,7 @@ class AvatarHD(torch.nn.Module):
         left = left.flip(dims=[3])
         if left.shape[1] > 3:
             left = left[:, :-1]
-        xy, _ = self.XY_gen(lat, front.contiguous())
-        yz, _ = self.YZ_gen(lat, torch.cat([left, right], dim=1).contiguous())
-        return torch.stack([xy, yz], dim=0)
+        return two_stream_planes(self, lat, front, torch.cat([left, right], dim=1))
 
     @torch.no_grad()
     def frame(self, ray_batch, background, latent_code, inv_head_T, front, left, right, style):

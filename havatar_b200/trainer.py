@@ -217,6 +217,13 @@ class PlaneNeRF(nn.Module):
         left = left_render_cond.flip(dims=[3])
         if left.shape[1] > 3:
             left = left[:, :-1]
+        # the two generators on two streams (autograd replays each backward on its forward stream, so training overlaps them
+        # too; parallel.GradSync orders its collectives after both streams)
+        if front_render_cond.is_cuda:
+            from .pipeline import two_stream_planes
+
+            self.triPlane_embeddings = two_stream_planes(self, lat, front_render_cond, torch.cat([left, right_render_cond], dim=1))
+            return
         xy, _ = self.XY_gen(lat, front_render_cond.contiguous())
         yz, _ = self.YZ_gen(lat, torch.cat([left, right_render_cond], dim=1).contiguous())
         self.triPlane_embeddings = torch.stack([xy, yz], dim=0)
