@@ -17,6 +17,20 @@ _SIDE = {}
 _FORK = {}      # device index -> (main, side) streams of the most recent two-stream plane generation
 
 
+def aux_stream(device, slot):
+    """A persistent side stream of `device` (slot 0 = YZ plane generator, 1 = skinning-weight volume decoder)."""
+    key = (device.index, slot)
+    st = _SIDE.get(key)
+    if st is None:
+        st = _SIDE[key] = torch.cuda.Stream(device)
+    return st
+
+
+def note_fork(device, *streams):
+    cur = _FORK.get(device.index, ())
+    _FORK[device.index] = tuple(dict.fromkeys(cur + streams))
+
+
 def forked_streams(device):
     """Streams that may hold gradient work of the plane generators' backward on `device` (parallel.GradSync orders its
     collectives after all of them)."""
@@ -34,11 +48,9 @@ def two_stream_planes(owner, lat, front, sides):
         yz, _ = owner.YZ_gen(lat, sides.contiguous())
         return torch.stack([xy, yz], dim=0)
     main = torch.cuda.current_stream(front.device)
-    side = _SIDE.get(front.device.index)
-    if side is None:
-        side = _SIDE[front.device.index] = torch.cuda.Stream(front.device)
+    side = aux_stream(front.device, 0)
     sides = sides.contiguous()
-    _FORK[front.device.index] = (main, side)
+    note_fork(front.device, main, side)
     side.wait_stream(main)
     with torch.cuda.stream(side):
         yz, _ = owner.YZ_gen(lat, sides)

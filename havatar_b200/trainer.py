@@ -272,9 +272,26 @@ class Trainer(nn.Module):
         """model/nerf_trainer.py:38-92 without the chunk loop; returns the 7-tuple of predict_and_render_radiance."""
         opt = getattr(self.cfg.nerf, inputs["mode"])
         inv_head_T = inputs["inv_head_T"]
+        # the skinning-weight VolumeDecoder (torch conv3d) is independent of the plane generators: evaluate it on its own stream
+        # while they run (its backward then overlaps theirs as well)
+        wvol, vol_stream = None, None
+        if inv_head_T.is_cuda:
+            from . import pipeline
+
+            main = torch.cuda.current_stream(inv_head_T.device)
+            vol_stream = pipeline.aux_stream(inv_head_T.device, 1)
+            pipeline.note_fork(inv_head_T.device, main, vol_stream)
+            vol_stream.wait_stream(main)
+            with torch.cuda.stream(vol_stream):
+                wvol = self.headpose_skin_net.volume()
         self.model_coarse.set_conditional_embedding(inputs["front_render_cond"], inputs["left_render_cond"],
                                                     inputs["right_render_cond"], inputs["latent_code"],
                                                     inv_head_T.reshape(inv_head_T.shape[0], -1))
+        if vol_stream is not None:
+            main.wait_stream(vol_stream)
+            wvol.record_stream(main)
+        else:
+            wvol = self.headpose_skin_net.volume()
         ray_batch, bg = inputs.get("ray_batch"), inputs["background_prior"]
         cam = {}
         if ray_batch is None:       # rays generated inside the kernel from the 18-float camera block (havatar_b200/data.py)
@@ -302,8 +319,7 @@ class Trainer(nn.Module):
             rnd["noise_coarse"] = torch.randn(B, R, nc, device=dev) * std
             if nf > 0:
                 rnd["noise_fine"] = torch.randn(B, R, (nc + 1) // 2 + nf, device=dev) * std
-        args = (ray_batch, bg, inv_head_T, self.model_coarse.triPlane_embeddings, self.headpose_skin_net.volume(),
-                self.model_coarse.mlp_weights(), nc, nf)
+        args = (ray_batch, bg, inv_head_T, self.model_coarse.triPlane_embeddings, wvol, self.model_coarse.mlp_weights(), nc, nf)
         prec = "fp16" if self.precision == "auto" else self.precision
         if torch.is_grad_enabled():
             o = hrender.render_rays_autograd(*args, boxes=self._boxes(), precision=prec, **cam, **rnd)
