@@ -38,9 +38,17 @@ def pack_weights_cached(weight, scale=1.0, up=1, transpose_io=False, precision="
     key = (weight.data_ptr(), weight._version, styleunet._EPOCH[0], tuple(weight.shape), float(scale))
     slot = (int(up), bool(transpose_io), precision, bool(flip))
     hit = cache.get(slot)
+    cur = torch.cuda.current_stream(weight.device)
     if hit is None or hit[0] != key:
-        hit = (key, pack_weights(weight, scale, up=up, transpose_io=transpose_io, precision=precision, flip=flip))
+        packed = pack_weights(weight, scale, up=up, transpose_io=transpose_io, precision=precision, flip=flip)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        hit = (key, packed, cur.cuda_stream, ev)
         cache[slot] = hit
+    elif hit[2] != cur.cuda_stream:
+        # packed on another stream (two passes of one network running side by side, pipeline.run_parallel): order this
+        # stream after the packing kernel
+        cur.wait_event(hit[3])
     return hit[1]
 
 

@@ -31,6 +31,27 @@ def note_fork(device, *streams):
     _FORK[device.index] = tuple(dict.fromkeys(cur + streams))
 
 
+def run_parallel(fn_main, fn_side, device, slot=2):
+    """(fn_main(), fn_side()) with fn_side on a side stream: for independent sub-graphs whose kernels are too small to fill the
+    GPU alone (e.g. the discriminator on the real and on the generated images).  Autograd replays each backward on the stream of
+    its forward, so the two backward passes overlap as well."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        return fn_main(), fn_side()
+    main = torch.cuda.current_stream(device)
+    side = aux_stream(device, slot)
+    note_fork(device, main, side)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        b = fn_side()
+    a = fn_main()
+    main.wait_stream(side)
+    for t in (b if isinstance(b, (tuple, list)) else (b,)):
+        if isinstance(t, torch.Tensor):
+            t.record_stream(main)
+    return a, b
+
+
 def forked_streams(device):
     """Streams that may hold gradient work of the plane generators' backward on `device` (parallel.GradSync orders its
     collectives after all of them)."""

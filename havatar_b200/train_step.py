@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
-from . import parallel, styleunet, trainer
+from . import parallel, pipeline, styleunet, trainer
 
 
 def default_cfg(num_coarse=64, num_fine=16, perturb=True, noise_std=0.1, inp_size=128, out_size=512, lr=5e-4):
@@ -193,7 +193,9 @@ class StageOneStep:
         if self.disc is not None:
             self.d.requires_grad(True)
             real = batch["target"].reshape(-1, P, P, 3).permute(0, 3, 1, 2).contiguous()
-            d_loss = d_logistic_loss(self.disc(real), self.disc(fake.detach()))
+            fake_d = fake.detach()
+            real_pred, fake_pred = pipeline.run_parallel(lambda: self.disc(real), lambda: self.disc(fake_d), self.device)
+            d_loss = d_logistic_loss(real_pred, fake_pred)
             d_loss.backward()
             self.d.step()
         return {"loss": loss.detach(), "d_loss": None if d_loss is None else d_loss.detach()}
@@ -267,7 +269,8 @@ class StageTwoStep:
         with torch.no_grad():
             render, _, _ = self.net(**self._inp(batch, "d"))
             fake = self.generator(self._noise(B, batch.get("z_d")), render[:, 3:].contiguous(), noise=batch.get("gen_noise_d"))
-        d_loss = d_logistic_loss(self.disc(gt_hr), self.disc(fake)) * self.gan_w
+        real_pred, fake_pred = pipeline.run_parallel(lambda: self.disc(gt_hr), lambda: self.disc(fake), self.device)
+        d_loss = d_logistic_loss(real_pred, fake_pred) * self.gan_w
         d_loss.backward()
         self.d.step()
         return {"d_loss": d_loss.detach(), "d": (d_loss / self.gan_w).detach()}
