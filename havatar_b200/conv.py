@@ -27,6 +27,11 @@ def _check(t, name):
     return t.detach().contiguous()
 
 
+# Bumped by every CUDA-graph capture this package starts (graph.GraphedForward, train_step.Graphed): a weight image packed inside
+# one capture lives in that graph's memory pool and its event belongs to that capture, so it is reused only inside the same one.
+CAPTURE_GEN = [0]
+
+
 def pack_weights_cached(weight, scale=1.0, up=1, transpose_io=False, precision="fp16", flip=False, cache=None):
     """pack_weights memoised in `cache` (a dict owned by the module that owns `weight`) on (storage, version, cache epoch):
     within one training iteration the same parameter is packed once per (layout, precision) even when several passes use it
@@ -39,15 +44,19 @@ def pack_weights_cached(weight, scale=1.0, up=1, transpose_io=False, precision="
     slot = (int(up), bool(transpose_io), precision, bool(flip))
     hit = cache.get(slot)
     cur = torch.cuda.current_stream(weight.device)
-    if hit is None or hit[0] != key:
+    capturing = torch.cuda.is_current_stream_capturing()
+    # an image packed inside a CUDA-graph capture lives in that graph's memory and may only be reused inside the same capture
+    gen = CAPTURE_GEN[0] if capturing else None
+    if hit is None or hit[0] != key or (hit[4] is not None and hit[4] != gen):
         packed = pack_weights(weight, scale, up=up, transpose_io=transpose_io, precision=precision, flip=flip)
         ev = torch.cuda.Event()
         ev.record(cur)
-        hit = (key, packed, cur.cuda_stream, ev)
+        hit = (key, packed, cur.cuda_stream, ev, gen)
         cache[slot] = hit
-    elif hit[2] != cur.cuda_stream:
-        # packed on another stream (two passes of one network running side by side, pipeline.run_parallel): order this
-        # stream after the packing kernel
+    elif hit[2] != cur.cuda_stream and (hit[4] is not None or not capturing):
+        # packed on another stream (two passes of one network running side by side, pipeline.run_parallel): order this stream
+        # after the packing kernel.  (An image packed eagerly and met again under capture needs no edge: every capture in this
+        # package starts after a device synchronisation, and a capture may not depend on uncaptured work.)
         cur.wait_event(hit[3])
     return hit[1]
 

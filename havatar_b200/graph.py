@@ -19,6 +19,9 @@ class GraphedForward:
                 self.fn(*self.static_in)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        from . import conv
+
+        conv.CAPTURE_GEN[0] += 1
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph), torch.no_grad():
             self.static_out = self.fn(*self.static_in)

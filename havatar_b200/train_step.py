@@ -338,6 +338,9 @@ class Graphed:
                 # entry would leave the graph without the kernel that refreshes it, and eager code must not reuse graph memory
                 styleunet.invalidate_caches()
                 if graphable:
+                    from . import conv
+
+                    conv.CAPTURE_GEN[0] += 1
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=self.stream):
                         self.outs[name] = fn(self.static)
