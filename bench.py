@@ -538,6 +538,8 @@ def run_ours(args):
     threads = os.cpu_count() or 1
     cpu_kind = "port"
     try:
+        if args.no_reference_gpu:
+            raise RuntimeError("skipped (--no-reference-gpu)")
         if _ref_installed():      # the unmodified reference on this box's host cores (bounded sample: 1/8 of the frame x 3)
             rc_ = _ref_child(["--device", "cpu", "--chunks", "8", "--reps", "3", "--warmup", "1"], 600)
             cpu_rate, cpu_s, cpu_sample, cpu_kind = rc_["rays_per_sec"], sum(rc_["seconds"]), rc_["sample"], "reference"
@@ -549,7 +551,7 @@ def run_ours(args):
     # for sm_100a by baseline/install_ref.py) on this GPU, in its own process -- Trainer.nerf_forward's 4096-ray chunk loop at
     # the same frame / weights / planes, fp32; plus its SWGAN_unet and whole HD frame.  This is the >= 10x denominator.
     ref_real = None
-    if _ref_installed() and world == 1:
+    if _ref_installed() and world == 1 and not args.no_reference_gpu:
         try:
             tmp = os.path.join("/tmp", "hav_ref_gpu_%d.npz" % os.getpid())
             ref_real = _ref_child(["--device", "cuda", "--reps", "3", "--hd", "--out", tmp], 900)
@@ -652,6 +654,8 @@ def main():
     ap.add_argument("--train-deadline", type=int, default=300, help="seconds after which the training legs are abandoned")
     ap.add_argument("--no-train", dest="no_train", action="store_true", help="skip the training-step measurement")
     ap.add_argument("--no-hd", dest="no_hd", action="store_true", help="skip the secondary HD frames/s measurement")
+    ap.add_argument("--no-reference-gpu", dest="no_reference_gpu", action="store_true",
+                    help="skip the reference legs that run in child processes (profiling runs under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
