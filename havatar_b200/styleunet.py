@@ -406,6 +406,39 @@ class _CondEncoder:
         return feats
 
 
+class _SkipFork:
+    """The ToRGB pyramid of SWGAN_unet (styleUnet.py:1398-1406) depends on each level's feature map but nothing on the main
+    path depends on it until the final inverse wavelet transform: its ~25 small launches per level (1x1 modulated convolution,
+    Haar synthesis -> x2 upsample -> Haar analysis of the running skip, adds) run on a side stream beside the next level's
+    convolutions.  `with fork.branch(x): ...` runs the body on the side stream after everything issued so far; `join(t)` hands
+    the result back to the main stream."""
+
+    def __init__(self, device):
+        self.on = torch.device(device).type == "cuda"
+        if self.on:
+            from . import pipeline
+
+            self.main = torch.cuda.current_stream(device)
+            self.side = pipeline.aux_stream(torch.device(device), 3)
+            pipeline.note_fork(torch.device(device), self.main, self.side)
+
+    def branch(self, *consumed):
+        import contextlib
+
+        if not self.on:
+            return contextlib.nullcontext()
+        self.side.wait_stream(self.main)
+        for t in consumed:
+            t.record_stream(self.side)
+        return torch.cuda.stream(self.side)
+
+    def join(self, t):
+        if self.on:
+            self.main.wait_stream(self.side)
+            t.record_stream(self.main)
+        return t
+
+
 class SWGAN_unet(nn.Module):
     """styleUnet.py:1190-1410."""
 
@@ -470,6 +503,7 @@ class SWGAN_unet(nn.Module):
             return T.swgan_unet_forward(self, latent, condition_img, noise)
         feats = _CondEncoder.run(self, condition_img)
         i, skip, out = 0, None, None
+        fork = _SkipFork(condition_img.device)
         for conv1, conv2, n1, n2, to_rgb in zip(self.convs[::2], self.convs[1::2], noise[::2], noise[1::2], self.to_rgbs):
             if i == 0:
                 out = self.comb_convs[-1](feats[-1], out_cl=True)
@@ -477,9 +511,10 @@ class SWGAN_unet(nn.Module):
                 out = self.comb_convs[-1 - (i // 2)](torch.cat([out, feats[-1 - (i // 2)]], dim=-1), out_cl=True)
             out = conv1(out, latent[:, i], noise=n1, out_cl=True)
             out = conv2(out, latent[:, i + 1], noise=n2, out_cl=True)
-            skip = to_rgb(out, latent[:, i + 2], skip)          # 12-channel wavelet skip stays NCHW fp32
+            with fork.branch(out):
+                skip = to_rgb(out, latent[:, i + 2], skip)      # 12-channel wavelet skip stays NCHW fp32
             i += 2
-        return self.iwt(skip)
+        return self.iwt(fork.join(skip))
 
 
 class Discriminator(nn.Module):

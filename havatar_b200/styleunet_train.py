@@ -142,8 +142,11 @@ def cond_encoder(net, cond_img):
 
 def swgan_unet_forward(net, latent, condition_img, noise):
     """SWGAN_unet.forward after the style / noise bookkeeping (styleUnet.py:1379-1410)."""
+    from .styleunet import _SkipFork
+
     feats = cond_encoder(net, condition_img)
     i, skip, out = 0, None, None
+    fork = _SkipFork(condition_img.device)          # the ToRGB pyramid on a side stream (its backward follows it there)
     for conv1, conv2, n1, n2, rgb in zip(net.convs[::2], net.convs[1::2], noise[::2], noise[1::2], net.to_rgbs):
         if i == 0:
             out = conv_layer(net.comb_convs[-1], feats[-1])
@@ -151,9 +154,10 @@ def swgan_unet_forward(net, latent, condition_img, noise):
             out = conv_layer(net.comb_convs[-1 - (i // 2)], torch.cat([out, feats[-1 - (i // 2)]], dim=1))
         out = styled_conv(conv1, out, latent[:, i], n1)
         out = styled_conv(conv2, out, latent[:, i + 1], n2)
-        skip = to_rgb(rgb, out, latent[:, i + 2], skip)
+        with fork.branch(out):
+            skip = to_rgb(rgb, out, latent[:, i + 2], skip)
         i += 2
-    return net.iwt(skip)
+    return net.iwt(fork.join(skip))
 
 
 def stylegan_zxc_forward(net, latent, cond_feats, noise):
