@@ -17,9 +17,27 @@ _SIDE = {}
 _FORK = {}      # device index -> (main, side) streams of the most recent two-stream plane generation
 
 
+_NAMESPACE = [0]
+
+
+class stream_namespace:
+    """While active, aux_stream() hands out a separate family of side streams: two branches of the iteration that each fork
+    their own sub-streams (train_step.StageTwoStep.dg_step) must not share them, or they would serialise on each other."""
+
+    def __init__(self, ns):
+        self.ns = int(ns)
+
+    def __enter__(self):
+        self.prev, _NAMESPACE[0] = _NAMESPACE[0], self.ns
+
+    def __exit__(self, *exc):
+        _NAMESPACE[0] = self.prev
+
+
 def aux_stream(device, slot):
-    """A persistent side stream of `device` (slot 0 = YZ plane generator, 1 = skinning-weight volume decoder)."""
-    key = (device.index, slot)
+    """A persistent side stream of `device` (slot 0 = YZ plane generator, 1 = skinning-weight volume decoder, 2 = second
+    discriminator pass, 3 = ToRGB pyramid, 4 = the G-step forward of the overlapped stage-two iteration)."""
+    key = (device.index, slot + 16 * _NAMESPACE[0])
     st = _SIDE.get(key)
     if st is None:
         st = _SIDE[key] = torch.cuda.Stream(device)

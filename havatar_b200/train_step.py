@@ -203,9 +203,10 @@ class StageOneStep:
 
 class StageTwoStep:
     def __init__(self, n_frames=8, device="cuda", cfg=None, precision="fp16", render_size=128, gen_size=512, d_reg_every=16,
-                 r1=10.0, latent=64, n_mlp=4, seed=0, capturable=False, lr=1e-3, nerf_lr=None):
+                 r1=10.0, latent=64, n_mlp=4, seed=0, capturable=False, lr=1e-3, nerf_lr=None, overlap=True):
         """lr: su_args.lr as train_avatarHD.py:118 overrides it (1e-3); nerf_lr: cfg.optimizer.lr (1e-4 in
-        config/singleview_512_HD_base.yml:116)."""
+        config/singleview_512_HD_base.yml:116).  overlap: on iterations without the R1 pass, run the G step's forward (render +
+        generator, which do not depend on the discriminator) on a side stream WHILE the D step runs (dg_step)."""
         torch.manual_seed(seed)
         self.cfg = cfg or default_cfg(inp_size=render_size, out_size=gen_size, lr=1e-4)
         nerf_lr = float(_cfg_get(self.cfg, "optimizer.lr", 1e-4)) if nerf_lr is None else nerf_lr
@@ -226,6 +227,7 @@ class StageTwoStep:
         self.d = _Group([self.disc], lr * d_ratio, betas=(0.0, 0.99 ** d_ratio))                             # :120
         self.render_size, self.gen_size, self.latent = render_size, gen_size, latent
         self.d_reg_every, self.r1, self.it = d_reg_every, r1, 0
+        self.overlap = bool(overlap) and self.device.type == "cuda"
         self.accum = 0.5 ** (32 / (10 * 1000))                                                               # :162
         self.gan_w = torch.tensor(1e-3, dtype=torch.float32, device=self.device)
 
@@ -242,7 +244,15 @@ class StageTwoStep:
         self.gan_w.fill_(min(1e-3 * 1.1 ** ((self.it - 1) // 500), 0.1))                                       # :205-206
 
     def parts(self):
+        """The parts of THIS iteration (after pre_step): the overlapped D + G part unless the R1 pass sits between them."""
+        if self.overlap and (self.it - 1) % self.d_reg_every != 0:
+            return [("dg", self.dg_step, True)]
         return [("d", self.d_step, True), ("r1", self.r1_step, False), ("g", self.g_step, True)]
+
+    def all_parts(self):
+        """Every part any iteration can consist of (what train_step.Graphed captures)."""
+        seq = [("d", self.d_step, True), ("r1", self.r1_step, False), ("g", self.g_step, True)]
+        return seq + ([("dg", self.dg_step, True)] if self.overlap else [])
 
     def __call__(self, batch):
         """batch: the StageOneStep keys with full low-res frames (R = render_size^2) plus gt_hr_img [B,3,G,G] and gt_lr_mask
@@ -262,10 +272,12 @@ class StageTwoStep:
                     front_render_cond=batch["front_render_cond"], left_render_cond=batch["left_render_cond"],
                     right_render_cond=batch["right_render_cond"], randoms=batch.get("randoms_" + phase))
 
-    def d_step(self, batch):                                                                                    # :211-231
+    def d_step(self, batch, toggle=True):                                                                       # :211-231
         gt_hr = batch["gt_hr_img"]
         B = gt_hr.shape[0]
-        self.nerf.requires_grad(False), self.g.requires_grad(False), self.d.requires_grad(True)
+        if toggle:
+            self.nerf.requires_grad(False), self.g.requires_grad(False)
+        self.d.requires_grad(True)
         with torch.no_grad():
             render, _, _ = self.net(**self._inp(batch, "d"))
             fake = self.generator(self._noise(B, batch.get("z_d")), render[:, 3:].contiguous(), noise=batch.get("gen_noise_d"))
@@ -286,20 +298,26 @@ class StageTwoStep:
         self.d.step()
         return {"r1": (r1_loss / self.gan_w).detach()}                                                       # loss_dict["r1"], :240
 
-    def g_step(self, batch):                                                                                    # :243-303
+    def _g_forward(self, batch):
+        """The part of the G step that does not involve the discriminator (:243-262): low-res render with gradients, its
+        losses, the generator forward."""
         gt_hr, rs, gs = batch["gt_hr_img"], self.render_size, self.gen_size
         B = gt_hr.shape[0]
         gt_lr = F.interpolate(F.interpolate(gt_hr, size=(rs, rs), mode="bilinear", align_corners=True), size=(gs, gs),
                               mode="bilinear", align_corners=True)                                              # :202-204
-        self.nerf.requires_grad(True), self.g.requires_grad(True), self.d.requires_grad(False)
         render, mask, lat = self.net(**self._inp(batch, "g"))
         lr_img = F.interpolate(render[:, :3], size=(gs, gs), mode="bilinear", align_corners=True)
         rgb_loss = F.mse_loss(lr_img, gt_lr)
         mask_loss = self.cfg.experiment.mask_weight * F.binary_cross_entropy(mask.clip(1e-3, 1.0 - 1e-3), batch["gt_lr_mask"])
-        g_loss = rgb_loss + lat + mask_loss
         fake = self.generator(self._noise(B, batch.get("z_g")), render[:, 3:].contiguous(), noise=batch.get("gen_noise_g"))
-        g_ns, hr_l1 = g_nonsaturating_loss(self.disc(fake)), F.l1_loss(fake, gt_hr)
-        g_loss = g_loss + g_ns * self.gan_w + hr_l1
+        hr_l1 = F.l1_loss(fake, gt_hr)
+        return dict(fake=fake, partial=rgb_loss + lat + mask_loss + hr_l1, rgb_loss=rgb_loss, mask_loss=mask_loss, hr_l1=hr_l1)
+
+    def _g_finish(self, gf):
+        """:264-303 from the discriminator's verdict on: adversarial term, one backward, generator and render Adam steps, EMA."""
+        self.d.requires_grad(False)
+        g_ns = g_nonsaturating_loss(self.disc(gf["fake"]))
+        g_loss = gf["partial"] + g_ns * self.gan_w
         g_loss.backward()
         self.g.step()
         self.nerf.step()
@@ -307,8 +325,34 @@ class StageTwoStep:
             pe, pg = list(self.g_ema.parameters()), list(self.generator.parameters())
             torch._foreach_mul_(pe, self.accum)
             torch._foreach_add_(pe, pg, alpha=1 - self.accum)
-        return {"g_loss": g_loss.detach(), "rgb_loss": rgb_loss.detach(), "mask_loss": mask_loss.detach(), "g_nonsat": g_ns.detach(),
-                "hr_l1": hr_l1.detach()}
+        return {"g_loss": g_loss.detach(), "rgb_loss": gf["rgb_loss"].detach(), "mask_loss": gf["mask_loss"].detach(),
+                "g_nonsat": g_ns.detach(), "hr_l1": gf["hr_l1"].detach()}
+
+    def g_step(self, batch):                                                                                    # :243-303
+        self.nerf.requires_grad(True), self.g.requires_grad(True)
+        return self._g_finish(self._g_forward(batch))
+
+    def dg_step(self, batch):
+        """D step and G step of an iteration without the R1 pass, with the G step's forward overlapped: the low-res render and
+        the generator forward of the G step read only weights the D step does not touch, so they run on a side stream (with
+        their own family of sub-streams) while the D step -- no-grad render + generator, discriminator forward / backward, Adam
+        -- runs on the main one; the streams join before the updated discriminator judges the G step's image.  Same arithmetic
+        and update order as d_step(); g_step(), only the random draws are taken in a different order."""
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        side = pipeline.aux_stream(dev, 4)
+        pipeline.note_fork(dev, main, side)
+        self.nerf.requires_grad(True), self.g.requires_grad(True)
+        side.wait_stream(main)
+        with torch.cuda.stream(side), pipeline.stream_namespace(1):
+            gf = self._g_forward(batch)
+        out = self.d_step(batch, toggle=False)
+        main.wait_stream(side)
+        for v in gf.values():
+            v.record_stream(main)
+        out.update(self._g_finish(gf))
+        out["r1"] = None
+        return out
 
 
 class Graphed:
@@ -333,7 +377,7 @@ class Graphed:
                 if not grp.flat and grp.sync is None:
                     grp.opt.zero_grad(set_to_none=True)
             step.pre_step()
-            for name, fn, graphable in step.parts():
+            for name, fn, graphable in (step.all_parts() if hasattr(step, "all_parts") else step.parts()):
                 # derived-tensor caches (packed weights, ...) must not cross a capture boundary: a hit on an eagerly built
                 # entry would leave the graph without the kernel that refreshes it, and eager code must not reuse graph memory
                 styleunet.invalidate_caches()

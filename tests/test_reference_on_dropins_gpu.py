@@ -93,10 +93,12 @@ def test_reference_training_utilities_drive_our_modules(clean_imports):
     assert torch.isfinite(r1) and abs(float(r1) - float(r1_ours)) < 1e-3 * abs(float(r1_ours)) + 1e-9
     (10.0 / 2 * r1 * 16 + 0 * pred[0]).sum().backward()   # train_avatarHD.py:239: the 0 * pred term reaches the biases
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in disc.parameters())
-    g = SWGAN_unet(inp_size=16, inp_ch=8, out_ch=3, out_size=64, style_dim=64, n_mlp=2).cuda()
-    g_ema = SWGAN_unet(inp_size=16, inp_ch=8, out_ch=3, out_size=64, style_dim=64, n_mlp=2).cuda()
+    g = SWGAN_unet(inp_size=32, inp_ch=8, out_ch=3, out_size=128, style_dim=64, n_mlp=4).cuda()
+    g_ema = SWGAN_unet(inp_size=32, inp_ch=8, out_ch=3, out_size=128, style_dim=64, n_mlp=4).cuda()
     su.accumulate(g_ema, g, 0)                             # train_avatarHD.py:115
     assert all(torch.equal(a, b) for a, b in zip(g_ema.parameters(), g.parameters()))
     noise = su.mixing_noise(2, 64, 0.0, "cuda")
-    img = g(noise, torch.randn(2, 8, 16, 16, device="cuda"))
-    assert img.shape == (2, 3, 64, 64) and torch.isfinite(su.g_nonsaturating_loss(disc(img)))
+    img = g(noise, torch.randn(2, 8, 32, 32, device="cuda"))
+    assert img.shape == (2, 3, 128, 128)
+    disc128 = Discriminator(128, 3).cuda()
+    assert torch.isfinite(su.g_nonsaturating_loss(disc128(img)))

@@ -101,3 +101,37 @@ def test_graphed_stage_two_step_with_eager_r1():
     assert any(o["r1"] is not None for o in outs)
     moved, total = _moved(g0, [step.generator])
     assert moved >= 0.9 * total
+
+
+def test_overlapped_stage_two_iteration_equals_the_sequential_one():
+    """StageTwoStep.dg_step (G-step forward on a side stream while the D step runs) against d_step(); g_step() on an iteration
+    without the R1 pass: same weights, same supplied random draws -> same losses and the same updated weights up to the
+    summation-order noise of the atomics in the render backward."""
+    import numpy as np
+
+    from havatar_b200 import synth
+
+    def run(overlap):
+        step = train_step.StageTwoStep(n_frames=2, render_size=32, gen_size=128, d_reg_every=4, seed=0, overlap=overlap)
+        batch = train_step.synthetic_batch(2, 2, "cuda", seed=1, render_size=32, gen_size=128)
+        for ph in ("d", "g"):
+            r = synth.randoms(2, 32 * 32, 64, 16, seed=5 if ph == "d" else 6)
+            batch["randoms_" + ph] = {k: torch.from_numpy(r[k]).cuda() for k in ("t_rand", "u_rand", "noise_coarse", "noise_fine")}
+            batch["z_" + ph] = torch.from_numpy(synth.named_normal("z" + ph, (2, 64), 1)).cuda()
+            batch["gen_noise_" + ph] = [torch.from_numpy(synth.named_normal("n%s%d" % (ph, i), (1, 1, 2 ** r_, 2 ** r_), 1)).cuda()
+                                        for i, r_ in enumerate(r_ for r_ in range(4, 7) for _ in range(2))]
+        outs = [step(batch) for _ in range(2)]           # iteration 0 regularises (sequential path); iteration 1 is the one under test
+        torch.cuda.synchronize()
+        assert ("dg" in [n for n, _, _ in step.parts()]) == overlap
+        return outs[1], step
+
+    a, sa = run(False)
+    b, sb = run(True)
+    for k in ("d", "g_loss", "rgb_loss", "hr_l1", "g_nonsat"):
+        assert abs(float(a[k]) - float(b[k])) < 2e-3 * abs(float(a[k])) + 1e-6, (k, float(a[k]), float(b[k]))
+    for ma, mb in ((sa.generator, sb.generator), (sa.disc, sb.disc), (sa.net.model_coarse.layers_xyz, sb.net.model_coarse.layers_xyz)):
+        # Adam's first steps move a weight by ~lr * sign(g): entries whose gradient sign flips under reordering noise differ by
+        # up to 2 lr per step; everything else agrees closely (fraction taken over the whole sub-network)
+        diff = torch.cat([(pa - pb).detach().abs().reshape(-1) for pa, pb in zip(ma.parameters(), mb.parameters())])
+        assert float(diff.max()) <= 4.1 * 1e-3, float(diff.max())
+        assert float((diff > 2e-4).float().mean()) < 0.05
