@@ -120,7 +120,7 @@ class _Group:
 
 class StageOneStep:
     def __init__(self, n_frames=4, device="cuda", cfg=None, precision="fp16", patch=64, lr=None, with_discriminator=True, seed=0,
-                 capturable=False, pretrain_wc_iters=0):
+                 capturable=False, pretrain_wc_iters=0, overlap=True):
         """pretrain_wc_iters > 0: a run that does not resume from a checkpoint first fits the skinning-weight volume to the head
         box (train_avatar.py:93-95 uses 3000 iterations); load a checkpoint into `self.net` instead when resuming."""
         torch.manual_seed(seed)
@@ -139,6 +139,9 @@ class StageOneStep:
         self.g = _Group([self.net], lr)                                                                   # train_avatar.py:68-71
         self.d = _Group([self.disc], 2e-3 * 16 / 17, betas=(0.0, 0.99 ** (16 / 17))) if self.disc is not None else None
         self.patch, self.it, self.lr0 = patch, 0, lr
+        # overlap: run the patch discriminator's own forward / backward on a side stream WHILE the render network's backward runs
+        # (neither reads what the other writes; both optimiser steps wait for both)
+        self.overlap = bool(overlap) and self.device.type == "cuda"
 
     def groups(self):
         return [g for g in (self.g, self.d) if g is not None]
@@ -187,17 +190,36 @@ class StageOneStep:
             B = rgb.shape[0]
             fake = rgb[..., :3].reshape(B, P, P, 3).permute(0, 3, 1, 2).contiguous()
             loss = loss + 0.05 * g_nonsaturating_loss(self.disc(fake))       # in the slot of the 0.05-weighted patch term (:144)
-        loss.backward()                                                                                             # :149
-        self.g.step()                                                                                               # :151 (clears the gradients)
         d_loss = None
-        if self.disc is not None:
+
+        def d_pass():
             self.d.requires_grad(True)
             real = batch["target"].reshape(-1, P, P, 3).permute(0, 3, 1, 2).contiguous()
             fake_d = fake.detach()
             real_pred, fake_pred = pipeline.run_parallel(lambda: self.disc(real), lambda: self.disc(fake_d), self.device)
-            d_loss = d_logistic_loss(real_pred, fake_pred)
-            d_loss.backward()
+            dl = d_logistic_loss(real_pred, fake_pred)
+            dl.backward()
+            return dl
+
+        if self.disc is not None and self.overlap:
+            main = torch.cuda.current_stream(self.device)
+            side = pipeline.aux_stream(self.device, 4)
+            pipeline.note_fork(self.device, main, side)
+            side.wait_stream(main)
+            fake.record_stream(side)
+            with torch.cuda.stream(side), pipeline.stream_namespace(1):
+                d_loss = d_pass()
+            loss.backward()                                                                                         # :149
+            main.wait_stream(side)
+            d_loss.record_stream(main)
+            self.g.step()                                                                                           # :151 (clears the gradients)
             self.d.step()
+        else:
+            loss.backward()
+            self.g.step()
+            if self.disc is not None:
+                d_loss = d_pass()
+                self.d.step()
         return {"loss": loss.detach(), "d_loss": None if d_loss is None else d_loss.detach()}
 
 

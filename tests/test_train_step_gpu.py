@@ -135,3 +135,23 @@ def test_overlapped_stage_two_iteration_equals_the_sequential_one():
         diff = torch.cat([(pa - pb).detach().abs().reshape(-1) for pa, pb in zip(ma.parameters(), mb.parameters())])
         assert float(diff.max()) <= 4.1 * 1e-3, float(diff.max())
         assert float((diff > 2e-4).float().mean()) < 0.05
+
+
+def test_overlapped_stage_one_discriminator_pass_equals_the_sequential_one():
+    """StageOneStep(overlap=True) runs the patch discriminator's own forward / backward on a side stream while the render
+    network's backward runs: same losses and weights as the sequential order (deterministic configuration)."""
+    def run(overlap):
+        cfg = train_step.default_cfg(num_coarse=32, num_fine=8, perturb=False, noise_std=0.0)
+        step = train_step.StageOneStep(n_frames=4, cfg=cfg, patch=64, seed=0, overlap=overlap)
+        batch = train_step.synthetic_batch(1, 4, "cuda", seed=0, patch=64)
+        outs = [step(batch) for _ in range(3)]
+        torch.cuda.synchronize()
+        return outs, step
+
+    (a, sa), (b, sb) = run(False), run(True)
+    for x, y in zip(a, b):
+        assert abs(float(x["loss"]) - float(y["loss"])) < 2e-3 * abs(float(x["loss"]))
+        assert abs(float(x["d_loss"]) - float(y["d_loss"])) < 2e-3 * abs(float(x["d_loss"]))
+    for ma, mb in ((sa.disc, sb.disc), (sa.net.model_coarse.layers_xyz, sb.net.model_coarse.layers_xyz)):
+        diff = torch.cat([(pa - pb).detach().abs().reshape(-1) for pa, pb in zip(ma.parameters(), mb.parameters())])
+        assert float((diff > 5e-4).float().mean()) < 0.05
