@@ -249,9 +249,15 @@ class GradSync:
                 from .pipeline import forked_streams
 
                 cur = torch.cuda.current_stream(b.flat.device)
+                capturing = torch.cuda.is_current_stream_capturing()
                 for s in forked_streams(b.flat.device):
-                    if s != cur:
-                        cur.wait_stream(s)
+                    if s == cur:
+                        continue
+                    if capturing:      # only streams that are part of this capture may be waited on (the others are idle)
+                        with torch.cuda.stream(s):
+                            if not torch.cuda.is_current_stream_capturing():
+                                continue
+                    cur.wait_stream(s)
             op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
             b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
             self.collectives += 1
