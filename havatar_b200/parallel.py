@@ -243,23 +243,34 @@ class GradSync:
 
     def _issue(self, b):
         if self.world > 1:
+            comm = None
             if b.flat.is_cuda:
-                # backward may run on more than one stream (the two plane generators, pipeline.two_stream_planes): everything
-                # enqueued so far on any of them precedes this collective
-                from .pipeline import forked_streams
+                # backward may run on more than one stream (pipeline.two_stream_planes, run_parallel, ...): the collective must
+                # follow everything enqueued so far on ANY of them.  It is issued from a dedicated staging stream that waits on
+                # all of them, so that no compute stream is held up by a sibling's unfinished work (a wait on the issuing
+                # stream itself would serialise the branches at every bucket boundary).
+                from .pipeline import aux_stream, forked_streams
 
-                cur = torch.cuda.current_stream(b.flat.device)
+                dev = b.flat.device
+                cur = torch.cuda.current_stream(dev)
+                comm = aux_stream(dev, 15)
                 capturing = torch.cuda.is_current_stream_capturing()
-                for s in forked_streams(b.flat.device):
-                    if s == cur:
+                comm.wait_stream(cur)
+                for s in forked_streams(dev):
+                    if s == cur or s == comm:
                         continue
                     if capturing:      # only streams that are part of this capture may be waited on (the others are idle)
                         with torch.cuda.stream(s):
                             if not torch.cuda.is_current_stream_capturing():
                                 continue
-                    cur.wait_stream(s)
+                    comm.wait_stream(s)
+                self._comm = comm
             op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
-            b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
+            if comm is not None:
+                with torch.cuda.stream(comm):
+                    b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
+            else:
+                b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
             self.collectives += 1
         b.ready = True
 
@@ -283,6 +294,9 @@ class GradSync:
                 b.work = None
             if self.world > 1 and self.average and not self._avg_in_collective:
                 b.flat.mul_(1.0 / self.world)
+        comm = getattr(self, "_comm", None)
+        if comm is not None:           # the staging stream rejoins the caller's stream (a capture must end with every fork joined)
+            torch.cuda.current_stream(comm.device).wait_stream(comm)
         for b in self.buckets:
             b.pending, b.ready = len(b.params), False
             for p in b.params:       # an optimiser's zero_grad(set_to_none=True) or a grad replaced by autograd breaks the views
