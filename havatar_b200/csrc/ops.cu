@@ -562,6 +562,12 @@ __global__ void __launch_bounds__(256) render_cond_kernel(float *__restrict__ ou
 
 using namespace hav;
 
+namespace hav {   // fir_cl.cu
+cudaError_t launch_blur4_cl_tma(void *out, const void *x, const float *kernel, int batch, int in_h, int in_w, int channels, int out_h,
+                                int out_w, int pad_x0, int pad_y0, const float *noise, float noise_weight, int noise_per_sample,
+                                const float *bias, int act, cudaStream_t st);
+}
+
 extern "C" int hav_make_render_cond(float *out, const uint8_t *render, const uint8_t *normal, int n, int pixels, void *stream) {
   if (n < 0 || pixels < 1) return HAV_E_SHAPE;
   if (n == 0) return HAV_OK;
@@ -661,6 +667,16 @@ extern "C" int hav_upfirdn2d_cl(void *out, const void *x, const float *kernel, i
   if (out_h < 1 || out_w < 1) return HAV_E_SHAPE;
   if (batch == 0) return HAV_OK;
   if (out == nullptr || x == nullptr || kernel == nullptr) return HAV_E_NULL;
+  if (up == 1 && down == 1 && kh == 4 && kw == 4 && (channels & 63) == 0) {
+    // every Blur of the StyleUNet: TMA-tiled kernel (fir_cl.cu); HAV_FIR_GENERIC=1 keeps the generic kernel for A/B runs
+    static const bool generic = getenv("HAV_FIR_GENERIC") != nullptr;
+    if (!generic) {
+      cudaError_t fe = launch_blur4_cl_tma(out, x, kernel, batch, in_h, in_w, channels, out_h, out_w, pad_x0, pad_y0, noise, noise_weight,
+                                           noise_per_sample, bias, act, (cudaStream_t)stream);
+      if (fe == cudaSuccess) return HAV_OK;
+      if (fe != cudaErrorNotSupported) return (int)fe;
+    }
+  }
   UfdClParams p;
   p.B = batch, p.in_h = in_h, p.in_w = in_w, p.C = channels, p.out_h = out_h, p.out_w = out_w, p.kh = kh, p.kw = kw;
   p.up = up, p.down = down, p.pad_x0 = pad_x0, p.pad_y0 = pad_y0, p.act = act, p.noise_weight = noise_weight;

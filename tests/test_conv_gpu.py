@@ -141,3 +141,31 @@ def test_upfirdn2d_channels_last_with_fused_tail(up, down, pad):
     assert rel_err(conv.to_nchw(got), ref) < 2e-3
     got = conv.upfirdn2d_cl(xcl, k, up=up, down=down, pad=pad, noise=noise, noise_weight=0.3, bias=bias, act=True)
     assert rel_err(conv.to_nchw(got), ref_tail) < 2e-3
+
+
+@pytest.mark.parametrize("C,H,W,pad,sep", [(64, 37, 45, (1, 1), True), (128, 16, 16, (2, 2), True), (64, 33, 70, (2, 1), True),
+                                            (192, 19, 35, (1, 1), False), (64, 5, 3, (2, 2), True)])
+def test_blur_channels_last_tma_tiles(C, H, W, pad, sep):
+    """hav_upfirdn2d_cl's TMA-tiled 4x4 path (C % 64 == 0; csrc/fir_cl.cu): ragged tile edges, the zero padding supplied by the
+    tensor map's out-of-bounds fill, several channel blocks / images per CTA, rank-one and general taps, per-sample noise."""
+    from havatar_b200 import op
+
+    torch.manual_seed(11)
+    B = 3
+    x = torch.randn(B, C, H, W, device="cuda")
+    if sep:
+        k = torch.tensor([1.0, 3.0, 3.0, 1.0], device="cuda")
+        k = k[None, :] * k[:, None]
+        k = k / k.sum() * 4
+    else:
+        k = torch.randn(4, 4, device="cuda")
+    ref = op.upfirdn2d(x.half().float(), k, pad=pad)
+    noise = torch.randn(B, 1, ref.shape[2], ref.shape[3], device="cuda")
+    bias = torch.randn(C, device="cuda")
+    ref_tail = F.leaky_relu(ref + 0.3 * noise + bias.view(1, -1, 1, 1), 0.2) * math.sqrt(2)
+    xcl = x.permute(0, 2, 3, 1).contiguous().half()
+    got = conv.upfirdn2d_cl(xcl, k, pad=pad)
+    assert tuple(got.shape) == (B, ref.shape[2], ref.shape[3], C)
+    assert rel_err(conv.to_nchw(got), ref) < 2e-3
+    got = conv.upfirdn2d_cl(xcl, k, pad=pad, noise=noise, noise_weight=0.3, bias=bias, act=True)
+    assert rel_err(conv.to_nchw(got), ref_tail) < 2e-3
