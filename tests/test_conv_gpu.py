@@ -169,3 +169,38 @@ def test_blur_channels_last_tma_tiles(C, H, W, pad, sep):
     assert rel_err(conv.to_nchw(got), ref) < 2e-3
     got = conv.upfirdn2d_cl(xcl, k, pad=pad, noise=noise, noise_weight=0.3, bias=bias, act=True)
     assert rel_err(conv.to_nchw(got), ref_tail) < 2e-3
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,k,up,down", [(1, 512, 512, 16, 3, 1, 1), (2, 320, 128, 8, 3, 1, 1), (1, 512, 12, 32, 1, 1, 1),
+                                                   (1, 512, 512, 8, 3, 2, 1), (1, 1024, 512, 17, 3, 1, 2), (1, 192, 72, 12, 3, 2, 1),
+                                                   (1, 1024, 512, 16, 3, 1, 1)])
+def test_cluster_split_k_layers(B, Cin, Cout, H, k, up, down):
+    """Few output tiles x many channel blocks: the channel blocks of a tile are split over the CTAs of a cluster and the partial
+    tiles reduced through distributed shared memory (conv_tc.cu).  Uneven splits (5 blocks over 4 CTAs), the four-accumulator
+    transposed form, the subsampled stride-2 form, narrow 1x1 heads, NCHW fp32 and channels-last fp16 tensors, full fused tail."""
+    torch.manual_seed(6)
+    x = torch.randn(B, Cin, H, H, device="cuda")
+    w = torch.randn(Cout, Cin, k, k, device="cuda")
+    s = torch.rand(B, Cin, device="cuda") + 0.5
+    d = torch.rand(B, Cout, device="cuda") + 0.5
+    bias = torch.randn(Cout, device="cuda")
+    scale = 1 / math.sqrt(Cin * k * k)
+    xs = x * s.view(B, Cin, 1, 1)
+    if up == 2:
+        ref = F.conv_transpose2d(xs, (w * scale).transpose(0, 1), stride=2, padding=0)
+    elif down == 2:
+        ref = F.conv2d(xs, w * scale, stride=2, padding=0)
+    else:
+        ref = F.conv2d(xs, w * scale, padding=k // 2)
+    noise = torch.randn(B, 1, ref.shape[2], ref.shape[3], device="cuda")
+    ref = F.leaky_relu(ref * d.view(B, Cout, 1, 1) + 0.21 * noise + bias.view(1, -1, 1, 1), 0.2) * math.sqrt(2)
+    pw = conv.pack_weights(w, scale, up=up)
+    kw = dict(in_scale=s, out_scale=d, noise=noise, noise_weight=0.21, bias=bias, act=True, up=up, down=down)
+    got = conv.conv2d(x, pw, **kw)
+    assert got.shape == ref.shape and rel_err(got, ref) < 1e-2
+    if Cout % 8 == 0:
+        xcl = x.permute(0, 2, 3, 1).contiguous().half()
+        got_cl = conv.conv2d(xcl, pw, out_cl=True, **kw)
+        assert rel_err(conv.to_nchw(got_cl), ref) < 1e-2
+        # the two layouts run the same MMAs in the same order on operands that agree to fp16 rounding
+        assert rel_err(conv.conv2d(xcl, pw, out_cl=False, **kw), ref) < 1e-2
