@@ -49,6 +49,13 @@ class RenderBwdArgs(C.Structure):
     ]
 
 
+class StyleLayer(C.Structure):
+    """hav_style_layer (include/havatar_b200.h)."""
+    _fields_ = [("mod_w", C.c_void_p), ("mod_b", C.c_void_p), ("wsq", C.c_void_p), ("cin", C.c_int32), ("cout", C.c_int32),
+                ("latent_index", C.c_int32), ("s_off", C.c_int32), ("d_off", C.c_int32), ("mod_scale", C.c_float),
+                ("mod_lr_mul", C.c_float), ("conv_scale", C.c_float)]
+
+
 class ConvArgs(C.Structure):
     """hav_conv_args (include/havatar_b200.h)."""
     _fields_ = [
@@ -86,6 +93,8 @@ SIGNATURES = {
     "hav_conv_pack_weights": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, _fp]),
     "hav_modconv_demod": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _fp]),
     "hav_conv2d_forward": (C.c_int, [C.POINTER(ConvArgs), _fp]),
+    "hav_conv_tap_squares": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    "hav_style_plan_run": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, _fp]),
     "hav_conv2d_wgrad": (C.c_int, [C.POINTER(ConvWgradArgs), _fp]),
     "hav_rowscale_dot": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int64, _fp]),
     "hav_adam_flat": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _fp]),

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libhavatar_b200.so")
-SOURCES = ["render_api.cu", "render_simt.cu", "render_tc.cu", "render_tc2.cu", "render_tc3.cu", "render_bwd.cu", "ops.cu", "fir_cl.cu", "conv_tc.cu", "conv_wgrad.cu", "optim.cu"]
+SOURCES = ["render_api.cu", "render_simt.cu", "render_tc.cu", "render_tc2.cu", "render_tc3.cu", "render_bwd.cu", "ops.cu", "fir_cl.cu", "conv_tc.cu", "style.cu", "conv_wgrad.cu", "optim.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"] + os.environ.get("HAV_NVCC_DEFS", "").split()
 

@@ -17,6 +17,9 @@ import random
 import torch
 from torch import nn
 
+import ctypes as C
+
+from . import _lib
 from . import conv as hconv
 from . import styleunet_train as T
 from .op import fused_leaky_relu, upfirdn2d
@@ -238,9 +241,12 @@ class ModulatedConv2d(nn.Module):
         self.fused = fused
         self._cache = _PackCache()
 
-    def run(self, x, style, noise=None, noise_weight=0.0, bias=None, act=False, out_cl=False):
-        s = self.modulation(style).contiguous()
-        d = hconv.modconv_demod(self.weight.detach()[0], s, self.scale, self.eps) if self.demodulate else None
+    def run(self, x, style, noise=None, noise_weight=0.0, bias=None, act=False, out_cl=False, sd=None):
+        if sd is not None:          # modulation / demodulation of the whole network computed up front (_StylePlan)
+            s, d = sd
+        else:
+            s = self.modulation(style).contiguous()
+            d = hconv.modconv_demod(self.weight.detach()[0], s, self.scale, self.eps) if self.demodulate else None
         packed = self._cache.get(self.weight, self.scale, self.upsample)
         if not self.upsample:
             return hconv.conv2d(x, packed, in_scale=s, out_scale=d, noise=noise, noise_weight=noise_weight, bias=bias, act=act,
@@ -306,13 +312,13 @@ class StyledConv(nn.Module):
         self.noise = NoiseInjection()
         self.activate = _ActBias(out_channel)
 
-    def forward(self, x, style, noise=None, out_cl=False):
+    def forward(self, x, style, noise=None, out_cl=False, sd=None):
         if noise is None:     # fresh N(0,1) per call, like NoiseInjection.forward (:306-309)
             h, w = (x.shape[1], x.shape[2]) if hconv.is_cl(x) else (x.shape[2], x.shape[3])
             f = 2 if self.conv.upsample else 1
             noise = torch.empty(x.shape[0], 1, h * f, w * f, dtype=torch.float32, device=x.device).normal_()
         noise, nw = self.noise.scaled(noise)
-        return self.conv.run(x, style, noise=noise, noise_weight=nw, bias=self.activate.bias, act=True, out_cl=out_cl)
+        return self.conv.run(x, style, noise=noise, noise_weight=nw, bias=self.activate.bias, act=True, out_cl=out_cl, sd=sd)
 
 
 class ToRGB(nn.Module):
@@ -330,11 +336,98 @@ class ToRGB(nn.Module):
         self.conv = ModulatedConv2d(in_channel, self.out_channel, 1, style_dim, demodulate=False)
         self.bias = nn.Parameter(torch.zeros(1, self.out_channel, 1, 1))
 
-    def forward(self, x, style, skip=None):
-        out = self.conv.run(x, style, bias=self.bias.view(-1))
+    def forward(self, x, style, skip=None, sd=None):
+        out = self.conv.run(x, style, bias=self.bias.view(-1), sd=sd)
         if skip is not None:
             skip = self.dwt(self.upsample(self.iwt(skip))) if self.use_wt else self.upsample(skip)
             out = out + skip
+        return out
+
+
+class _StylePlan:
+    """Every modulation vector and demodulation factor of one network's inference forward in two launches
+    (hav_style_plan_run) instead of one small linear + one reduction per layer (styleUnet.py:237-258).  `entries` lists the
+    network's ModulatedConv2d modules with the latent index each one reads, in call order.  The device table holds pointers,
+    sizes and scales only; the tap-summed squared weights it points to are refreshed in place when a weight changes."""
+
+    MAX_BATCH = 8
+
+    def __init__(self, entries):
+        self.entries = entries
+        self._tables = {}        # batch -> (pointer key, device table, prefixes, offsets, pinned host copies)
+        self._wsq = {}           # entry index -> [buffer, version key]
+
+    def _wsq_of(self, i, m):
+        w = m.weight.detach()[0]
+        slot = self._wsq.get(i)
+        if slot is None or slot[0].device != w.device:
+            slot = self._wsq[i] = [torch.empty(w.shape[0], w.shape[1], dtype=torch.float32, device=w.device), None]
+        key = (w.data_ptr(), m.weight._version, _EPOCH[0])
+        if slot[1] != key:
+            # refreshed in place (the table keeps pointing at it).  A training-step capture starts with a new cache epoch, so
+            # the refresh is captured with it and replayed with the weights of each iteration
+            with torch.cuda.device(w.device):
+                st = torch.cuda.current_stream(w.device).cuda_stream
+                _lib.check(_lib.lib().hav_conv_tap_squares(C.c_void_p(slot[0].data_ptr()), C.c_void_p(w.contiguous().data_ptr()),
+                                                           int(w.shape[0]), int(w.shape[1]), int(w.shape[2]), C.c_void_p(st)),
+                           "hav_conv_tap_squares")
+            slot[1] = key
+        return slot[0]
+
+    def _table(self, B, device):
+        wsq = [self._wsq_of(i, m) if m.demodulate else None for i, (m, _) in enumerate(self.entries)]
+        key = (str(device),) + tuple((m.modulation.weight.data_ptr(), 0 if m.modulation.bias is None else m.modulation.bias.data_ptr(),
+                                      0 if q is None else q.data_ptr()) for (m, _), q in zip(self.entries, wsq))
+        hit = self._tables.get(B)
+        if hit is not None and hit[0] == key:
+            return hit
+        n = len(self.entries)
+        arr = (_lib.StyleLayer * n)()
+        s_prefix, d_prefix, s_off, d_off, offs = [0], [0], 0, 0, []
+        for i, ((m, li), q) in enumerate(zip(self.entries, wsq)):
+            lin = m.modulation
+            a = arr[i]
+            a.mod_w, a.mod_b = lin.weight.data_ptr(), (lin.bias.data_ptr() if lin.bias is not None else None)
+            a.wsq = q.data_ptr() if q is not None else None
+            a.cin, a.cout, a.latent_index, a.s_off, a.d_off = m.in_channel, m.out_channel, int(li), s_off, d_off
+            a.mod_scale, a.mod_lr_mul, a.conv_scale = lin.scale, lin.lr_mul, m.scale
+            offs.append((s_off, d_off if q is not None else None))
+            s_off += B * m.in_channel
+            s_prefix.append(s_prefix[-1] + m.in_channel)
+            if q is not None:
+                d_off += B * m.out_channel
+                d_prefix.append(d_prefix[-1] + m.out_channel)
+            else:
+                d_prefix.append(d_prefix[-1])
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().pin_memory()
+        pref = torch.tensor([s_prefix, d_prefix], dtype=torch.int32).pin_memory()
+        table = torch.empty(host.numel(), dtype=torch.uint8, device=device)
+        pref_dev = torch.empty((2, n + 1), dtype=torch.int32, device=device)
+        table.copy_(host, non_blocking=True)          # pinned sources: legal inside a CUDA-graph capture too
+        pref_dev.copy_(pref, non_blocking=True)
+        hit = self._tables[B] = (key, table, pref_dev, offs, (s_off, d_off, s_prefix[-1], d_prefix[-1]), (host, pref))
+        return hit
+
+    def run(self, latent):
+        """latent [B, n_latent, D] -> [(s [B,Cin], d [B,Cout] or None)] per entry, or None when the batched path does not apply."""
+        B = int(latent.shape[0])
+        if not latent.is_cuda or B > self.MAX_BATCH or any(m.modulation.activation for m, _ in self.entries):
+            return None
+        lat = latent.detach().float().contiguous()
+        _, table, pref, offs, (s_tot, d_tot, s_rows, d_rows), _ = self._table(B, lat.device)
+        s_all = torch.empty(s_tot, dtype=torch.float32, device=lat.device)
+        d_all = torch.empty(max(d_tot, 1), dtype=torch.float32, device=lat.device)
+        with torch.cuda.device(lat.device):
+            st = torch.cuda.current_stream(lat.device).cuda_stream
+            _lib.check(_lib.lib().hav_style_plan_run(C.c_void_p(s_all.data_ptr()), C.c_void_p(d_all.data_ptr()), C.c_void_p(lat.data_ptr()), B,
+                                                     int(lat.shape[1]), int(lat.shape[2]), C.c_void_p(table.data_ptr()),
+                                                     C.c_void_p(pref[0].data_ptr()), C.c_void_p(pref[1].data_ptr()), len(self.entries),
+                                                     s_rows, d_rows, 1e-8, C.c_void_p(st)), "hav_style_plan_run")
+        out = []
+        for (m, _), (so, do) in zip(self.entries, offs):
+            s = s_all[so:so + B * m.in_channel].view(B, m.in_channel)
+            d = None if do is None else d_all[do:do + B * m.out_channel].view(B, m.out_channel)
+            out.append((s, d))
         return out
 
 
@@ -501,6 +594,12 @@ class SWGAN_unet(nn.Module):
         latent = _latents(styles, self.n_latent, inject_index)
         if ag:
             return T.swgan_unet_forward(self, latent, condition_img, noise)
+        if getattr(self, "_style_plan", None) is None:       # (module, latent index) in call order
+            ent = []
+            for k, (c1, c2, tr) in enumerate(zip(self.convs[::2], self.convs[1::2], self.to_rgbs)):
+                ent += [(c1.conv, 2 * k), (c2.conv, 2 * k + 1), (tr.conv, 2 * k + 2)]
+            self._style_plan = _StylePlan(ent)
+        sd = self._style_plan.run(latent)          # every modulation / demodulation of the network: two launches
         feats = _CondEncoder.run(self, condition_img)
         i, skip, out = 0, None, None
         fork = _SkipFork(condition_img.device)
@@ -509,10 +608,11 @@ class SWGAN_unet(nn.Module):
                 out = self.comb_convs[-1](feats[-1], out_cl=True)
             elif i < 2 * len(self.comb_convs):
                 out = self.comb_convs[-1 - (i // 2)](torch.cat([out, feats[-1 - (i // 2)]], dim=-1), out_cl=True)
-            out = conv1(out, latent[:, i], noise=n1, out_cl=True)
-            out = conv2(out, latent[:, i + 1], noise=n2, out_cl=True)
+            k3 = 3 * (i // 2)
+            out = conv1(out, latent[:, i], noise=n1, out_cl=True, sd=None if sd is None else sd[k3])
+            out = conv2(out, latent[:, i + 1], noise=n2, out_cl=True, sd=None if sd is None else sd[k3 + 1])
             with fork.branch(out):
-                skip = to_rgb(out, latent[:, i + 2], skip)      # 12-channel wavelet skip stays NCHW fp32
+                skip = to_rgb(out, latent[:, i + 2], skip, sd=None if sd is None else sd[k3 + 2])      # 12-channel wavelet skip stays NCHW fp32
             i += 2
         return self.iwt(fork.join(skip))
 
@@ -650,14 +750,17 @@ class StyleGAN_zxc(nn.Module):
         if ag:
             image = T.stylegan_zxc_forward(self, latent, cond_feats, noise)
             return (image, latent) if return_latents else (image, None)
+        if getattr(self, "_style_plan", None) is None:       # (module, latent index) in call order
+            self._style_plan = _StylePlan([(self.conv1.conv, 0)] + [(c.conv, k + 1) for k, c in enumerate(self.convs)])
+        sd = self._style_plan.run(latent)          # every modulation / demodulation of the network: two launches
         feats = _CondEncoder.run(self, cond_feats)
-        out = self.conv1(self.input(latent), latent[:, 0], noise=noise[0], out_cl=True)
+        out = self.conv1(self.input(latent), latent[:, 0], noise=noise[0], out_cl=True, sd=None if sd is None else sd[0])
         i = 1
         for conv1, conv2, n1, n2 in zip(self.convs[::2], self.convs[1::2], noise[1::2], noise[2::2]):
             if 1 < i <= 2 * len(feats) + 1:
                 out = self.comb_convs[-(i // 2)](torch.cat([out, feats[-(i // 2)]], dim=-1), out_cl=True)
-            out = conv1(out, latent[:, i], noise=n1, out_cl=True)
-            out = conv2(out, latent[:, i + 1], noise=n2, out_cl=True)
+            out = conv1(out, latent[:, i], noise=n1, out_cl=True, sd=None if sd is None else sd[i])
+            out = conv2(out, latent[:, i + 1], noise=n2, out_cl=True, sd=None if sd is None else sd[i + 1])
             i += 2
         image = self.conv_out(out)                               # back to the reference layout (NCHW fp32)
         return (image, latent) if return_latents else (image, None)

@@ -264,6 +264,26 @@ int hav_modconv_demod(float *demod, const float *w, const float *style, int batc
                       float eps, void *stream);
 int hav_conv2d_forward(const hav_conv_args *args, void *stream);
 
+/* Modulation vectors and demodulation factors of every modulated convolution of one network in two launches (the per-layer
+ * form above costs one small linear + one reduction per layer on the critical path of a frame; model/styleUnet.py:237-258).
+ * `layers` is a DEVICE array of n_layers descriptors; layer l computes
+ *   s[b,ci]   = (sum_d mod_w[ci,d] * latent[b, latent_index, d]) * mod_scale + mod_b[ci] * mod_lr_mul      (EqualLinear, :126-162)
+ *   d[b,co]   = rsqrt(conv_scale^2 * sum_ci s[b,ci]^2 * wsq[co,ci] + eps)    when wsq != NULL            (demodulate=True)
+ * into s_all + s_off ([batch,cin] block) and d_all + d_off ([batch,cout] block).  wsq[co,ci] = sum over taps of W^2
+ * (hav_conv_tap_squares; input independent, cache it per weight version).  s_prefix / d_prefix: DEVICE int arrays of
+ * n_layers + 1 running sums of cin / of cout-or-0 (layers without demodulation contribute 0 rows).  batch <= 8. */
+typedef struct hav_style_layer {
+  const float *mod_w;  /* [cin, style_dim] EqualLinear weight (unscaled parameter) */
+  const float *mod_b;  /* [cin] EqualLinear bias or NULL */
+  const float *wsq;    /* [cout, cin] tap-summed squares of the convolution weight, or NULL (no demodulation) */
+  int32_t cin, cout, latent_index, s_off, d_off;
+  float mod_scale, mod_lr_mul, conv_scale;
+} hav_style_layer;
+int hav_conv_tap_squares(float *wsq, const float *w, int cout, int cin, int ksize, void *stream);
+int hav_style_plan_run(float *s_all, float *d_all, const float *latent, int batch, int n_latent, int style_dim,
+                       const hav_style_layer *layers, const int *s_prefix, const int *d_prefix, int n_layers, int s_rows, int d_rows,
+                       float eps, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Backward of hav_conv2d_forward (replaces cuDNN's convolution_backward under model/op/conv2d_gradfix.py:94-227 for the
  * training steps train_avatar.py:149 / train_avatarHD.py:229,276).  For  y = out_scale * conv(in_scale * x, wscale * w):

@@ -66,3 +66,51 @@ def test_forward_matches_reference_golden(golden_dir, name, mode):
     # fp16 operands, fp32 accumulation, ~20 convolutions deep: 2e-2 of the output range (stated tolerance)
     err = np.abs(out - ref).max() / np.abs(ref).max()
     assert err < 2e-2, float(err)
+
+
+@pytest.mark.gpu
+def test_style_plan_matches_per_layer_modulation():
+    """_StylePlan (hav_style_plan_run: all modulation vectors and demodulation factors of a network in two launches) against
+    the per-layer EqualLinear + hav_modconv_demod path it replaces, for mixed latents, and the networks' outputs with and
+    without it."""
+    from havatar_b200 import conv as hconv
+    from havatar_b200 import styleunet as su
+
+    torch.manual_seed(3)
+    net = su.SWGAN_unet(inp_size=32, inp_ch=16, out_ch=3, out_size=128, style_dim=64, n_mlp=2, middle_size=8).cuda().eval()
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, su.EqualLinear) and m.bias is not None:
+                m.bias.add_(torch.randn_like(m.bias) * 0.1)
+        B = 2
+        latent = torch.randn(B, net.n_latent, 64, device="cuda")
+        ent = []
+        for k, (c1, c2, tr) in enumerate(zip(net.convs[::2], net.convs[1::2], net.to_rgbs)):
+            ent += [(c1.conv, 2 * k), (c2.conv, 2 * k + 1), (tr.conv, 2 * k + 2)]
+        plan = su._StylePlan(ent)
+        got = plan.run(latent)
+        assert got is not None and len(got) == len(ent)
+        for (m, li), (s, d) in zip(ent, got):
+            s_ref = m.modulation(latent[:, li]).contiguous()
+            assert torch.allclose(s, s_ref, rtol=1e-5, atol=1e-6)
+            if m.demodulate:
+                d_ref = hconv.modconv_demod(m.weight.detach()[0], s_ref, m.scale, m.eps)
+                assert torch.allclose(d, d_ref, rtol=1e-5, atol=1e-7)
+            else:
+                assert d is None
+        # a weight modified in place is picked up (tap-summed squares refreshed in place, same table)
+        ent[0][0].weight.mul_(1.5)
+        d2 = plan.run(latent)[0][1]
+        assert torch.allclose(d2, hconv.modconv_demod(ent[0][0].weight.detach()[0], got[0][0], ent[0][0].scale, 1e-8), rtol=1e-5, atol=1e-7)
+        # whole network: batched plan vs the per-layer path
+        cond = torch.randn(B, 16, 32, 32, device="cuda")
+        style = torch.randn(B, 64, device="cuda")
+        noise = net.make_noise("cuda")
+        with_plan = net([style], cond, noise=noise)
+        old = su._StylePlan.run
+        su._StylePlan.run = lambda self, latent: None
+        try:
+            without = net([style], cond, noise=noise)
+        finally:
+            su._StylePlan.run = old
+        assert float((with_plan - without).abs().max()) <= 2e-3 * float(without.abs().max())
