@@ -36,7 +36,7 @@ class stream_namespace:
 
 def aux_stream(device, slot):
     """A persistent side stream of `device` (slot 0 = YZ plane generator, 1 = skinning-weight volume decoder, 2 = second
-    discriminator pass, 3 = ToRGB pyramid, 4 = the G-step forward of the overlapped stage-two iteration)."""
+    discriminator pass, 3 = ToRGB pyramid, 4 = the G-step forward of the overlapped stage-two iteration, 5 = style plans)."""
     key = (device.index, slot + 16 * _NAMESPACE[0])
     st = _SIDE.get(key)
     if st is None:

@@ -431,6 +431,31 @@ class _StylePlan:
         return out
 
 
+def _plan_beside(plan, latent, fn):
+    """(plan.run(latent), fn()): the style plan's two launches run on a side stream beside fn (the condition encoder, which
+    reads no style), and are joined before the first modulated convolution."""
+    if not latent.is_cuda:
+        return plan.run(latent), fn()
+    from . import pipeline
+
+    dev = latent.device
+    main, side = torch.cuda.current_stream(dev), pipeline.aux_stream(dev, 5)
+    pipeline.note_fork(dev, main, side)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        sd = plan.run(latent)
+    out = fn()
+    main.wait_stream(side)
+    if sd is not None:
+        seen = set()                     # all views share two buffers
+        for pair in sd:
+            for t_ in pair:
+                if t_ is not None and t_.untyped_storage().data_ptr() not in seen:
+                    seen.add(t_.untyped_storage().data_ptr())
+                    t_.record_stream(main)
+    return sd, out
+
+
 class ConvBlock(nn.Module):
     def __init__(self, in_channel, out_channel, blur_kernel=(1, 3, 3, 1), downsample=True):
         super().__init__()
@@ -599,8 +624,8 @@ class SWGAN_unet(nn.Module):
             for k, (c1, c2, tr) in enumerate(zip(self.convs[::2], self.convs[1::2], self.to_rgbs)):
                 ent += [(c1.conv, 2 * k), (c2.conv, 2 * k + 1), (tr.conv, 2 * k + 2)]
             self._style_plan = _StylePlan(ent)
-        sd = self._style_plan.run(latent)          # every modulation / demodulation of the network: two launches
-        feats = _CondEncoder.run(self, condition_img)
+        # every modulation / demodulation of the network: two launches, beside the condition encoder
+        sd, feats = _plan_beside(self._style_plan, latent, lambda: _CondEncoder.run(self, condition_img))
         i, skip, out = 0, None, None
         fork = _SkipFork(condition_img.device)
         for conv1, conv2, n1, n2, to_rgb in zip(self.convs[::2], self.convs[1::2], noise[::2], noise[1::2], self.to_rgbs):
@@ -752,8 +777,7 @@ class StyleGAN_zxc(nn.Module):
             return (image, latent) if return_latents else (image, None)
         if getattr(self, "_style_plan", None) is None:       # (module, latent index) in call order
             self._style_plan = _StylePlan([(self.conv1.conv, 0)] + [(c.conv, k + 1) for k, c in enumerate(self.convs)])
-        sd = self._style_plan.run(latent)          # every modulation / demodulation of the network: two launches
-        feats = _CondEncoder.run(self, cond_feats)
+        sd, feats = _plan_beside(self._style_plan, latent, lambda: _CondEncoder.run(self, cond_feats))
         out = self.conv1(self.input(latent), latent[:, 0], noise=noise[0], out_cl=True, sd=None if sd is None else sd[0])
         i = 1
         for conv1, conv2, n1, n2 in zip(self.convs[::2], self.convs[1::2], noise[1::2], noise[2::2]):
