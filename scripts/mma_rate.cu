@@ -92,6 +92,30 @@ __global__ void __launch_bounds__(32 + 256, 1) mma_rate_kernel(int mode, int N, 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
+// Second measurement: what one SM can pull from L2 with cp.async.bulk when every SM streams the same weight-like buffer (each
+// CTA walks `n` slices of `bytes` through a ring of `stages` slots; no MMAs).  This is the supply side of conv_tc's weight ring.
+__global__ void __launch_bounds__(32, 1) bulk_rate_kernel(const uint8_t *src, int src_slices, int bytes, int n, int stages, unsigned long long *out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sb = smem_u32(smem), bar = sb + 160 * 1024;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) mbar_init(bar + i * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const long long t0 = clock64();
+    int first = (blockIdx.x * 7) % src_slices;
+    for (int i = 0; i < n + stages; ++i) {
+      const int slot = i % stages;
+      if (i >= stages) mbar_wait_spin(bar + slot * 8, ((i - stages) / stages) & 1);     // slice i - stages has landed
+      if (i < n) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar + slot * 8), "r"((uint32_t)bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb + slot * bytes),
+                     "l"(src + (size_t)((first + i) % src_slices) * bytes), "r"((uint32_t)bytes), "r"(bar + slot * 8) : "memory");
+      }
+    }
+    const long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = (unsigned long long)(t1 - t0);
+  }
+}
+
 int main() {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -135,6 +159,26 @@ int main() {
              c.mode == 0 ? "smem" : c.mode == 1 ? "TMEM" : c.mode == 2 ? "sm128" : "TM128", c.N, tr, best_clk, 100.0 * ideal / best_clk, traffic,
              (double)sms * iters * 128.0 * c.N * 16 * 2 / (best_ms * 1e-3) / 1e12);
     }
+  }
+  {
+    const int bytes = 16384, src_slices = 288;       // 4.7 MB: one 512 x 512 x 3 x 3 fp16 weight tensor, L2 resident
+    uint8_t *src;
+    cudaMalloc(&src, (size_t)bytes * src_slices);
+    cudaMemset(src, 0, (size_t)bytes * src_slices);
+    cudaFuncSetAttribute(bulk_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 256);
+    printf("cp.async.bulk L2 -> shared memory, every SM streaming the same 4.7 MB buffer in 16 KB slices\n%8s %8s %12s %12s\n", "CTAs", "in flight", "B/clk/SM", "chip TB/s");
+    for (int ctas : {sms, 128, 64, 16})
+      for (int stages : {2, 4, 8}) {
+        unsigned long long h[4];
+        const int n = 2048;
+        for (int rep = 0; rep < 2; ++rep) {
+          bulk_rate_kernel<<<ctas, 32, 160 * 1024 + 256>>>(src, src_slices, bytes, n, stages, out);
+          if (cudaDeviceSynchronize() != cudaSuccess) { printf("bulk kernel failed\n"); return 1; }
+        }
+        cudaMemcpy(h, out, 32, cudaMemcpyDeviceToHost);
+        const double bpc = (double)n * bytes / (double)h[0];
+        printf("%8d %8d %12.1f %12.2f\n", ctas, stages, bpc, bpc * ctas * khz * 1e3 / 1e12);
+      }
   }
   return 0;
 }
