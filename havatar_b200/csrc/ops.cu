@@ -61,6 +61,50 @@ __global__ void __launch_bounds__(256) bias_act_scalar_kernel(float *__restrict_
   }
 }
 
+// FusedLeakyReLUFunctionBackward in one pass (model/op/fused_act.py:23-47: the gated gradient, then grad_input.sum over every
+// dim but the channel): grad_input = (ref > 0 ? g : g * alpha) * scale and, per (split, channel), the partial sum of grad_input
+// over the split's share of the channel's B x inner elements.  The caller adds the `splits` partials (a [splits,C] tensor):
+// fixed summation order, no atomics, and the second full read of grad_input by a separate reduction disappears.
+template <bool kVec>
+__global__ void __launch_bounds__(256) bias_act_backward_kernel(float *__restrict__ gin, float *__restrict__ partials,
+                                                                const float *__restrict__ g, const float *__restrict__ ref, int B, int C,
+                                                                long inner, long per, float alpha, float scale) {
+  const int c = blockIdx.y, s = blockIdx.x;
+  const long total = (long)B * inner, lo = (long)s * per, hi = lo + per < total ? lo + per : total;
+  float acc = 0.0f;
+  for (int b = (int)(lo / inner); b < B && (long)b * inner < hi; ++b) {
+    const long seg0 = (long)b * inner, i0 = (lo > seg0 ? lo : seg0) - seg0, i1 = (hi < seg0 + inner ? hi : seg0 + inner) - seg0;
+    const size_t base = ((size_t)b * C + c) * inner;
+    if (kVec) {     // inner % 4 == 0 and per % 4 == 0: aligned float4 runs that never straddle a plane
+      const float4 *g4 = reinterpret_cast<const float4 *>(g + base), *r4 = reinterpret_cast<const float4 *>(ref + base);
+      float4 *o4 = reinterpret_cast<float4 *>(gin + base);
+      for (long i = i0 / 4 + threadIdx.x; i < i1 / 4; i += blockDim.x) {
+        const float4 gv = __ldcs(g4 + i), rv = __ldcs(r4 + i);
+        float4 y;
+        y.x = (rv.x > 0.0f ? gv.x : gv.x * alpha) * scale, y.y = (rv.y > 0.0f ? gv.y : gv.y * alpha) * scale;
+        y.z = (rv.z > 0.0f ? gv.z : gv.z * alpha) * scale, y.w = (rv.w > 0.0f ? gv.w : gv.w * alpha) * scale;
+        o4[i] = y;
+        acc += (y.x + y.y) + (y.z + y.w);
+      }
+    } else {
+      for (long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const float gv = g[base + i], y = (ref[base + i] > 0.0f ? gv : gv * alpha) * scale;
+        gin[base + i] = y;
+        acc += y;
+      }
+    }
+  }
+  __shared__ float red[8];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partials[(size_t)s * C + c] = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // upfirdn2d  (model/op/upfirdn2d_kernel.cu:49-207; executable spec model/op/upfirdn2d.py:172-213)
 //   out[oy,ox] = sum_{ky,kx} U[oy*dy + ky - py0, ox*dx + kx - px0] * K[kh-1-ky, kw-1-kx]
@@ -604,6 +648,32 @@ extern "C" int hav_fused_bias_act(float *out, const float *x, const float *bias,
     bias_act_scalar_kernel<<<grid, 256, 0, st>>>(out, x, bias, ref, numel, bias != nullptr ? step_b : 1,
                                                  bias != nullptr ? size_b : 1, mode, alpha, scale);
   }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? HAV_OK : (int)e;
+}
+
+extern "C" int hav_bias_act_backward_splits(int batch, int channels, int64_t inner) {
+  if (batch < 1 || channels < 1 || inner < 1) return 0;
+  const int64_t total = (int64_t)batch * inner;
+  int64_t splits = (2 * kSMs + channels - 1) / channels;        // about two CTAs per SM over all channels ...
+  const int64_t cap = (total + 2047) / 2048;                    // ... of at least 2048 elements each
+  if (splits > cap) splits = cap;
+  if (splits > 64) splits = 64;
+  return splits < 1 ? 1 : (int)splits;
+}
+
+extern "C" int hav_bias_act_backward(float *grad_input, float *partials, const float *grad_out, const float *ref, int batch, int channels,
+                                     int64_t inner, int splits, float alpha, float scale, void *stream) {
+  if (batch < 0 || channels < 1 || inner < 1 || splits < 1 || splits > 64 || channels > 65535) return HAV_E_SHAPE;
+  if (batch == 0) return HAV_OK;
+  if (grad_input == nullptr || partials == nullptr || grad_out == nullptr || ref == nullptr) return HAV_E_NULL;
+  const int64_t total = (int64_t)batch * inner;
+  int64_t per = (total + splits - 1) / splits;
+  per = (per + 3) / 4 * 4;
+  const bool vec = (inner % 4 == 0) && (((uintptr_t)grad_input | (uintptr_t)grad_out | (uintptr_t)ref) & 15) == 0;
+  dim3 grid(splits, channels);
+  if (vec) bias_act_backward_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(grad_input, partials, grad_out, ref, batch, channels, inner, per, alpha, scale);
+  else bias_act_backward_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(grad_input, partials, grad_out, ref, batch, channels, inner, per, alpha, scale);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? HAV_OK : (int)e;
 }

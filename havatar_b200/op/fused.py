@@ -38,3 +38,28 @@ def fused_bias_act(input, bias, refer, act, grad, alpha, scale):
             b.numel() if b is not None else 1, int(act), int(grad), float(alpha), float(scale), C.c_void_p(stream))
     _lib.check(rc, "hav_fused_bias_act")
     return out
+
+
+def fused_bias_act_backward(grad_output, out, alpha, scale):
+    """(grad_input, grad_bias) of FusedLeakyReLU in one pass (hav_bias_act_backward): the gated gradient of
+    fused_bias_act(..., act=3, grad=1) and its sum over every dim but the channel (reference model/op/fused_act.py:31-45, which
+    runs the kernel and then a separate full-tensor reduction)."""
+    g, ref = grad_output.contiguous(), out.contiguous()
+    if not g.is_cuda or g.dtype != torch.float32 or ref.dtype != torch.float32 or ref.shape != g.shape or g.dim() < 2:
+        raise RuntimeError("fused_bias_act_backward needs float32 CUDA tensors of one shape [B, C, ...]")
+    B, Cc = int(g.shape[0]), int(g.shape[1])
+    inner = 1
+    for i in range(2, g.dim()):
+        inner *= int(g.size(i))
+    L = _lib.lib()
+    grad_input = torch.empty_like(g)
+    if g.numel() == 0:
+        return grad_input, g.new_zeros(Cc)
+    splits = int(L.hav_bias_act_backward_splits(B, Cc, inner))
+    partials = torch.empty((splits, Cc), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        stream = torch.cuda.current_stream(g.device).cuda_stream
+        _lib.check(L.hav_bias_act_backward(C.c_void_p(grad_input.data_ptr()), C.c_void_p(partials.data_ptr()), C.c_void_p(g.data_ptr()),
+                                           C.c_void_p(ref.data_ptr()), B, Cc, inner, splits, float(alpha), float(scale), C.c_void_p(stream)),
+                   "hav_bias_act_backward")
+    return grad_input, (partials[0] if splits == 1 else partials.sum(0))

@@ -19,13 +19,11 @@ class _LReLUBackward(Function):
         ctx.save_for_backward(out)
         ctx.negative_slope, ctx.scale = negative_slope, scale
         empty = grad_output.new_empty(0)
+        if has_bias and grad_output.dim() >= 2:      # gradient and its per-channel sum in one pass over the tensor
+            grad_input, grad_bias = fused.fused_bias_act_backward(grad_output, out, negative_slope, scale)
+            return grad_input, grad_bias.detach()
         grad_input = fused.fused_bias_act(grad_output.contiguous(), empty, out, 3, 1, negative_slope, scale)
-        if has_bias:
-            dims = [0] + list(range(2, grad_input.ndim))
-            grad_bias = grad_input.sum(dims).detach()
-        else:
-            grad_bias = empty
-        return grad_input, grad_bias
+        return grad_input, empty
 
     @staticmethod
     def backward(ctx, gg_input, gg_bias):

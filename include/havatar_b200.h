@@ -92,6 +92,14 @@ int hav_upfirdn2d(float *out, const float *x, const float *kernel, int major, in
                   int minor, int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0,
                   int pad_x1, int pad_y0, int pad_y1, void *stream);
 
+/* FusedLeakyReLUFunctionBackward in one pass (model/op/fused_act.py:23-47): for x [batch, channels, inner]
+ *   grad_input = (ref > 0 ? grad_out : grad_out * alpha) * scale        (== hav_fused_bias_act act 3, grad 1)
+ *   partials[s, c] = sum of grad_input over split s of channel c's batch * inner elements;   grad_bias[c] = sum_s partials[s, c]
+ * (fixed summation order; replaces the separate full-tensor reduction).  splits = hav_bias_act_backward_splits(...) <= 64. */
+int hav_bias_act_backward_splits(int batch, int channels, int64_t inner);
+int hav_bias_act_backward(float *grad_input, float *partials, const float *grad_out, const float *ref, int batch, int channels,
+                          int64_t inner, int splits, float alpha, float scale, void *stream);
+
 /* upfirdn2d on channels-last fp16 tensors (HAV_LAYOUT_NHWC_F16: x [B,H,W,C] -> out [B,Ho,Wo,C], C % 8 == 0), square up / down
  * factors, with the tail of StyledConv fused in (model/styleUnet.py:593-599 after the blur of :264-277):
  *   out = act( fir(x) + noise_weight * noise + bias[c] ),  act 0: none, 1: leaky-relu(0.2) * sqrt(2); noise / bias may be NULL. */

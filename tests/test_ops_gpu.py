@@ -81,6 +81,28 @@ def test_fused_leaky_relu_first_and_second_order_grads():
     assert torch.allclose(h, hr, atol=1e-5)
 
 
+@pytest.mark.parametrize("shape", [(2, 6, 5, 5), (4, 512, 16, 16), (1, 64, 257, 257), (3, 33, 7), (5, 512), (2, 128, 64, 64), (1, 12, 1, 1)])
+def test_fused_leaky_relu_backward_one_pass(shape):
+    """hav_bias_act_backward (gradient + per-channel partial sums in one pass) against torch autograd: vector and scalar paths,
+    splits over batch boundaries, 2-D inputs (the style MLP), bit-identical grad_input vs the two-launch form."""
+    from havatar_b200.op import fused
+
+    torch.manual_seed(1)
+    x = torch.randn(*shape, device="cuda", requires_grad=True)
+    b = torch.randn(shape[1], device="cuda", requires_grad=True)
+    y = op.fused_leaky_relu(x, b)
+    bshape = [1, -1] + [1] * (len(shape) - 2)
+    yr = torch.nn.functional.leaky_relu(x + b.view(*bshape), 0.2) * 2 ** 0.5
+    go = torch.randn_like(y)
+    gx, gb = torch.autograd.grad(y, (x, b), go)
+    gxr, gbr = torch.autograd.grad(yr, (x, b), go)
+    assert torch.allclose(gx, gxr, atol=1e-6)
+    n = x.numel() // shape[1]
+    assert torch.allclose(gb, gbr, atol=2e-6 * max(1.0, n ** 0.5), rtol=1e-5)
+    two_launch = fused.fused_bias_act(go.contiguous(), go.new_empty(0), y.detach(), 3, 1, 0.2, 2 ** 0.5)
+    assert torch.equal(gx, two_launch)
+
+
 def test_upfirdn2d_first_and_second_order_grads():
     torch.manual_seed(0)
     k = _t(ufd_kernel(np, [1, 3, 3, 1], 1.0))
