@@ -93,6 +93,8 @@ SIGNATURES = {
     "hav_conv_pack_weights": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, _fp]),
     "hav_bias_act_backward_splits": (C.c_int, [C.c_int, C.c_int, C.c_int64]),
     "hav_bias_act_backward": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_float, _fp]),
+    "hav_noise_bias_act": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_float, _fp]),
+    "hav_noise_bias_act_backward": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float, _fp]),
     "hav_modconv_demod": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _fp]),
     "hav_conv2d_forward": (C.c_int, [C.POINTER(ConvArgs), _fp]),
     "hav_conv_tap_squares": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),

@@ -61,17 +61,51 @@ __global__ void __launch_bounds__(256) bias_act_scalar_kernel(float *__restrict_
   }
 }
 
+// StyledConv's tail in one pass (model/styleUnet.py:596-598: NoiseInjection `image + weight * noise`, :300-310, then
+// FusedLeakyReLU): y = lrelu(x + nw * noise[b or 0, pixel] + bias[c]) * scale for x [B,C,inner]; nw is read from device memory
+// (it is a parameter).  One thread per 4 consecutive pixels of one (b, c) plane when inner % 4 == 0.
+template <bool kVec>
+__global__ void __launch_bounds__(256) noise_bias_act_kernel(float *__restrict__ out, const float *__restrict__ x, const float *__restrict__ bias,
+                                                             const float *__restrict__ noise, const float *__restrict__ nw_ptr, long n_units,
+                                                             long inner, int C, long noise_bstride, float alpha, float scale) {
+  const float nw = __ldg(nw_ptr);
+  constexpr int V = kVec ? 4 : 1;
+  const long units_per_plane = inner / V;
+  for (long u = (long)blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += (long)gridDim.x * blockDim.x) {
+    const long plane = u / units_per_plane, i = (u - plane * units_per_plane) * V;
+    const int c = (int)(plane % C);
+    const long b = plane / C;
+    const float bv = bias != nullptr ? __ldg(bias + c) : 0.0f;
+    if (kVec) {
+      const float4 xv = __ldcs(reinterpret_cast<const float4 *>(x + plane * inner + i));
+      const float4 nv = __ldg(reinterpret_cast<const float4 *>(noise + b * noise_bstride + i));
+      float4 y;
+      y.x = xv.x + nw * nv.x + bv, y.y = xv.y + nw * nv.y + bv, y.z = xv.z + nw * nv.z + bv, y.w = xv.w + nw * nv.w + bv;
+      y.x = (y.x > 0.0f ? y.x : y.x * alpha) * scale, y.y = (y.y > 0.0f ? y.y : y.y * alpha) * scale;
+      y.z = (y.z > 0.0f ? y.z : y.z * alpha) * scale, y.w = (y.w > 0.0f ? y.w : y.w * alpha) * scale;
+      *reinterpret_cast<float4 *>(out + plane * inner + i) = y;
+    } else {
+      float y = x[plane * inner + i] + nw * __ldg(noise + b * noise_bstride + i) + bv;
+      out[plane * inner + i] = (y > 0.0f ? y : y * alpha) * scale;
+    }
+  }
+}
+
 // FusedLeakyReLUFunctionBackward in one pass (model/op/fused_act.py:23-47: the gated gradient, then grad_input.sum over every
 // dim but the channel): grad_input = (ref > 0 ? g : g * alpha) * scale and, per (split, channel), the partial sum of grad_input
 // over the split's share of the channel's B x inner elements.  The caller adds the `splits` partials (a [splits,C] tensor):
 // fixed summation order, no atomics, and the second full read of grad_input by a separate reduction disappears.
+// With noise != nullptr a second table npart[s, c] collects sum(grad_input * noise): the gradient of NoiseInjection's weight is
+// its sum over (s, c)  (d/dw of x + w * noise, the reference gets it from two more full-tensor reductions).
 template <bool kVec>
 __global__ void __launch_bounds__(256) bias_act_backward_kernel(float *__restrict__ gin, float *__restrict__ partials,
                                                                 const float *__restrict__ g, const float *__restrict__ ref, int B, int C,
-                                                                long inner, long per, float alpha, float scale) {
+                                                                long inner, long per, float alpha, float scale,
+                                                                const float *__restrict__ noise = nullptr, long noise_bstride = 0,
+                                                                float *__restrict__ npart = nullptr) {
   const int c = blockIdx.y, s = blockIdx.x;
   const long total = (long)B * inner, lo = (long)s * per, hi = lo + per < total ? lo + per : total;
-  float acc = 0.0f;
+  float acc = 0.0f, nacc = 0.0f;
   for (int b = (int)(lo / inner); b < B && (long)b * inner < hi; ++b) {
     const long seg0 = (long)b * inner, i0 = (lo > seg0 ? lo : seg0) - seg0, i1 = (hi < seg0 + inner ? hi : seg0 + inner) - seg0;
     const size_t base = ((size_t)b * C + c) * inner;
@@ -85,23 +119,29 @@ __global__ void __launch_bounds__(256) bias_act_backward_kernel(float *__restric
         y.z = (rv.z > 0.0f ? gv.z : gv.z * alpha) * scale, y.w = (rv.w > 0.0f ? gv.w : gv.w * alpha) * scale;
         o4[i] = y;
         acc += (y.x + y.y) + (y.z + y.w);
+        if (noise != nullptr) {
+          const float4 nv = __ldg(reinterpret_cast<const float4 *>(noise + b * noise_bstride) + i);
+          nacc += (y.x * nv.x + y.y * nv.y) + (y.z * nv.z + y.w * nv.w);
+        }
       }
     } else {
       for (long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
         const float gv = g[base + i], y = (ref[base + i] > 0.0f ? gv : gv * alpha) * scale;
         gin[base + i] = y;
         acc += y;
+        if (noise != nullptr) nacc += y * __ldg(noise + b * noise_bstride + i);
       }
     }
   }
-  __shared__ float red[8];
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __shared__ float red[16];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o), nacc += __shfl_xor_sync(0xffffffffu, nacc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc, red[8 + (threadIdx.x >> 5)] = nacc;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float t = 0.0f;
-    for (int w = 0; w < 8; ++w) t += red[w];
+    float t = 0.0f, tn = 0.0f;
+    for (int w = 0; w < 8; ++w) t += red[w], tn += red[8 + w];
     partials[(size_t)s * C + c] = t;
+    if (npart != nullptr) npart[(size_t)s * C + c] = tn;
   }
 }
 
@@ -674,6 +714,41 @@ extern "C" int hav_bias_act_backward(float *grad_input, float *partials, const f
   dim3 grid(splits, channels);
   if (vec) bias_act_backward_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(grad_input, partials, grad_out, ref, batch, channels, inner, per, alpha, scale);
   else bias_act_backward_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(grad_input, partials, grad_out, ref, batch, channels, inner, per, alpha, scale);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? HAV_OK : (int)e;
+}
+
+extern "C" int hav_noise_bias_act(float *out, const float *x, const float *bias, const float *noise, const float *noise_weight, int batch,
+                                  int channels, int64_t inner, int noise_per_sample, float alpha, float scale, void *stream) {
+  if (batch < 0 || channels < 1 || inner < 1) return HAV_E_SHAPE;
+  if (batch == 0) return HAV_OK;
+  if (out == nullptr || x == nullptr || noise == nullptr || noise_weight == nullptr) return HAV_E_NULL;
+  const bool vec = (inner % 4 == 0) && (((uintptr_t)out | (uintptr_t)x | (uintptr_t)noise) & 15) == 0;
+  const long n_units = (long)batch * channels * (inner / (vec ? 4 : 1));
+  const long want = (n_units + 255) / 256;
+  const int grid = (int)(want < (long)kSMs * 16 ? want : (long)kSMs * 16);
+  const long nb = noise_per_sample ? inner : 0;
+  if (vec) noise_bias_act_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(out, x, bias, noise, noise_weight, n_units, inner, channels, nb, alpha, scale);
+  else noise_bias_act_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(out, x, bias, noise, noise_weight, n_units, inner, channels, nb, alpha, scale);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? HAV_OK : (int)e;
+}
+
+extern "C" int hav_noise_bias_act_backward(float *grad_input, float *partials, float *noise_partials, const float *grad_out, const float *ref,
+                                           const float *noise, int batch, int channels, int64_t inner, int noise_per_sample, int splits,
+                                           float alpha, float scale, void *stream) {
+  if (batch < 0 || channels < 1 || inner < 1 || splits < 1 || splits > 64 || channels > 65535) return HAV_E_SHAPE;
+  if (batch == 0) return HAV_OK;
+  if (grad_input == nullptr || partials == nullptr || noise_partials == nullptr || grad_out == nullptr || ref == nullptr || noise == nullptr)
+    return HAV_E_NULL;
+  const int64_t total = (int64_t)batch * inner;
+  int64_t per = (total + splits - 1) / splits;
+  per = (per + 3) / 4 * 4;
+  const bool vec = (inner % 4 == 0) && (((uintptr_t)grad_input | (uintptr_t)grad_out | (uintptr_t)ref | (uintptr_t)noise) & 15) == 0;
+  dim3 grid(splits, channels);
+  const long nb = noise_per_sample ? inner : 0;
+  if (vec) bias_act_backward_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(grad_input, partials, grad_out, ref, batch, channels, inner, per, alpha, scale, noise, nb, noise_partials);
+  else bias_act_backward_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(grad_input, partials, grad_out, ref, batch, channels, inner, per, alpha, scale, noise, nb, noise_partials);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? HAV_OK : (int)e;
 }

@@ -22,6 +22,7 @@ import torch.nn.functional as F
 
 from . import conv as hconv
 from .op import fused_leaky_relu
+from .op.fused_act import noise_leaky_relu
 
 _NATIVE = [True]
 
@@ -102,8 +103,7 @@ def styled_conv(m, x, style, noise=None):
     out = mod_conv(m.conv, x, style)
     if noise is None:
         noise = out.new_empty(out.shape[0], 1, out.shape[2], out.shape[3]).normal_()
-    out = out + m.noise.weight * noise
-    return fused_leaky_relu(out, m.activate.bias)
+    return noise_leaky_relu(out, noise, m.noise.weight, m.activate.bias)      # one launch; one backward pass for all three gradients
 
 
 def to_rgb(m, x, style, skip=None):

@@ -100,6 +100,16 @@ int hav_bias_act_backward_splits(int batch, int channels, int64_t inner);
 int hav_bias_act_backward(float *grad_input, float *partials, const float *grad_out, const float *ref, int batch, int channels,
                           int64_t inner, int splits, float alpha, float scale, void *stream);
 
+/* StyledConv's tail in one pass (model/styleUnet.py:596-598 = NoiseInjection :300-310 followed by FusedLeakyReLU): for x [batch,
+ * channels, inner] and noise [batch or 1, 1, inner],  out = lrelu(x + *noise_weight * noise + bias[c], alpha) * scale.  noise_weight
+ * points to DEVICE memory (it is a parameter).  Backward: grad_input and partials as hav_bias_act_backward, plus
+ * noise_partials[s, c] = sum(grad_input * noise) over the split: grad of the noise weight = sum over (s, c). */
+int hav_noise_bias_act(float *out, const float *x, const float *bias, const float *noise, const float *noise_weight, int batch, int channels,
+                       int64_t inner, int noise_per_sample, float alpha, float scale, void *stream);
+int hav_noise_bias_act_backward(float *grad_input, float *partials, float *noise_partials, const float *grad_out, const float *ref,
+                                const float *noise, int batch, int channels, int64_t inner, int noise_per_sample, int splits, float alpha,
+                                float scale, void *stream);
+
 /* upfirdn2d on channels-last fp16 tensors (HAV_LAYOUT_NHWC_F16: x [B,H,W,C] -> out [B,Ho,Wo,C], C % 8 == 0), square up / down
  * factors, with the tail of StyledConv fused in (model/styleUnet.py:593-599 after the blur of :264-277):
  *   out = act( fir(x) + noise_weight * noise + bias[c] ),  act 0: none, 1: leaky-relu(0.2) * sqrt(2); noise / bias may be NULL. */

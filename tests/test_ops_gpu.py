@@ -103,6 +103,29 @@ def test_fused_leaky_relu_backward_one_pass(shape):
     assert torch.equal(gx, two_launch)
 
 
+@pytest.mark.parametrize("shape,per_sample", [((2, 6, 5, 5), False), ((4, 512, 16, 16), False), ((2, 64, 33, 33), True), ((1, 128, 64, 64), False)])
+def test_noise_leaky_relu_matches_unfused_formulation(shape, per_sample):
+    """StyledConv's tail in one launch (hav_noise_bias_act) and its one-pass backward (grad_x, grad_bias, grad of the noise weight)
+    against the reference formulation fused_leaky_relu(x + weight * noise, bias) differentiated by torch (styleUnet.py:300-310, 596-598)."""
+    from havatar_b200.op.fused_act import noise_leaky_relu
+
+    torch.manual_seed(2)
+    x = torch.randn(*shape, device="cuda", requires_grad=True)
+    b = torch.randn(shape[1], device="cuda", requires_grad=True)
+    w = torch.full((1,), 0.37, device="cuda", requires_grad=True)
+    noise = torch.randn(shape[0] if per_sample else 1, 1, shape[2], shape[3], device="cuda")
+    y = noise_leaky_relu(x, noise, w, b)
+    yr = torch.nn.functional.leaky_relu(x + w * noise + b.view(1, -1, 1, 1), 0.2) * 2 ** 0.5
+    assert torch.allclose(y, yr, atol=1e-6, rtol=1e-6)
+    go = torch.randn_like(y)
+    gx, gw, gb = torch.autograd.grad(y, (x, w, b), go)
+    gxr, gwr, gbr = torch.autograd.grad(yr, (x, w, b), go)
+    n = x.numel() // shape[1]
+    assert torch.allclose(gx, gxr, atol=1e-6)
+    assert torch.allclose(gb, gbr, atol=2e-6 * max(1.0, n ** 0.5), rtol=1e-5)
+    assert torch.allclose(gw, gwr, atol=2e-6 * max(1.0, x.numel() ** 0.5), rtol=1e-4)
+
+
 def test_upfirdn2d_first_and_second_order_grads():
     torch.manual_seed(0)
     k = _t(ufd_kernel(np, [1, 3, 3, 1], 1.0))
