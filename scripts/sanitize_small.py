@@ -54,3 +54,34 @@ y = op.fused_leaky_relu(torch.randn(2, 5, 7, 3, device="cuda"), torch.randn(5, d
 rays = render.get_rays(9, 11, (700., 690., 0.5, 0.5), np.eye(4)[:3], 2.4, 5.0)
 torch.cuda.synchronize()
 print("ok")
+# end of round 2: TMA-tiled channels-last blur (ragged tiles, out-of-bounds fill), cluster split-K convolutions (uneven split,
+# transposed form, channels-last), the style plan, the one-pass activation backward and the fused noise tail
+xcl = torch.randn(2, 19, 35, 128, device="cuda").half()
+for pad in ((1, 1), (2, 2), (2, 1)):
+    for kk in (k, torch.randn(4, 4, device="cuda")):
+        y = conv.upfirdn2d_cl(xcl, kk, pad=pad, noise=torch.randn(2, 1, 19 + sum(pad) - 3, 35 + sum(pad) - 3, device="cuda"),
+                              noise_weight=0.2, bias=torch.randn(128, device="cuda"), act=True)
+torch.cuda.synchronize()
+print("blur cl tma", tuple(y.shape), float(y.float().abs().mean()))
+for (B, cin, cout, H, ks, up, down) in ((1, 512, 512, 16, 3, 1, 1), (2, 320, 128, 8, 3, 1, 1), (1, 512, 512, 8, 3, 2, 1), (1, 1024, 512, 17, 3, 1, 2),
+                                        (1, 512, 12, 32, 1, 1, 1)):
+    xx = torch.randn(B, H, H, cin, device="cuda").half()
+    pw = conv.pack_weights(torch.randn(cout, cin, ks, ks, device="cuda"), 1 / math.sqrt(cin * ks * ks), up=up)
+    y = conv.conv2d(xx, pw, in_scale=torch.rand(B, cin, device="cuda"), out_scale=torch.rand(B, cout, device="cuda"),
+                    bias=torch.randn(cout, device="cuda"), act=True, up=up, down=down, out_cl=cout % 8 == 0)
+    torch.cuda.synchronize()
+    print("conv split-K", cin, cout, H, up, down, tuple(y.shape), float(y.float().abs().mean()))
+from havatar_b200 import styleunet as su
+net = su.SWGAN_unet(inp_size=32, inp_ch=16, out_ch=3, out_size=64, style_dim=64, n_mlp=2, middle_size=8).cuda().eval()
+with torch.no_grad():
+    img = net([torch.randn(2, 64, device="cuda")], torch.randn(2, 16, 32, 32, device="cuda"), noise=net.make_noise("cuda"))
+torch.cuda.synchronize()
+print("style plan + unet", tuple(img.shape), float(img.abs().mean()))
+from havatar_b200.op.fused_act import noise_leaky_relu
+for shp in ((2, 6, 5, 5), (3, 40, 16, 16)):
+    xg = torch.randn(*shp, device="cuda", requires_grad=True)
+    bg = torch.randn(shp[1], device="cuda", requires_grad=True)
+    wg = torch.full((1,), 0.3, device="cuda", requires_grad=True)
+    (op.fused_leaky_relu(xg, bg).sum() + noise_leaky_relu(xg, torch.randn(1, 1, shp[2], shp[3], device="cuda"), wg, bg).sum()).backward()
+torch.cuda.synchronize()
+print("act backward ok", float(bg.grad.abs().mean()), float(wg.grad))
