@@ -25,6 +25,10 @@
 // writes the partial tile to its own shared memory, and after a cluster barrier CTA r sums column slice r of all partial
 // tiles through distributed shared memory, applies the fused tail and stores -- no global workspace, no atomics, a fixed
 // summation order.
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "tc_common.cuh"
 
 namespace hav {
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
   const uint32_t smem_base = smem_u32(smem);
   const int kSmBar = P.ring_bytes + kOffBar, kSmA = P.ring_bytes + kOffA, kBStages = P.b_stages;
   const uint32_t bar_bfull = smem_base + kSmBar, bar_bfree = bar_bfull + kBStagesMax * 8, bar_afree = bar_bfree + kBStagesMax * 8,
-                 bar_afull = bar_afree + 16, bar_acc = bar_afull + 16;
+                 bar_afull = bar_afree + 16, bar_acc = bar_afull + 16, bar_tmem = bar_acc + 32;    // tmem slot sits between them
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kSmBar + 304);
   float *sscale = reinterpret_cast<float *>(smem + P.ring_bytes + kOffScale);   // [2][64] modulation of the staged channel block
   float *epi = reinterpret_cast<float *>(smem + P.ring_bytes + kOffEpi);        // [n_tile] out_scale | [n_tile] bias
@@ -229,13 +233,9 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
   const uint32_t b_bytes = (uint32_t)P.n_tile * kCinBlk * 2;     // = ring slot size
 
   HAV_CONV_STAMP(0, tid == 0);
-  if (warp_u == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + kSmBar + 304), "r"(P.tmem_cols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
   if (tid == 32) {
     for (int i = 0; i < kBStages; ++i) mbar_init(bar_bfull + i * 8, 1), mbar_init(bar_bfree + i * 8, 1);
-    mbar_init(bar_afree, 1), mbar_init(bar_afree + 8, 1), mbar_init(bar_acc, 1);
+    mbar_init(bar_afree, 1), mbar_init(bar_afree + 8, 1), mbar_init(bar_acc, 1), mbar_init(bar_tmem, 1);
     mbar_init(bar_afull, kStageThreads), mbar_init(bar_afull + 8, kStageThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -244,12 +244,10 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
     epi[j] = (P.out_scale != nullptr && co < P.Cout) ? __ldg(P.out_scale + (size_t)(blockIdx.x / (P.tiles_x * P.tiles_y)) * P.Cout + co) : 1.0f;
     epi[P.n_tile + j] = (P.bias != nullptr && co < P.Cout) ? __ldg(P.bias + co) : 0.0f;
   }
-  tc_fence_before();
   __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_acc = *tmem_slot;
   HAV_CONV_STAMP(1, tid == 0);
   const uint8_t *wsrc = P.wpack + ((size_t)nt * P.kblocks + kb_begin) * taps * b_bytes;
+  uint32_t tmem_acc = 0;
 
   if (warp_u == kStageThreads / 32) {
     // ================= control warp =================
@@ -258,6 +256,18 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
         mbar_expect_tx(bar_bfull + i * 8, b_bytes);
         bulk_g2s(smem_base + kSmB + i * b_bytes, wsrc + (size_t)i * b_bytes, b_bytes, bar_bfull + i * 8);
       }
+    }
+    __syncwarp();
+    // the accumulator columns are allocated here, off the staging warps' path (they need the address only for the epilogue and
+    // pick it up through bar_tmem); the first weight slices are already in flight
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + kSmBar + 304), "r"(P.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    tc_fence_before();
+    __syncwarp();
+    tc_fence_after();
+    tmem_acc = *tmem_slot;
+    if (elect_one()) {
+      mbar_arrive_conv(bar_tmem);
       const uint32_t idesc = instr_desc(P.n_tile, kBF16);
       // ring position of the current step / of the previous step, kept incrementally (the ring depth is a launch parameter)
       int slot = 0, sphase = 0, ps = 0, pphase = 0, step = 0;
@@ -387,6 +397,9 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
     }
     // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., column half w/4.  Row m = tile position (vy0 + m/8, vx0 + m%8);
     //      polyphase: accumulator block ph = 2a+b holds output (2i+a, 2j+b)
+    mbar_wait_spin(bar_tmem, 0);
+    tc_fence_after();
+    tmem_acc = *tmem_slot;
     if (my_kblocks > 0) {
       mbar_wait_spin(bar_acc, 0);
       tc_fence_after();
@@ -494,7 +507,7 @@ __global__ void __launch_bounds__(kThreadsV2) conv_tc_kernel(const ConvDev P) {
   HAV_CONV_STAMP(9, tid == 0);
   tc_fence_before();
   __syncthreads();
-  if (warp_u == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(P.tmem_cols));
+  if (warp_u == kStageThreads / 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(P.tmem_cols));
   HAV_CONV_STAMP(10, tid == 0);
 }
 
@@ -603,43 +616,76 @@ extern "C" int hav_conv2d_forward(const hav_conv_args *a, void *stream) {
   const long sp_tiles = (long)a->batch * P.tiles_x * P.tiles_y;
   if (sp_tiles > 2147483647L || P.n_tiles > 65535) return HAV_E_SHAPE;
   // split-K over a cluster when the layer has many channel blocks and too few output tiles to occupy the chip
-  P.ksplit = 1;
+  const long ctas = sp_tiles * P.n_tiles;
+  const int n_cols = (a->up == 2 ? 4 : 1) * P.n_tile;
+  int ks_first = 1;
   {
-    static const bool no_split = getenv("HAV_CONV_NO_SPLITK") != nullptr;      // A/B aid
-    const long ctas = sp_tiles * P.n_tiles;
-    const int n_cols = (a->up == 2 ? 4 : 1) * P.n_tile;
+    static const bool no_split = getenv("HAV_CONV_NO_SPLITK") != nullptr;      // A/B aids
+    static const int max_split = getenv("HAV_CONV_MAX_SPLIT") ? atoi(getenv("HAV_CONV_MAX_SPLIT")) : 8;
     if (!no_split && !dn && P.kblocks >= 2 && ctas * 2 <= 148) {
-      int ks = 8;        // the cluster's CTAs take one SM each (the partial tile needs the shared memory): stay within one wave
+      int ks = max_split < 8 ? (max_split < 1 ? 1 : max_split) : 8;
       while (ks > 1 && (ks > P.kblocks || ctas * ks > 148 || n_cols % (8 * ks) != 0)) ks >>= 1;
-      P.ksplit = ks;
+      ks_first = ks;
     }
   }
-  dim3 grid((unsigned)sp_tiles, P.n_tiles, P.ksplit);
-  cudaError_t e;
-  {
-    // weight ring: 64 KB keeps two CTAs per SM; a launch of at most one CTA per SM takes 128 KB (the ring's depth is what
-    // hides the L2 latency of the weight stream when a single CTA owns the SM)
-    const long total_ctas = sp_tiles * P.n_tiles * P.ksplit;
+  int smem_bytes = 0;
+  // ring geometry and shared-memory size for a given split
+  auto geometry = [&](int ks) -> bool {
+    P.ksplit = ks;
+    // weight ring: 64 KB keeps two CTAs per SM; a launch of at most one CTA per SM takes 128 KB
+    const long total_ctas = ctas * ks;
     const int slot = P.n_tile * conv::kCinBlk * 2;
     static const int deep_max = getenv("HAV_CONV_DEEP_MAX_CTAS") ? atoi(getenv("HAV_CONV_DEEP_MAX_CTAS")) : 148;   // A/B aid
-    const int budget = (!dn && total_ctas <= deep_max) ? conv::kBRingBytesDeep : conv::kBRingBytes;
-    int budget_eff = budget;
-    if (P.ksplit > 1) {     // the partial-tile dump shares the 227 KB with the ring
-      const int room = 227 * 1024 - conv::kOffDump - (a->up == 2 ? 4 : 1) * P.n_tile * 128 * 4;
-      if (room < budget_eff) budget_eff = room;
+    int budget = (!dn && total_ctas <= deep_max) ? conv::kBRingBytesDeep : conv::kBRingBytes;
+    if (ks > 1) {     // the partial-tile dump shares the 227 KB with the ring
+      const int room = 227 * 1024 - conv::kOffDump - n_cols * 128 * 4;
+      if (room < budget) budget = room;
     }
-    P.b_stages = budget_eff / slot < conv::kBStagesMax ? budget_eff / slot : conv::kBStagesMax;
-    if (P.b_stages < 2) return HAV_E_SHAPE;
+    P.b_stages = budget / slot < conv::kBStagesMax ? budget / slot : conv::kBStagesMax;
+    if (P.b_stages < 2) return false;
     P.ring_bytes = P.b_stages * slot;
-  }
-  int smem_bytes = P.ring_bytes + (dn ? conv::kSmemTailDN : conv::kSmemTail);
-  if (P.ksplit > 1) {
-    const int need = P.ring_bytes + conv::kOffDump + (a->up == 2 ? 4 : 1) * P.n_tile * 128 * 4;    // partial-tile dump
-    if (need > smem_bytes) smem_bytes = need;
-  }
+    smem_bytes = P.ring_bytes + (dn ? conv::kSmemTailDN : conv::kSmemTail);
+    if (ks > 1) {
+      const int need = P.ring_bytes + conv::kOffDump + n_cols * 128 * 4;    // partial-tile dump
+      if (need > smem_bytes) smem_bytes = need;
+    }
+    return true;
+  };
+  cudaError_t e;
   auto launch = [&](auto kern) -> cudaError_t {
-    cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (er != cudaSuccess) return er;
+    // every cluster of a split launch must be resident at once (a second wave of clusters would double the layer's time):
+    // halve the split until the device can hold them (clusters are placed inside one GPC, so this is less than SMs / size)
+    int ks = ks_first;
+    for (;; ks >>= 1) {
+      if (!geometry(ks)) return cudaErrorInvalidValue;
+      cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+      if (er != cudaSuccess) return er;
+      if (ks == 1) break;
+      static std::mutex mu;
+      static std::map<std::tuple<const void *, int, int, int>, int> cache;      // (kernel, device, split, smem) -> resident clusters
+      int dev = 0;
+      cudaGetDevice(&dev);
+      const auto key = std::make_tuple((const void *)kern, dev, ks, smem_bytes);
+      int resident = -1;
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) resident = it->second;
+      }
+      if (resident < 0) {
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3(1, 1, ks), q.blockDim = dim3(conv::kThreadsV2), q.dynamicSmemBytes = smem_bytes;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = 1, qa[0].val.clusterDim.y = 1, qa[0].val.clusterDim.z = ks;
+        q.attrs = qa, q.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&resident, kern, &q) != cudaSuccess) resident = 0, (void)cudaGetLastError();
+        std::lock_guard<std::mutex> lk(mu);
+        cache[key] = resident;
+      }
+      if (ctas <= resident) break;
+    }
+    dim3 grid((unsigned)sp_tiles, P.n_tiles, P.ksplit);
     if (P.ksplit == 1) {
       kern<<<grid, conv::kThreadsV2, smem_bytes, (cudaStream_t)stream>>>(P);
       return cudaGetLastError();
