@@ -177,9 +177,13 @@ class GradSync:
     `.grad` of every parameter is a view into its bucket and must stay one: use `sync.zero_grad()` (one memset per bucket)
     instead of `optimizer.zero_grad()` (whose default set_to_none=True would drop the views)."""
 
-    def __init__(self, params, group=None, bucket_bytes=64 << 20, average=True, layout=None):
+    def __init__(self, params, group=None, bucket_bytes=None, average=True, layout=None):
         """layout: a FlatLayout that already owns the gradient views (buckets become contiguous slices of its flat gradient
         buffer); None allocates per-bucket buffers here."""
+        if bucket_bytes is None:      # 64 MiB unless HAV_GRAD_BUCKET_MB says otherwise (a tuning aid)
+            import os
+
+            bucket_bytes = int(os.environ.get("HAV_GRAD_BUCKET_MB", "64")) << 20
         self.group = group
         self.layout = layout
         if layout is not None:
