@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhavatar_b200.so")
 
-HAV_ABI_VERSION = 2
+HAV_ABI_VERSION = 3
 PREC_FP32, PREC_BF16, PREC_FP16, PREC_FP16X3 = 0, 1, 2, 3
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16, "fp16x3": PREC_FP16X3}
 
@@ -64,6 +64,7 @@ class ConvArgs(C.Structure):
         ("act", C.c_int32), ("noise_per_sample", C.c_int32), ("noise_weight", C.c_float),
         ("in_layout", C.c_int32), ("out_layout", C.c_int32),
         ("x", _fp), ("wpack", _fp), ("in_scale", _fp), ("out_scale", _fp), ("noise", _fp), ("bias", _fp), ("out", _fp),
+        ("residual", _fp),
     ]
 
 

@@ -107,8 +107,10 @@ def to_nchw(t):
     return t.permute(0, 3, 1, 2).float().contiguous() if is_cl(t) else t
 
 
-def conv2d(x, packed, in_scale=None, out_scale=None, noise=None, noise_weight=0.0, bias=None, act=False, up=1, down=1, out_cl=False):
-    """out = act(conv(x * in_scale[:, :, None, None], W) * out_scale[:, :, None, None] + noise_weight * noise + bias).
+def conv2d(x, packed, in_scale=None, out_scale=None, noise=None, noise_weight=0.0, bias=None, act=False, up=1, down=1, out_cl=False,
+           residual=None):
+    """out = act(conv(x * in_scale[:, :, None, None], W) * out_scale[:, :, None, None] + noise_weight * noise + bias) [+ residual].
+    residual: a tensor of the output's shape and layout, added after the activation in the same launch.
     up=2: conv_transpose2d(stride 2, pad 0) (pack the weight with up=2); down=2: stride 2, pad 0; else pad k//2.
     x is NCHW float32, or channels-last float16 [B,H,W,C] (the internal hand-over layout); out_cl selects the output layout."""
     L = _lib.lib()
@@ -166,6 +168,12 @@ def conv2d(x, packed, in_scale=None, out_scale=None, noise=None, noise_weight=0.
     else:
         out = torch.empty((B, packed.cout, Ho, Wo), dtype=torch.float32, device=x.device)
     a.out = C.c_void_p(out.data_ptr())
+    if residual is not None:
+        if residual.shape != out.shape or residual.dtype != out.dtype or residual.device != out.device:
+            raise _lib.HavError("residual must have the output's shape %s, dtype and device" % (tuple(out.shape),))
+        residual = residual.detach().contiguous()
+        keep.append(residual)
+        a.residual = C.c_void_p(residual.data_ptr())
     with torch.cuda.device(x.device):
         st = torch.cuda.current_stream(x.device).cuda_stream
         _lib.check(L.hav_conv2d_forward(C.byref(a), C.c_void_p(st)), "hav_conv2d_forward")

@@ -64,6 +64,7 @@ struct ConvDev {
   const float *x, *in_scale, *out_scale, *noise, *bias;
   const uint8_t *wpack;
   float *out;
+  const float *residual;   // out's shape and layout, added after the activation (or nullptr)
   float noise_weight;
   int noise_bstride;   // 0 = one noise image broadcast over the batch
 };
@@ -169,15 +170,26 @@ __device__ __forceinline__ void conv_tail_store8(const ConvDev &P, const float *
   if (OUTCL) {
     // channels-last fp16: 8 channels of this pixel = 16 contiguous bytes (Cout % 8 == 0 is checked on the host)
     if (co0 + 8 <= P.Cout) {
-      uint16_t *oc = reinterpret_cast<uint16_t *>(P.out) + (((size_t)b * P.Ho + oy) * P.Wo + ox) * P.Cout + co0;
+      const size_t off = (((size_t)b * P.Ho + oy) * P.Wo + ox) * P.Cout + co0;
+      if (P.residual != nullptr) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(P.residual) + off));
+        const __half2 *rh = reinterpret_cast<const __half2 *>(&r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(rh[j]);
+          v[2 * j] += f.x, v[2 * j + 1] += f.y;
+        }
+      }
+      uint16_t *oc = reinterpret_cast<uint16_t *>(P.out) + off;
       *reinterpret_cast<uint4 *>(oc) = make_uint4(pack2<false>(v[0], v[1]), pack2<false>(v[2], v[3]), pack2<false>(v[4], v[5]), pack2<false>(v[6], v[7]));
     }
   } else {
     const size_t plane = (size_t)P.Ho * P.Wo;
-    float *ob = P.out + ((size_t)b * P.Cout) * plane + (size_t)oy * P.Wo + ox;
+    const size_t off = ((size_t)b * P.Cout) * plane + (size_t)oy * P.Wo + ox;
+    float *ob = P.out + off;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      if (co0 + j < P.Cout) ob[(size_t)(co0 + j) * plane] = v[j];
+      if (co0 + j < P.Cout) ob[(size_t)(co0 + j) * plane] = v[j] + (P.residual != nullptr ? __ldg(P.residual + off + (size_t)(co0 + j) * plane) : 0.0f);
   }
 }
 
@@ -612,6 +624,7 @@ extern "C" int hav_conv2d_forward(const hav_conv_args *a, void *stream) {
   P.tiles_x = (vw + conv::kTileW - 1) / conv::kTileW, P.tiles_y = (vh + conv::kTileH - 1) / conv::kTileH;
   P.x = (const float *)a->x, P.in_scale = a->in_scale, P.out_scale = a->out_scale, P.noise = a->noise, P.bias = a->bias;
   P.wpack = (const uint8_t *)a->wpack, P.out = (float *)a->out, P.noise_weight = a->noise_weight;
+  P.residual = (const float *)a->residual;
   P.noise_bstride = a->noise_per_sample ? P.Ho * P.Wo : 0;
   const long sp_tiles = (long)a->batch * P.tiles_x * P.tiles_y;
   if (sp_tiles > 2147483647L || P.n_tiles > 65535) return HAV_E_SHAPE;

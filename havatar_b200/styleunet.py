@@ -145,9 +145,10 @@ class EqualConv2d(nn.Module):
         self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
         self._cache = _PackCache()
 
-    def run(self, x, bias=None, act=False, out_cl=False):
+    def run(self, x, bias=None, act=False, out_cl=False, residual=None):
         b = bias if bias is not None else self.bias
-        return hconv.conv2d(x, self._cache.get(self.weight, self.scale, False), bias=b, act=act, down=self.stride, out_cl=out_cl)
+        return hconv.conv2d(x, self._cache.get(self.weight, self.scale, False), bias=b, act=act, down=self.stride, out_cl=out_cl,
+                            residual=residual)
 
     def forward(self, x):
         return self.run(x)
@@ -181,13 +182,13 @@ class ConvLayer(nn.Sequential):
         super().__init__(*layers)
         self.activate = activate
 
-    def forward(self, x, out_cl=False):
+    def forward(self, x, out_cl=False, residual=None):
         mods = list(self)
         if isinstance(mods[0], Blur):
             x = mods[0](x)
             mods = mods[1:]
         act_bias = mods[1].bias if self.activate else None
-        return mods[0].run(x, bias=act_bias, act=self.activate, out_cl=out_cl)
+        return mods[0].run(x, bias=act_bias, act=self.activate, out_cl=out_cl, residual=residual)
 
 
 class EqualLinear(nn.Module):
@@ -241,16 +242,18 @@ class ModulatedConv2d(nn.Module):
         self.fused = fused
         self._cache = _PackCache()
 
-    def run(self, x, style, noise=None, noise_weight=0.0, bias=None, act=False, out_cl=False, sd=None):
+    def run(self, x, style, noise=None, noise_weight=0.0, bias=None, act=False, out_cl=False, sd=None, residual=None):
         if sd is not None:          # modulation / demodulation of the whole network computed up front (_StylePlan)
             s, d = sd
         else:
             s = self.modulation(style).contiguous()
             d = hconv.modconv_demod(self.weight.detach()[0], s, self.scale, self.eps) if self.demodulate else None
         packed = self._cache.get(self.weight, self.scale, self.upsample)
+        if residual is not None and self.upsample:
+            raise hconv._lib.HavError("a fused residual is only available on the non-upsampling convolution")
         if not self.upsample:
             return hconv.conv2d(x, packed, in_scale=s, out_scale=d, noise=noise, noise_weight=noise_weight, bias=bias, act=act,
-                                out_cl=out_cl)
+                                out_cl=out_cl, residual=residual)
         # convT stride 2 (polyphase) -> 4x4 blur (:264-277); both in channels-last fp16, the StyledConv tail rides on the blur
         y = hconv.conv2d(x, packed, in_scale=s, out_scale=d, up=2, out_cl=True)
         y = self.blur(y, noise=noise, noise_weight=noise_weight, bias=bias, act=act)
@@ -337,11 +340,9 @@ class ToRGB(nn.Module):
         self.bias = nn.Parameter(torch.zeros(1, self.out_channel, 1, 1))
 
     def forward(self, x, style, skip=None, sd=None):
-        out = self.conv.run(x, style, bias=self.bias.view(-1), sd=sd)
-        if skip is not None:
+        if skip is not None:          # `out + skip` (:625-626) rides on the conv's epilogue
             skip = self.dwt(self.upsample(self.iwt(skip))) if self.use_wt else self.upsample(skip)
-            out = out + skip
-        return out
+        return self.conv.run(x, style, bias=self.bias.view(-1), sd=sd, residual=skip)
 
 
 class _StylePlan:
@@ -484,10 +485,10 @@ class FromRGB(nn.Module):
     def forward(self, x, skip=None, out_cl=False):
         if self.downsample:
             x = self.dwt(self.downsample(self.iwt(x))) if self.use_wt else self.downsample(x)
-        out = self.conv(x, out_cl=out_cl or (skip is not None and hconv.is_cl(skip)))
-        if skip is not None:
-            out = out + skip
-        return x, out
+        cl = out_cl or (skip is not None and hconv.is_cl(skip))
+        if skip is not None and hconv.is_cl(skip) != cl:
+            return x, self.conv(x, out_cl=cl) + skip
+        return x, self.conv(x, out_cl=cl, residual=skip)          # `out + skip` (:464-465) rides on the conv's epilogue
 
 
 _CHANNELS = lambda m: {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * m, 128: 128 * m, 256: 64 * m, 512: 32 * m, 1024: 16 * m}

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define HAV_ABI_VERSION 2
+#define HAV_ABI_VERSION 3
 
 /* argument errors (negative); positive return values are cudaError_t */
 #define HAV_OK 0
@@ -272,6 +272,8 @@ typedef struct hav_conv_args {
   const float *noise;       /* or NULL */
   const float *bias;        /* [Cout] or NULL */
   void *out;
+  const void *residual;     /* NULL, or a tensor of out's shape and layout added AFTER the activation: out = act(...) + residual
+                               (FromRGB's `out + skip`, model/styleUnet.py:464-465; ToRGB's, :625-626) */
 } hav_conv_args;
 
 uint64_t hav_conv_wpack_bytes(int cout, int cin, int ksize, int up);

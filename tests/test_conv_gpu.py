@@ -204,3 +204,27 @@ def test_cluster_split_k_layers(B, Cin, Cout, H, k, up, down):
         assert rel_err(conv.to_nchw(got_cl), ref) < 1e-2
         # the two layouts run the same MMAs in the same order on operands that agree to fp16 rounding
         assert rel_err(conv.conv2d(xcl, pw, out_cl=False, **kw), ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,k", [(2, 64, 128, 24, 1), (1, 512, 512, 16, 3), (1, 128, 12, 40, 1)])
+def test_residual_added_in_the_epilogue(B, Cin, Cout, H, k):
+    """hav_conv_args.residual: out = act(conv + bias) + residual in one launch (FromRGB / ToRGB skip additions), both layouts, with
+    and without cluster split-K."""
+    torch.manual_seed(8)
+    x = torch.randn(B, Cin, H, H, device="cuda")
+    w = torch.randn(Cout, Cin, k, k, device="cuda")
+    bias = torch.randn(Cout, device="cuda")
+    res = torch.randn(B, Cout, H, H, device="cuda")
+    scale = 1 / math.sqrt(Cin * k * k)
+    ref = F.leaky_relu(F.conv2d(x, w * scale, padding=k // 2) + bias.view(1, -1, 1, 1), 0.2) * math.sqrt(2) + res
+    pw = conv.pack_weights(w, scale)
+    got = conv.conv2d(x, pw, bias=bias, act=True, residual=res)
+    assert rel_err(got, ref) < 1e-2
+    assert torch.equal(got, conv.conv2d(x, pw, bias=bias, act=True) + res)          # fp32 NCHW: the same addition, bit for bit
+    if Cout % 8 == 0:
+        xcl, rcl = x.permute(0, 2, 3, 1).contiguous().half(), res.permute(0, 2, 3, 1).contiguous().half()
+        got_cl = conv.conv2d(xcl, pw, bias=bias, act=True, out_cl=True, residual=rcl)
+        assert rel_err(conv.to_nchw(got_cl), F.leaky_relu(F.conv2d(x, w * scale, padding=k // 2) + bias.view(1, -1, 1, 1), 0.2) * math.sqrt(2)
+                       + rcl.permute(0, 3, 1, 2).float()) < 1e-2
+    with pytest.raises(Exception):
+        conv.conv2d(x, pw, bias=bias, residual=res[:, :, 1:])
