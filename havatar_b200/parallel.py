@@ -9,7 +9,7 @@ B200-side equivalent, written for NVLink 5 / NVSwitch:
   * buckets are filled in reverse parameter order (the order backward produces gradients); a post-accumulate hook counts a
     bucket's parameters down and issues its all-reduce asynchronously the moment the last one lands, so the exchange of the
     early buckets overlaps the rest of backward (NCCL runs it on its own stream);
-  * collectives are issued strictly in bucket order on every rank (a ready bucket waits for its predecessors), so ranks can
+  * collectives are issued in the order the buckets complete, which is the same on every rank (same autograd graph), so ranks can
     never disagree on the order of NCCL calls;
   * `finish()` issues what is left (parameters that received no gradient this step), waits, and divides by the world size
     (ReduceOp.AVG inside NCCL; an explicit scale on backends without it, e.g. gloo in the CPU tests).
@@ -159,11 +159,11 @@ class FlatAdam:
 
 
 class _Bucket:
-    __slots__ = ("flat", "params", "pending", "ready", "work")
+    __slots__ = ("flat", "params", "pending", "ready", "issued", "work")
 
     def __init__(self, flat, params):
         self.flat, self.params = flat, params
-        self.pending, self.ready, self.work = len(params), False, None
+        self.pending, self.ready, self.issued, self.work = len(params), False, False, None
 
 
 class GradSync:
@@ -213,6 +213,7 @@ class GradSync:
         if cur:
             self._close(cur)
         self._next = 0
+        self.issued_in_backward = 0   # buckets whose exchange started from inside backward (diagnostic)
         self.collectives = 0          # all-reduces issued since construction (bench / tests read it)
         self.bytes_per_step = sum(b.flat.numel() * b.flat.element_size() for b in self.buckets)
 
@@ -279,19 +280,24 @@ class GradSync:
         b.ready = True
 
     def _issue_ready(self):
-        while self._next < len(self.buckets) and self.buckets[self._next].ready:
-            b = self.buckets[self._next]
-            if b.work is None:
+        """Issue every bucket that is complete and not yet on its way, in the order they became complete.  Every rank runs the
+        same autograd graph through the same single-threaded engine, so that order is the same on every rank (and under a CUDA-
+        graph capture it is frozen at capture time).  A strict bucket-index order would be safe too, but one straggler in an
+        early bucket (a style MLP whose gradient is the last of its network to arrive sits in the first bucket of the reversed
+        parameter list) then holds every later bucket back until the end of backward and the whole exchange is exposed."""
+        for b in self.buckets:
+            if b.ready and not b.issued:
+                b.issued = True
                 self._issue(b)
-            self._next += 1
+                self.issued_in_backward += 1
 
     def finish(self):
         """Issue the buckets backward did not complete, wait for all of them, apply the 1/world scale where the collective
         did not, and re-arm for the next step."""
-        for b in self.buckets[self._next:]:
-            if b.work is None:
+        for b in self.buckets:
+            if not b.issued:
+                b.issued = True
                 self._issue(b)
-        self._next = len(self.buckets)
         for b in self.buckets:
             if b.work is not None:
                 b.work.wait()
@@ -302,7 +308,7 @@ class GradSync:
         if comm is not None:           # the staging stream rejoins the caller's stream (a capture must end with every fork joined)
             torch.cuda.current_stream(comm.device).wait_stream(comm)
         for b in self.buckets:
-            b.pending, b.ready = len(b.params), False
+            b.pending, b.ready, b.issued = len(b.params), False, False
             for p in b.params:       # an optimiser's zero_grad(set_to_none=True) or a grad replaced by autograd breaks the views
                 if p.grad is None or p.grad.data_ptr() < b.flat.data_ptr() or \
                         p.grad.data_ptr() >= b.flat.data_ptr() + b.flat.numel() * b.flat.element_size():

@@ -13,7 +13,12 @@ rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_S
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
-    dist.init_process_group("nccl", device_id=dev)
+    if os.environ.get("HAV_NCCL_HIGH_PRIO"):
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+    else:
+        dist.init_process_group("nccl", device_id=dev)
 stages = [int(a) for a in sys.argv[1:]] or [1, 2]
 for stage in stages:
     if stage == 1:
@@ -31,16 +36,23 @@ for stage in stages:
     if world > 1:
         dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(n_t + 1)]
     a.record()
-    for _ in range(n_t):
+    marks[0].record()
+    for i in range(n_t):
         run(batch)
+        marks[i + 1].record()
     b.record()
     torch.cuda.synchronize()
     ms = torch.tensor([a.elapsed_time(b) / n_t], dtype=torch.float64, device=dev)
+    if rank == 0 and os.environ.get("HAV_PER_ITER"):
+        print("  per iteration (rank 0):", " ".join("%.1f" % marks[i].elapsed_time(marks[i + 1]) for i in range(n_t)), flush=True)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     syncs = [g.sync for g in st.groups() if g.sync is not None]
     if rank == 0:
+        print("  buckets issued from inside backward since construction: %s of %s collectives" % (
+            [s_.issued_in_backward for s_ in syncs], [s_.collectives for s_ in syncs]), flush=True)
         print("stage %d, %d GPU(s): %.2f ms per iteration; %d buckets, %.0f MB exchanged (bucket %s MB, NCCL_MAX_NCHANNELS=%s, NCCL_ALGO=%s)" % (
             stage, world, float(ms), sum(len(s.buckets) for s in syncs), sum(s.bytes_per_step for s in syncs) / 1e6,
             os.environ.get("HAV_GRAD_BUCKET_MB", "64"), os.environ.get("NCCL_MAX_NCHANNELS", "-"), os.environ.get("NCCL_ALGO", "-")), flush=True)
