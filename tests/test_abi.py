@@ -122,3 +122,15 @@ def test_flat_layout_views_on_cpu():
     assert float(lay.flat_g.abs().sum()) > 0.0
     lay.flat_p.zero_()
     assert all(float(p.detach().abs().sum()) == 0.0 for p in net.parameters())
+
+
+def test_bias_act_backward_splits_is_a_host_function(lib):
+    """hav_bias_act_backward_splits needs no GPU: 1..64 partial sums per channel, about two CTAs per SM over all channels, never
+    more than one per 2048 elements."""
+    assert lib.hav_bias_act_backward_splits(0, 4, 16) == 0
+    assert lib.hav_bias_act_backward_splits(4, 512, 16 * 16) == 1
+    assert lib.hav_bias_act_backward_splits(1, 64, 512 * 512) == 5
+    assert lib.hav_bias_act_backward_splits(1, 3, 1024 * 1024) == 64
+    assert lib.hav_bias_act_backward_splits(2, 12, 100) == 1
+    assert lib.hav_style_plan_run(None, None, None, 1, 1, 1, None, None, None, 1, 1, 0, 1e-8, None) == -1     # NULL tensors
+    assert lib.hav_bias_act_backward(None, None, None, None, 1, 4, 16, 65, 0.2, 1.0, None) == -2               # splits > 64
