@@ -20,3 +20,14 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+def within(name, measured, limit):
+    """assert measured < limit, and -- when HAV_TEST_REPORT names a file -- append 'name measured limit' to it, so that the margins
+    of the stated tolerances can be read off a GPU run (profiles/*_tolerance_margins.txt)."""
+    measured = float(measured)
+    path = os.environ.get("HAV_TEST_REPORT")
+    if path:
+        with open(path, "a") as f:
+            f.write("%-70s measured %.3e   limit %.1e   margin %.1fx\n" % (name, measured, limit, limit / max(measured, 1e-30)))
+    assert measured < limit, (name, measured, limit)

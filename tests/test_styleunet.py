@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import within
 from havatar_b200 import styleunet
 from oracle.gen_golden import STYLEUNET_CASES, styleunet_inputs
 
@@ -63,9 +64,10 @@ def test_forward_matches_reference_golden(golden_dir, name, mode):
         assert out.shape[-1] == case["kw"]["out_size"]
         out = out[..., ::st, ::st]
     assert out.shape == ref.shape
-    # fp16 operands, fp32 accumulation, ~20 convolutions deep: 2e-2 of the output range (stated tolerance)
+    # fp16 operands, fp32 accumulation, ~20 convolutions deep: 4e-3 of the output range (stated tolerance; measured on B200
+    # 2e-4 .. 1.04e-3 over the six fixtures and both paths, profiles/r02zz_tolerance_margins.txt -- the limit was 2e-2 until then)
     err = np.abs(out - ref).max() / np.abs(ref).max()
-    assert err < 2e-2, float(err)
+    within("styleunet %s %s" % (name, mode), err, 4e-3)
 
 
 @pytest.mark.gpu

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import within
 from havatar_b200 import synth, trainer
 from oracle.gen_golden import TRAIN_GRAD_KEYS, train_step_inputs, train_step_loss, trainer_inputs
 
@@ -50,10 +51,11 @@ def test_validation_forward_matches_reference_golden(golden_dir):
     assert render.shape == (1, 67, 128, 128) and mask.shape == (1, 1, 128, 128)
     assert abs(float(lat) - float(g["latent_code_loss"])) < 1e-7
     r, m = render.cpu().numpy()[:, :, ::4, ::4], mask.cpu().numpy()[:, :, ::4, ::4]
-    # fp16 operands through two 20-conv plane generators and the radiance MLP: 3e-2 of the output range (stated)
-    assert np.abs(m - g["mask"]).max() < 3e-2, float(np.abs(m - g["mask"]).max())
+    # fp16 operands through two 20-conv plane generators and the radiance MLP: 2e-3 of the output range (stated; measured 1e-4 /
+    # 2.4e-4, profiles/r02zz_tolerance_margins.txt -- the limit was 3e-2 until then)
+    within("trainer validation mask", np.abs(m - g["mask"]).max(), 2e-3)
     err = np.abs(r - g["render"]).max() / np.abs(g["render"]).max()
-    assert err < 3e-2, float(err)
+    within("trainer validation render", err, 2e-3)
     # the frozen-volume path of inference (avatarHD_reenactment.py:144)
     net.headpose_skin_net.fix_canonical_W()
     w = net.headpose_skin_net.volume()
@@ -84,8 +86,8 @@ def test_training_step_gradients_match_reference_golden(golden_dir):
     out = net(mode="train", fidx=torch.tensor([1, 3]).cuda(), render_full_img=False, ray_batch=t(sc["ray_batch"]),
               background_prior=t(sc["background_prior"]), inv_head_T=t(sc["inv_head_T"]),
               randoms={k: t(rnd[k]) for k in ("t_rand", "u_rand", "noise_coarse", "noise_fine")}, **{k: t(v) for k, v in conds.items()})
-    assert np.abs(out[4].detach().cpu().numpy() - g["rgb_fine"]).max() < 3e-2 * np.abs(g["rgb_fine"]).max()
-    assert np.abs(out[6].detach().cpu().numpy() - g["acc_fine"]).max() < 3e-2
+    within("trainer train rgb_fine", np.abs(out[4].detach().cpu().numpy() - g["rgb_fine"]).max() / np.abs(g["rgb_fine"]).max(), 2e-3)
+    within("trainer train acc_fine", np.abs(out[6].detach().cpu().numpy() - g["acc_fine"]).max(), 2e-3)
     loss = train_step_loss(torch, out, t(target), t(mask))
     assert abs(float(loss) - float(g["loss"])) < 2e-3 * abs(float(g["loss"])), (float(loss), float(g["loss"]))
     loss.backward()
@@ -100,5 +102,7 @@ def test_training_step_gradients_match_reference_golden(golden_dir):
             assert np.abs(got).max() < 1e-6, k
             continue
         errs[k] = float(np.abs(got - ref).max() / np.abs(ref).max())
-    # 16-bit render operands (forward and backward) feeding fp32 / TF32 generator backward: 5e-2 of each tensor's range
-    assert all(e < 5e-2 for e in errs.values()), errs
+    # 16-bit render operands (forward and backward) feeding the generators' 16-bit tensor-core backward: 3e-2 of each tensor's range
+    # (measured 1e-4 .. 1.2e-2, profiles/r02zz_tolerance_margins.txt -- the limit was 5e-2 until then)
+    for k, e in errs.items():
+        within("trainer train grad " + k, e, 3e-2)
