@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import within
 from havatar_b200 import train_step
 from oracle.gen_golden import STAGE_TWO_CASE, STAGE_TWO_GRAD_KEYS, stage_two_inputs, stage_two_states, subsample
 
@@ -69,13 +70,14 @@ def test_stage_two_iteration_matches_the_reference(golden_dir):
     torch.cuda.synchronize()
     assert calls == ["d", "r1", "g", "nerf"]                 # iteration 0 regularises (i % d_reg_every == 0, train_avatarHD.py:209)
 
-    # ---- losses.  16-bit tensor-core operands through three deep networks: 2e-2 relative on O(1) losses; the R1 penalty is a
-    #      second-order quantity of ~4e-3 absolute
+    # ---- losses.  16-bit tensor-core operands through three deep networks: 2e-3 relative on O(1) losses (measured 9e-6 .. 6e-4,
+    #      profiles/r02zz_tolerance_margins.txt; the limit was 2e-2 until then); the R1 penalty is a second-order quantity of ~4e-3
+    #      absolute: 2.5e-2 relative (measured 7.6e-3)
     f = lambda k: float(out[k])
-    assert abs(f("d") - float(g["d_loss"])) < 2e-2 * abs(float(g["d_loss"])), (f("d"), float(g["d_loss"]))
-    assert abs(f("r1") - float(g["r1"])) < 5e-2 * abs(float(g["r1"])), (f("r1"), float(g["r1"]))
+    within("stage two d_loss (relative)", abs(f("d") - float(g["d_loss"])) / abs(float(g["d_loss"])), 2e-3)
+    within("stage two r1 (relative)", abs(f("r1") - float(g["r1"])) / abs(float(g["r1"])), 2.5e-2)
     for k in ("g_loss", "rgb_loss", "mask_loss", "g_nonsat", "hr_l1"):
-        assert abs(f(k) - float(g[k])) < 2e-2 * abs(float(g[k])), (k, f(k), float(g[k]))
+        within("stage two %s (relative)" % k, abs(f(k) - float(g[k])) / abs(float(g[k])), 2e-3)
     # ---- gradients.  Metric = relative L2 error and cosine against the reference's gradient (a max-norm over a tensor whose
     #      entries cancel heavily measures the noise floor of the 16-bit operands, not the agreement of the two gradients).
     #      Inputs are not identical by then: the D step sees OUR generator's fake image (1e-2-class differences), the R1 pass
