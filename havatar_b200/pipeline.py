@@ -6,6 +6,8 @@
 
 AvatarHD owns the three networks + the radiance MLP weights and a skinning-weight volume; `frame()` is one frame,
 `graphed()` returns a CUDA-graph replay of it for fixed shapes.  Inference only."""
+import os
+
 import torch
 
 from . import render as hrender
@@ -134,11 +136,17 @@ class AvatarHD(torch.nn.Module):
         o = hrender.render_rays(ray_batch, background, inv_head_T, planes, self.wvol, weights, self.num_coarse, self.num_fine,
                                 boxes=self.boxes, precision=self.precision)
         rgb = o.rgb_fine if self.num_fine > 0 else o.rgb_coarse
-        render = rgb.view(B, h, w, 67).permute(0, 3, 1, 2).contiguous()              # nerf_trainer.py:111-113
-        if self._noise is None or self._noise[0].device != render.device:
-            self._noise = self.upsampler.make_noise(render.device)
-        image = self.upsampler([style], render[:, 3:].contiguous(), noise=self._noise)   # avatarHD_reenactment.py:167
-        return image, render[:, :3]
+        maps = rgb.view(B, h, w, 67)                                                   # pixel r <-> ray r (nerf_trainer.py:111-113)
+        if self._noise is None or self._noise[0].device != maps.device:
+            self._noise = self.upsampler.make_noise(maps.device)
+        if os.environ.get("HAV_HD_NCHW"):            # A/B aid: the reference's layout all the way (two permute copies, fp32 entry layers)
+            render = maps.permute(0, 3, 1, 2).contiguous()
+            return self.upsampler([style], render[:, 3:].contiguous(), noise=self._noise), render[:, :3]
+        # the render's output IS channels-last: the 64 feature channels go to the upsampler as one fp16 [B,h,w,64] tensor (one
+        # cast kernel), whose entry layers then run on the channels-last kernels (TMA-tiled blur, 16-byte staging loads)
+        feats = maps[..., 3:].to(torch.float16).contiguous()
+        image = self.upsampler([style], feats, noise=self._noise)                      # avatarHD_reenactment.py:167
+        return image, maps[..., :3].permute(0, 3, 1, 2)
 
     def graphed(self, *example):
         return GraphedForward(lambda *a: self.frame(*a), *example)

@@ -75,6 +75,8 @@ class Downsample(nn.Module):
         self.pad = ((p + 1) // 2, p // 2)
 
     def forward(self, x):
+        if hconv.is_cl(x):          # channels-last fp16 hand-over (the condition pyramid of a channels-last condition image)
+            return hconv.upfirdn2d_cl(x, self.kernel, up=1, down=self.factor, pad=self.pad)
         return upfirdn2d(x, self.kernel, up=1, down=self.factor, pad=self.pad)
 
 

@@ -116,3 +116,20 @@ def test_style_plan_matches_per_layer_modulation():
         finally:
             su._StylePlan.run = old
         assert float((with_plan - without).abs().max()) <= 2e-3 * float(without.abs().max())
+
+
+@pytest.mark.gpu
+def test_channels_last_condition_image_matches_nchw():
+    """SWGAN_unet fed a channels-last fp16 condition image ([B,H,W,C]: what the HD frame hands over from the render) against the
+    same network on the NCHW fp32 image: the entry layers (blur, stride-2 convolution, the FromRGB pyramid) change kernels, the
+    result agrees to the fp16 rounding of the input."""
+    torch.manual_seed(5)
+    net = styleunet.SWGAN_unet(inp_size=64, inp_ch=64, out_ch=3, out_size=128, style_dim=64, n_mlp=2, middle_size=8).cuda().eval()
+    cond = torch.randn(2, 64, 64, 64, device="cuda")
+    style = torch.randn(2, 64, device="cuda")
+    noise = net.make_noise("cuda")
+    with torch.no_grad():
+        ref = net([style], cond, noise=noise)
+        got = net([style], cond.permute(0, 2, 3, 1).contiguous().half(), noise=noise)
+    assert got.shape == ref.shape
+    within("unet channels-last condition image", float((got - ref).abs().max() / ref.abs().max()), 4e-3)
